@@ -1,0 +1,225 @@
+"""Generate the golden vectors under tests/golden/ by running the UNMODIFIED reference
+(/root/reference/src, imported with imageio/matplotlib stubbed as SURVEY.md 8c describes).
+
+Run in the authoring container only (the GPU box has no /root/reference):
+    python tests/golden/make_golden.py
+The reference has no golden vectors of its own; these pin the oracle.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))          # tests/ -> fixtures
+for m in ("imageio", "matplotlib", "matplotlib.pyplot"):
+    sys.modules.setdefault(m, types.ModuleType(m))
+sys.path.insert(0, "/root/reference/src")
+
+import torch  # noqa: E402
+import cv2  # noqa: E402
+
+import fixtures as fx  # noqa: E402
+from nerf_models.ibl_nerf_renderer import raw2outputs, raw2outputs_simple, raw2outputs_depth, render_rays  # noqa: E402
+from nerf_models.ibl_nerf import IBLNeRF, run_network  # noqa: E402
+from nerf_models.positional_embedder import get_embedder  # noqa: E402
+from nerf_models.nerf_renderer_helper import sample_pdf  # noqa: E402
+from nerf_models.normal_from_depth import get_normal_from_depth_gradient_epsilon  # noqa: E402
+from nerf_models.microfacet import fresnel_schlick_roughness  # noqa: E402
+
+torch.autograd.set_detect_anomaly(False)
+torch.set_num_threads(8)
+
+
+def npz(name, **arrs):
+    out = {}
+    for k, v in arrs.items():
+        if isinstance(v, torch.Tensor):
+            v = v.detach().cpu().numpy()
+        out[k] = v
+    np.savez_compressed(os.path.join(HERE, name), **out)
+    print("wrote", name, len(out), "arrays")
+
+
+def dump_lut():
+    lut = cv2.imread("/root/reference/data/ibl_brdf_lut.png")
+    lut = cv2.cvtColor(lut, cv2.COLOR_BGR2RGB)
+    assert lut[..., 2].max() == 0
+    npz("brdf_lut_rg.npz", rg=lut[..., :2].copy())
+
+
+def g_posenc():
+    g = torch.Generator().manual_seed(21)
+    x = (torch.rand(96, 3, generator=g) * 2 - 1) * 6.0
+    e10, d10 = get_embedder(10, 0)
+    e4, d4 = get_embedder(4, 0)
+    assert (d10, d4) == (63, 27)
+    npz("posenc.npz", x=x, e10=e10(x), e4=e4(x))
+
+
+def g_sample_pdf():
+    g = torch.Generator().manual_seed(22)
+    n = 40
+    z = fx.make_sorted_z(n, 64, seed=23)
+    bins = .5 * (z[:, 1:] + z[:, :-1])
+    w = torch.rand(n, 62, generator=g) ** 4
+    w[3] = 0.0                      # all-zero weights -> uniform pdf
+    w[4, :30] = 0.0
+    w[5] = 0.0
+    w[5, 17] = 1.0                  # one spike: many denom<1e-5 bins
+    u = torch.rand(n, 128, generator=g)
+    u[0, 0] = 0.0
+    # reference cannot take u as an argument: reproduce its two u sources (det linspace, pytest numpy seed 0)
+    s_det = sample_pdf(bins, w, 128, det=True)
+    s_rand = sample_pdf(bins, w, 128, det=False, pytest=True)
+    # and the explicit-u path via the same arithmetic, run with the reference's own ops (for the bit-exact index test)
+    wp = w + 1e-5
+    pdf = wp / torch.sum(wp, -1, keepdim=True)
+    cdf = torch.cumsum(pdf, -1)
+    cdf = torch.cat([torch.zeros_like(cdf[..., :1]), cdf], -1)
+    inds = torch.searchsorted(cdf, u.contiguous(), right=True)
+    npz("sample_pdf.npz", bins=bins, weights=w, u=u, cdf=cdf, inds=inds, s_det=s_det, s_rand_pytest=s_rand)
+
+
+def g_composite():
+    n, c = 24, 18
+    for s in (64, 192):
+        raw = fx.make_raw(n, s, c, seed=30 + s)
+        raw[2, :, 0] = -1.0                  # empty ray: acc == 0 -> disp NaN
+        raw[3, :, 0] = 50.0                  # opaque at first sample
+        z = fx.make_sorted_z(n, s, seed=31 + s)
+        ro, rd = fx.make_rays(n, seed=32 + s)
+        rawp = raw.clone().requires_grad_(True)
+        q = lambda pts, vd, net: rawp
+        res = raw2outputs(ro, rd, z, z[:, :64], q, fx.STUB_NET, gamma_correct=False, approximate_radiance=False)
+        g = torch.Generator().manual_seed(33)
+        keys = ["weights", "depth_map", "acc_map", "albedo_map", "roughness_map", "irradiance_map",
+                "radiance_map", "radiance_map_1", "radiance_map_2", "radiance_map_3"]
+        cot = {k: torch.randn(res[k].shape, generator=g) for k in keys}
+        loss = sum((res[k] * cot[k]).sum() for k in keys)
+        loss.backward()
+        out = {k: res[k] for k in keys + ["disp_map"]}
+        out.update({"cot_" + k: v for k, v in cot.items()})
+        # raw2outputs_simple / raw2outputs_depth on the same raw
+        rad, crs = raw2outputs_simple(raw, z, rd)
+        dres = raw2outputs_depth(ro, rd, z, lambda p, v, f: raw[..., :1], fx.STUB_NET, 0.)
+        npz("composite_S%d.npz" % s, raw=raw, z=z, rays_o=ro, rays_d=rd, g_raw=rawp.grad,
+            simple_rad=rad, simple_c1=crs[0], simple_c2=crs[1], simple_c3=crs[2],
+            depth_only=dres["depth_map"], depth_only_w=dres["weights"], visibility=dres["visibility"], **out)
+
+
+def g_shading():
+    """raw2outputs with approximate_radiance=True over the analytic field: normal-from-depth-epsilon,
+    LUT fetch, Fresnel, reflected-ray march, mip lerp, gamma; plus d(loss)/d(raw)."""
+    n, s = 32, 64
+    lut = fx.load_lut()
+    ro, rd = fx.make_rays(n, seed=41)
+    ro = ro * 0.3
+    z = fx.make_sorted_z(n, s, seed=42)
+    near = torch.full((n, 1), fx.NEAR)
+    far = torch.full((n, 1), fx.FAR)
+    cap = {}
+
+    def q(pts, vd, net):
+        r = fx.analytic_query(pts, vd, net)
+        if vd is not None and "main" not in cap:
+            r = r.clone().requires_grad_(True)
+            cap["main"] = r
+        return r
+    for coef in ("F", "F0"):
+        cap.clear()
+        res = raw2outputs(ro, rd, z, z, q, fx.STUB_NET, brdf_lut=lut, epsilon=0.01, gamma_correct=True,
+                          approximate_radiance=True, lut_coefficient=coef,
+                          target_normal_map_for_radiance_calculation="normal_map_from_depth_gradient_epsilon",
+                          correct_depth_for_prefiltered_radiance_infer=True, near=near, far=far)
+        g = torch.Generator().manual_seed(43)
+        cot = torch.randn(n, 3, generator=g)
+        (res["color_map"] * cot).sum().backward()
+        keep = {k: v for k, v in res.items() if v is not None}
+        npz("shading_%s.npz" % coef, rays_o=ro, rays_d=rd, z=z, cot_color=cot, g_raw=cap["main"].grad, **keep)
+    nrm = get_normal_from_depth_gradient_epsilon(ro, rd, fx.analytic_query, fx.STUB_NET, z, epsilon=0.01)
+    npz("normal_eps.npz", rays_o=ro, rays_d=rd, z=z, normal=nrm)
+
+
+def build_nets():
+    torch.manual_seed(0)
+    coarse = IBLNeRF(**fx.KITCHEN_ARCH)
+    fine = IBLNeRF(**fx.KITCHEN_ARCH)
+    return coarse, fine
+
+
+def g_mlp():
+    coarse, fine = build_nets()
+    cs = fx.state_checksums(coarse)
+    fs = fx.state_checksums(fine)
+    e10, _ = get_embedder(10, 0)
+    e4, _ = get_embedder(4, 0)
+    fx.structure_(coarse, e10, seed=11)
+    fx.structure_(fine, e10, seed=12)
+    g = torch.Generator().manual_seed(51)
+    pts = (torch.rand(2, 80, 3, generator=g) * 2 - 1) * 3.0
+    vd = torch.randn(2, 3, generator=g)
+    q = lambda p, v, f: run_network(p, v, f, e10, e4, 65536)
+    for p in coarse.parameters():
+        p.grad = None
+    full = q(pts, vd, coarse)
+    sig = q(pts, None, coarse)
+    cot = torch.randn(full.shape, generator=g)
+    (full * cot).sum().backward()
+    grads = {"g_" + k.replace(".", "__"): v.grad for k, v in coarse.named_parameters()}
+    npz("mlp.npz", pts=pts, viewdirs=vd, full=full, sigma=sig, cot=cot,
+        **{"ck_c_" + k.replace(".", "__"): v for k, v in cs.items()},
+        **{"ck_f_" + k.replace(".", "__"): v for k, v in fs.items()}, **grads)
+
+
+def g_render_rays():
+    coarse, fine = build_nets()
+    e10, _ = get_embedder(10, 0)
+    e4, _ = get_embedder(4, 0)
+    fx.structure_(coarse, e10, seed=11)
+    fx.structure_(fine, e10, seed=12)
+    lut = fx.load_lut()
+    n = 40
+    ro, rd = fx.make_rays(n, seed=1)
+    tg = fx.make_targets(n)
+    q = lambda p, v, f: run_network(p, v, f, e10, e4, 65536)
+    near = torch.full((n, 1), fx.NEAR)
+    far = torch.full((n, 1), fx.FAR)
+    vdn = rd / rd.norm(dim=-1, keepdim=True)
+    rays = torch.cat([ro, rd, near, far, vdn], -1)
+    kw = dict(network_fn=coarse, network_fine=fine, network_query_fn=q, N_samples=64, N_importance=128,
+              perturb=1.0, raw_noise_std=0., pytest=True, brdf_lut=lut, epsilon=0.01, gamma_correct=True,
+              lut_coefficient="F", target_normal_map_for_radiance_calculation="normal_map_from_depth_gradient_epsilon",
+              correct_depth_for_prefiltered_radiance_infer=True, use_viewdirs=True, white_bkgd=False, lindisp=False)
+    for tag, approx in (("full", True), ("rad", False)):
+        for net in (coarse, fine):
+            for p in net.parameters():
+                p.grad = None
+        res = render_rays(rays, approximate_radiance=approx, **kw)
+        loss = fx.phase_b_loss(res, tg)
+        loss.backward()
+        gsel = {}
+        for nm, net in (("c", coarse), ("f", fine)):
+            for k, v in net.named_parameters():
+                g_ = v.grad
+                key = "g_%s_%s" % (nm, k.replace(".", "__"))
+                if g_ is None:
+                    continue
+                if g_.numel() <= 1024:
+                    gsel[key] = g_
+                gsel["n" + key] = torch.tensor([g_.double().norm().item(), g_.double().sum().item()])
+        npz("render_rays_%s.npz" % tag, rays=rays, loss=loss.detach(), **{k: v for k, v in res.items()}, **gsel)
+    # deterministic test-time render (perturb=0 -> det=True u = linspace)
+    kw2 = dict(kw)
+    kw2.update(perturb=0., pytest=False)
+    with torch.no_grad():
+        res = render_rays(rays, approximate_radiance=True, **kw2)
+    npz("render_rays_test.npz", rays=rays, **{k: v for k, v in res.items()})
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["lut", "posenc", "sample_pdf", "composite", "shading", "mlp", "render_rays"]
+    for w in which:
+        {"lut": dump_lut, "posenc": g_posenc, "sample_pdf": g_sample_pdf, "composite": g_composite,
+         "shading": g_shading, "mlp": g_mlp, "render_rays": g_render_rays}[w]()
