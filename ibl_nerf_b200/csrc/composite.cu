@@ -1,0 +1,413 @@
+// raw2outputs alpha compositing, forward and backward (north-star subsystem 4).
+// One warp per ray.  The ray's raw[S,C] tile is brought into shared memory with 16-byte cp.async
+// (fully coalesced, double buffered per warp); the transmittance scan is a warp shuffle product scan
+// with a carry across 32-sample rows; per-sample state lives in registers / shared memory only.
+#include "common.cuh"
+
+namespace ibln {
+
+constexpr int CP_WARPS = 4;
+constexpr int MAXCH = 32;
+
+__device__ __forceinline__ float head_act(float x, int sigm) { return sigm ? sigmoidf_fast(x) : fmaxf(x, 0.f); }
+__device__ __forceinline__ float head_dact(float x, float y, int sigm) { return sigm ? y * (1.f - y) : (x > 0.f ? 1.f : 0.f); }
+
+// Issue the async copy of one ray's tile (n_float floats) into smem. Falls back to scalar loads
+// when the tile is not 16-byte tileable.
+__device__ __forceinline__ void tile_load_async(float* dst, const float* __restrict__ src, int n_float, int lane, bool vec_ok) {
+  if (vec_ok) {
+    int n4 = n_float >> 2;
+    for (int i = lane; i < n4; i += 32) cp_async16(dst + 4 * i, src + 4 * i);
+  } else {
+    for (int i = lane; i < n_float; i += 32) dst[i] = src[i];
+  }
+  cp_async_commit();
+}
+
+struct RayAlpha {   // per-sample quantities of one 32-sample row
+  float alpha, om, T, w;
+};
+
+// alpha / transmittance / weight for sample i of the row, given the running carry (product of om
+// over all previous rows).  Updates carry.
+__device__ __forceinline__ RayAlpha row_alpha(float sig, float dist, bool valid, float& carry, int lane) {
+  RayAlpha r;
+  r.alpha = valid ? 1.0f - expf(-fmaxf(sig, 0.f) * dist) : 0.f;
+  r.om = valid ? (1.0f - r.alpha) + 1e-10f : 1.0f;
+  float p = r.om;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    float v = __shfl_up_sync(FULL, p, o);
+    if (lane >= o) p *= v;
+  }
+  float excl = __shfl_up_sync(FULL, p, 1);
+  r.T = carry * (lane == 0 ? 1.0f : excl);
+  r.w = r.alpha * r.T;
+  carry *= __shfl_sync(FULL, p, 31);
+  return r;
+}
+
+template <bool SIMPLE>
+__global__ void __launch_bounds__(CP_WARPS * 32)
+composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays_d,
+                     const float* __restrict__ noise, int n, int S, int C, int nc, int sigm,
+                     float* __restrict__ weights, float* __restrict__ maps, float* __restrict__ maps_srgb,
+                     float* __restrict__ pre_out) {
+  extern __shared__ __align__(16) float sm[];
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = S * C;
+  float* buf0 = sm + (size_t)warp * (2 * tile + 32);
+  float* buf1 = buf0 + tile;
+  float* s_out = buf1 + tile;   // 32 floats of per-ray results
+  const bool vec_ok = (tile % 4 == 0) && ((reinterpret_cast<uintptr_t>(raw) & 15) == 0);
+  const int stride = gridDim.x * CP_WARPS;
+  int r = blockIdx.x * CP_WARPS + warp;
+  if (r < n) tile_load_async(buf0, raw + (int64_t)r * tile, tile, lane, vec_ok);
+  int it = 0;
+  for (; r < n; r += stride, ++it) {
+    float* cur = (it & 1) ? buf1 : buf0;
+    float* nxt = (it & 1) ? buf0 : buf1;
+    int rn = r + stride;
+    if (rn < n) { tile_load_async(nxt, raw + (int64_t)rn * tile, tile, lane, vec_ok); cp_async_wait<1>(); }
+    else cp_async_wait<0>();
+    __syncwarp();
+
+    float dx = rays_d[3 * r], dy = rays_d[3 * r + 1], dz = rays_d[3 * r + 2];
+    float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
+    const float* zr = z + (int64_t)r * S;
+    float carry = 1.0f;
+    float a_depth = 0.f, a_acc = 0.f, a_rough = 0.f, a_irr = 0.f;
+    float a_col[15];
+#pragma unroll
+    for (int c = 0; c < 15; ++c) a_col[c] = 0.f;   // albedo 0..2, radiance 3..5, coarse 6..14
+
+    for (int base = 0; base < S; base += 32) {
+      int i = base + lane;
+      bool valid = i < S;
+      float zi = valid ? zr[i] : 0.f;
+      float dist = (valid && i < S - 1) ? (zr[i + 1] - zi) : 1e10f;
+      dist *= dnorm;
+      const float* px = cur + (size_t)(valid ? i : 0) * C;
+      float sig = px[0];
+      if (noise != nullptr && valid) sig += noise[(int64_t)r * S + i];
+      RayAlpha ra = row_alpha(sig, dist, valid, carry, lane);
+      if (valid) {
+        if (!SIMPLE) {
+          weights[(int64_t)r * S + i] = ra.w;
+          a_depth += ra.w * zi;
+          a_acc += ra.w;
+          a_rough += ra.w * sigmoidf_fast(px[4]);
+          a_irr += ra.w * head_act(px[5], sigm);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) a_col[c] += ra.w * sigmoidf_fast(px[1 + c]);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) a_col[3 + c] += ra.w * head_act(px[6 + c], sigm);
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          if (k < nc) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) a_col[6 + 3 * k + c] += ra.w * head_act(px[9 + 3 * k + c], sigm);
+          }
+      }
+    }
+    // reductions
+    if (!SIMPLE) {
+      a_depth = warp_sum(a_depth); a_acc = warp_sum(a_acc); a_rough = warp_sum(a_rough); a_irr = warp_sum(a_irr);
+    }
+#pragma unroll
+    for (int c = 0; c < 15; ++c) a_col[c] = warp_sum(a_col[c]);
+    if (lane == 0) {
+      if (!SIMPLE) {
+        float q = a_depth / a_acc;
+        float m = (q != q) ? q : fmaxf(1e-10f, q);    // torch.max propagates NaN (acc == 0)
+        s_out[IBLN_MAP_DEPTH] = a_depth; s_out[IBLN_MAP_ACC] = a_acc; s_out[IBLN_MAP_DISP] = 1.0f / m;
+        s_out[IBLN_MAP_TEND] = carry; s_out[IBLN_MAP_ROUGH] = a_rough; s_out[IBLN_MAP_IRR] = a_irr;
+#pragma unroll
+        for (int c = 0; c < 15; ++c) s_out[IBLN_MAP_ALBEDO + c] = (c < 6 + 3 * nc) ? a_col[c] : 0.f;
+        for (int c = 21; c < 24; ++c) s_out[c] = 0.f;
+      } else {
+#pragma unroll
+        for (int c = 0; c < 12; ++c) s_out[c] = a_col[3 + c];
+      }
+    }
+    __syncwarp();
+    if (!SIMPLE) {
+      if (lane < IBLN_MAPS_STRIDE) {
+        float v = s_out[lane];
+        maps[(int64_t)r * IBLN_MAPS_STRIDE + lane] = v;
+        if (maps_srgb != nullptr) {
+          bool colour = (lane == IBLN_MAP_IRR) || (lane >= IBLN_MAP_ALBEDO && lane < IBLN_MAP_COARSE + 9);
+          maps_srgb[(int64_t)r * IBLN_MAPS_STRIDE + lane] = colour ? srgbf(v) : v;
+        }
+      }
+    } else {
+      if (lane < 3 + 3 * nc) pre_out[(int64_t)r * (3 + 3 * nc) + lane] = s_out[lane];
+    }
+    __syncwarp();
+  }
+}
+
+// Backward.  Pass 1 recomputes the forward scan (alpha, T kept in shared memory) and the maps the
+// non-linear outputs need (depth, acc, colour maps for the sRGB derivative); pass 2 walks the ray in
+// reverse for the suffix sum  sum_{k>i} gw_k w_k  and writes g_raw through the staging tile.
+__global__ void __launch_bounds__(CP_WARPS * 32)
+composite_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays_d,
+                     const float* __restrict__ noise, const float* __restrict__ g_weights,
+                     const float* __restrict__ g_maps, const float* __restrict__ g_srgb, int n, int S, int C, int nc,
+                     int sigm, float* __restrict__ g_raw) {
+  extern __shared__ __align__(16) float sm[];
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = S * C;
+  const int Sp = (S + 31) & ~31;
+  float* cur = sm + (size_t)warp * (tile + 3 * Sp + 32);
+  float* s_alpha = cur + tile;
+  float* s_T = s_alpha + Sp;
+  float* s_dist = s_T + Sp;
+  float* s_g = s_dist + Sp;     // 24 combined per-ray gradients
+  const bool vec_ok = (tile % 4 == 0) && ((reinterpret_cast<uintptr_t>(raw) & 15) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(g_raw) & 15) == 0);
+  for (int r = blockIdx.x * CP_WARPS + warp; r < n; r += gridDim.x * CP_WARPS) {
+    tile_load_async(cur, raw + (int64_t)r * tile, tile, lane, vec_ok);
+    float dx = rays_d[3 * r], dy = rays_d[3 * r + 1], dz = rays_d[3 * r + 2];
+    float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
+    const float* zr = z + (int64_t)r * S;
+    cp_async_wait<0>();
+    __syncwarp();
+    // ---- pass 1
+    float carry = 1.0f;
+    float a_depth = 0.f, a_acc = 0.f, a_irr = 0.f;
+    float a_col[15];
+#pragma unroll
+    for (int c = 0; c < 15; ++c) a_col[c] = 0.f;
+    for (int base = 0; base < S; base += 32) {
+      int i = base + lane;
+      bool valid = i < S;
+      float zi = valid ? zr[i] : 0.f;
+      float dist = (valid && i < S - 1) ? (zr[i + 1] - zi) : 1e10f;
+      dist *= dnorm;
+      const float* px = cur + (size_t)(valid ? i : 0) * C;
+      float sig = px[0];
+      if (noise != nullptr && valid) sig += noise[(int64_t)r * S + i];
+      RayAlpha ra = row_alpha(sig, dist, valid, carry, lane);
+      s_alpha[i] = ra.alpha; s_T[i] = ra.T; s_dist[i] = (sig > 0.f) ? dist : 0.f;
+      if (valid) {
+        a_depth += ra.w * zi; a_acc += ra.w;
+        if (g_srgb != nullptr) {
+          a_irr += ra.w * head_act(px[5], sigm);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) a_col[c] += ra.w * sigmoidf_fast(px[1 + c]);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) a_col[3 + c] += ra.w * head_act(px[6 + c], sigm);
+#pragma unroll
+          for (int k = 0; k < 3; ++k)
+            if (k < nc) {
+#pragma unroll
+              for (int c = 0; c < 3; ++c) a_col[6 + 3 * k + c] += ra.w * head_act(px[9 + 3 * k + c], sigm);
+            }
+        }
+      }
+    }
+    a_depth = warp_sum(a_depth); a_acc = warp_sum(a_acc);
+    if (g_srgb != nullptr) {
+      a_irr = warp_sum(a_irr);
+#pragma unroll
+      for (int c = 0; c < 15; ++c) a_col[c] = warp_sum(a_col[c]);
+    }
+    // combined per-ray gradients wrt the LINEAR maps
+    if (lane < IBLN_MAPS_STRIDE) {
+      float g = g_maps ? g_maps[(int64_t)r * IBLN_MAPS_STRIDE + lane] : 0.f;
+      if (g_srgb != nullptr) {
+        float gs = g_srgb[(int64_t)r * IBLN_MAPS_STRIDE + lane];
+        bool colour = (lane == IBLN_MAP_IRR) || (lane >= IBLN_MAP_ALBEDO && lane < IBLN_MAP_COARSE + 9);
+        if (colour) {
+          float lin = (lane == IBLN_MAP_IRR) ? a_irr : 0.f;
+#pragma unroll
+          for (int c = 0; c < 15; ++c) if (lane == IBLN_MAP_ALBEDO + c) lin = a_col[c];
+          g += gs * dsrgbf(lin);
+        } else {
+          g += gs;
+        }
+      }
+      s_g[lane] = g;
+    }
+    __syncwarp();
+    float gdepth = s_g[IBLN_MAP_DEPTH], gacc = s_g[IBLN_MAP_ACC], gdisp = s_g[IBLN_MAP_DISP];
+    if (gdisp != 0.f) {
+      float q = a_depth / a_acc;
+      if (q > 1e-10f) {     // disp = 1/q : d/d depth = -1/(q^2 acc), d/d acc = depth/(q^2 acc^2)
+        float iq2 = 1.0f / (q * q);
+        gdepth += gdisp * (-iq2 / a_acc);
+        gacc += gdisp * (iq2 * a_depth / (a_acc * a_acc));
+      }
+    }
+    // d T_end / d alpha_i = -T_end / om_i  -> folds into the suffix term as an extra "sample" at the end
+    float g_tend = s_g[IBLN_MAP_TEND] * carry;
+    // ---- pass 2 (reverse)
+    float suffix = g_tend;
+    for (int base = (Sp - 32); base >= 0; base -= 32) {
+      int i = base + lane;
+      bool valid = i < S;
+      float* px = cur + (size_t)(valid ? i : 0) * C;
+      float alpha = s_alpha[i], T = s_T[i], w = alpha * T;
+      float zi = valid ? zr[i] : 0.f;
+      float gw = 0.f;
+      float go[18];
+#pragma unroll
+      for (int c = 0; c < 18; ++c) go[c] = 0.f;
+      if (valid) {
+        gw = (g_weights ? g_weights[(int64_t)r * S + i] : 0.f) + gdepth * zi + gacc;
+        // radiance (live weights)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float x = px[6 + c], y = head_act(x, sigm), gm = s_g[IBLN_MAP_RAD + c];
+          gw += gm * y;
+          go[6 + c] = w * gm * head_dact(x, y, sigm);
+        }
+        // detached-weight heads
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { float x = px[1 + c], y = sigmoidf_fast(x); go[1 + c] = w * s_g[IBLN_MAP_ALBEDO + c] * y * (1.f - y); }
+        { float x = px[4], y = sigmoidf_fast(x); go[4] = w * s_g[IBLN_MAP_ROUGH] * y * (1.f - y); }
+        { float x = px[5], y = head_act(x, sigm); go[5] = w * s_g[IBLN_MAP_IRR] * head_dact(x, y, sigm); }
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          if (k < nc) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              float x = px[9 + 3 * k + c], y = head_act(x, sigm);
+              go[9 + 3 * k + c] = w * s_g[IBLN_MAP_COARSE + 3 * k + c] * head_dact(x, y, sigm);
+            }
+          }
+      }
+      // inclusive suffix scan of gw*w over the row (towards higher lanes)
+      float t = valid ? gw * w : 0.f;
+      float p = t;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        float v = __shfl_down_sync(FULL, p, o);
+        if (lane + o < 32) p += v;
+      }
+      float excl = p - t + suffix;          // sum over k > i
+      suffix += __shfl_sync(FULL, p, 0);
+      if (valid) {
+        float om = (1.0f - alpha) + 1e-10f;
+        float galpha = gw * T - excl / om;
+        go[0] = galpha * s_dist[i] * (1.0f - alpha);   // d alpha/d sigma = dist * exp(-sigma dist), 0 where sigma <= 0
+#pragma unroll
+        for (int c = 0; c < 18; ++c) if (c < C) px[c] = go[c];
+        for (int c = 18; c < C; ++c) px[c] = 0.f;
+      }
+    }
+    __syncwarp();
+    float* dst = g_raw + (int64_t)r * tile;
+    if (vec_ok) {
+      for (int i = lane; i < (tile >> 2); i += 32) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<float4*>(cur)[i];
+    } else {
+      for (int i = lane; i < tile; i += 32) dst[i] = cur[i];
+    }
+    __syncwarp();
+  }
+}
+
+// sigma-only depth compositing (normal estimator / raw2outputs_depth): no tile staging needed.
+__global__ void __launch_bounds__(CP_WARPS * 32)
+depth_fwd_kernel(const float* __restrict__ sigma, const float* __restrict__ z, const float* __restrict__ rays_d,
+                 int reps, int n, int S, float* __restrict__ depth, float* __restrict__ weights,
+                 float* __restrict__ visibility) {
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int64_t rows = (int64_t)reps * n;
+  for (int64_t m = (int64_t)blockIdx.x * CP_WARPS + warp; m < rows; m += (int64_t)gridDim.x * CP_WARPS) {
+    int r = (int)(m % n);
+    float dx = rays_d[3 * r], dy = rays_d[3 * r + 1], dz = rays_d[3 * r + 2];
+    float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
+    const float* zr = z + (int64_t)r * S;
+    const float* sr = sigma + m * S;
+    float carry = 1.0f, a_depth = 0.f;
+    for (int base = 0; base < S; base += 32) {
+      int i = base + lane;
+      bool valid = i < S;
+      float zi = valid ? zr[i] : 0.f;
+      float dist = (valid && i < S - 1) ? (zr[i + 1] - zi) : 1e10f;
+      dist *= dnorm;
+      RayAlpha ra = row_alpha(valid ? sr[i] : 0.f, dist, valid, carry, lane);
+      if (valid) {
+        a_depth += ra.w * zi;
+        if (weights != nullptr) weights[m * S + i] = ra.w;
+      }
+    }
+    a_depth = warp_sum(a_depth);
+    if (lane == 0) {
+      depth[m] = a_depth;
+      if (visibility != nullptr) visibility[m] = carry;
+    }
+  }
+}
+
+static int comp_grid(int64_t n, int device, int ctas_per_sm) {
+  int64_t need = (n + CP_WARPS - 1) / CP_WARPS;
+  int64_t cap = (int64_t)num_sms(device) * ctas_per_sm;
+  return (int)(need < cap ? (need > 0 ? need : 1) : cap);
+}
+
+}  // namespace ibln
+
+using namespace ibln;
+
+template <bool SIMPLE>
+static int launch_fwd(const float* raw, const float* z, const float* d, const float* noise, int n, int S, int C, int nc,
+                      int sigm, float* weights, float* maps, float* maps_srgb, float* pre, int device, void* stream) {
+  if (n < 0 || S < 1 || C < 9 + 3 * nc || C > MAXCH || nc < 0 || nc > 3 || !raw || !z || !d) return IBLN_EINVAL;
+  if (n == 0) return 0;
+  DeviceGuard g(device);
+  size_t smem = (size_t)CP_WARPS * (2 * (size_t)S * C + 32) * sizeof(float);
+  if (smem > 220 * 1024) return IBLN_EINVAL;
+  auto kern = composite_fwd_kernel<SIMPLE>;
+  IBLN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = (int)((220 * 1024) / (smem + 1024));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 8) per_sm = 8;
+  kern<<<comp_grid(n, device, per_sm), CP_WARPS * 32, smem, (cudaStream_t)stream>>>(raw, z, d, noise, n, S, C, nc, sigm,
+                                                                                   weights, maps, maps_srgb, pre);
+  IBLN_RETURN_LAST();
+}
+
+extern "C" int ibln_composite_fwd(const float* raw, const float* z, const float* rays_d, const float* noise, int n,
+                                  int S, int C, int nc, int sigm, float* weights, float* maps, float* maps_srgb,
+                                  int device, void* stream) {
+  if (!weights || !maps) return IBLN_EINVAL;
+  return launch_fwd<false>(raw, z, rays_d, noise, n, S, C, nc, sigm, weights, maps, maps_srgb, nullptr, device, stream);
+}
+
+extern "C" int ibln_composite_simple_fwd(const float* raw, const float* z, const float* dirs, int n, int S, int C, int nc,
+                                         int sigm, float* pre_out, int device, void* stream) {
+  if (!pre_out) return IBLN_EINVAL;
+  return launch_fwd<true>(raw, z, dirs, nullptr, n, S, C, nc, sigm, nullptr, nullptr, nullptr, pre_out, device, stream);
+}
+
+extern "C" int ibln_composite_bwd(const float* raw, const float* z, const float* rays_d, const float* noise,
+                                  const float* g_weights, const float* g_maps, const float* g_maps_srgb, int n, int S,
+                                  int C, int nc, int sigm, float* g_raw, int device, void* stream) {
+  if (n < 0 || S < 1 || C < 9 + 3 * nc || C > MAXCH || nc < 0 || nc > 3 || !raw || !z || !rays_d || !g_raw) return IBLN_EINVAL;
+  if (n == 0) return 0;
+  DeviceGuard g(device);
+  int Sp = (S + 31) & ~31;
+  size_t smem = (size_t)CP_WARPS * ((size_t)S * C + 3 * Sp + 32) * sizeof(float);
+  if (smem > 220 * 1024) return IBLN_EINVAL;
+  IBLN_CUDA(cudaFuncSetAttribute(composite_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = (int)((220 * 1024) / (smem + 1024));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 8) per_sm = 8;
+  composite_bwd_kernel<<<comp_grid(n, device, per_sm), CP_WARPS * 32, smem, (cudaStream_t)stream>>>(
+      raw, z, rays_d, noise, g_weights, g_maps, g_maps_srgb, n, S, C, nc, sigm, g_raw);
+  IBLN_RETURN_LAST();
+}
+
+extern "C" int ibln_depth_fwd(const float* sigma, const float* z, const float* rays_d, int reps, int n, int S,
+                              float* depth, float* weights, float* visibility, int device, void* stream) {
+  if (reps < 1 || n < 0 || S < 1 || !sigma || !z || !rays_d || !depth) return IBLN_EINVAL;
+  if (n == 0) return 0;
+  DeviceGuard g(device);
+  depth_fwd_kernel<<<comp_grid((int64_t)reps * n, device, 16), CP_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      sigma, z, rays_d, reps, n, S, depth, weights, visibility);
+  IBLN_RETURN_LAST();
+}

@@ -1,0 +1,252 @@
+// Stratified and hierarchical sampling kernels (north-star subsystem 1).
+// One warp per ray: warp-level prefix scan for the CDF, binary search in shared memory for the
+// inverse, warp bitonic sort for the coarse+fine merge.
+#include "common.cuh"
+
+namespace ibln {
+
+// ---------------------------------------------------------------- stratified z
+// torch.linspace(0,1,S) is evaluated symmetrically (start+step*i in the lower half, end-step*(S-1-i)
+// in the upper half); reproduce that and keep every op un-contracted so z is bit-identical to
+// ibl_nerf_renderer.py:670-692.
+__device__ __forceinline__ float linspace01(int i, int s) {
+  float step = __fdiv_rn(1.0f, (float)(s - 1));
+  return (i < s / 2) ? __fmul_rn(step, (float)i) : __fsub_rn(1.0f, __fmul_rn(step, (float)(s - 1 - i)));
+}
+__device__ __forceinline__ float z_lin(float nr, float fr, int i, int s, int lindisp) {
+  float t = linspace01(i, s);
+  if (!lindisp) return __fadd_rn(__fmul_rn(nr, __fsub_rn(1.0f, t)), __fmul_rn(fr, t));
+  float a = __fmul_rn(__fdiv_rn(1.0f, nr), __fsub_rn(1.0f, t));
+  float b = __fmul_rn(__fdiv_rn(1.0f, fr), t);
+  return __fdiv_rn(1.0f, __fadd_rn(a, b));
+}
+
+__global__ void stratified_z_kernel(const float* __restrict__ nearp, const float* __restrict__ farp,
+                                    const float* __restrict__ t_rand, int n, int s, int lindisp,
+                                    float* __restrict__ z_out) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)n * s) return;
+  int r = (int)(idx / s), i = (int)(idx % s);
+  float nr = nearp[r], fr = farp[r];
+  float zi = z_lin(nr, fr, i, s, lindisp);
+  if (t_rand != nullptr && s > 1) {
+    float lo = zi, hi = zi;
+    if (i > 0) lo = __fmul_rn(0.5f, __fadd_rn(zi, z_lin(nr, fr, i - 1, s, lindisp)));
+    if (i < s - 1) hi = __fmul_rn(0.5f, __fadd_rn(z_lin(nr, fr, i + 1, s, lindisp), zi));
+    zi = __fadd_rn(lo, __fmul_rn(__fsub_rn(hi, lo), t_rand[idx]));
+  }
+  z_out[idx] = zi;
+}
+
+// ---------------------------------------------------------------- inverse CDF
+// searchsorted(cdf, u, right=True): first index with cdf[idx] > u.
+__device__ __forceinline__ int upper_bound(const float* cdf, int n, float u) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (cdf[mid] <= u) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__device__ __forceinline__ float invert_one(const float* cdf, const float* bins, int nbins, float u, int* ind_out) {
+  int ind = upper_bound(cdf, nbins, u);
+  *ind_out = ind;
+  int below = max(ind - 1, 0), above = min(ind, nbins - 1);
+  float c0 = cdf[below], c1 = cdf[above], b0 = bins[below], b1 = bins[above];
+  float den = __fsub_rn(c1, c0);
+  if (den < 1e-5f) den = 1.0f;
+  float t = __fdiv_rn(__fsub_rn(u, c0), den);
+  return __fadd_rn(b0, __fmul_rn(t, __fsub_rn(b1, b0)));
+}
+
+// Build cdf[0..nbins) in shared memory from nbins-1 weights (warp-cooperative).
+// pdf = (w+1e-5)/sum; cdf = [0, cumsum(pdf)]  (nerf_renderer_helper.py:93-96)
+__device__ __forceinline__ void warp_build_cdf(const float* __restrict__ w, int nw, float* cdf, int lane) {
+  float part = 0.f;
+  for (int i = lane; i < nw; i += 32) part += w[i] + 1e-5f;
+  float total = warp_sum(part);
+  float carry = 0.f;
+  if (lane == 0) cdf[0] = 0.f;
+  for (int base = 0; base < nw; base += 32) {
+    int i = base + lane;
+    float p = (i < nw) ? __fdiv_rn(w[i] + 1e-5f, total) : 0.f;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      float v = __shfl_up_sync(FULL, p, o);
+      if (lane >= o) p += v;
+    }
+    if (i < nw) cdf[i + 1] = carry + p;
+    carry += __shfl_sync(FULL, p, 31);
+  }
+  __syncwarp();
+}
+
+constexpr int SP_WARPS = 4;
+
+__global__ void __launch_bounds__(SP_WARPS * 32)
+sample_pdf_kernel(const float* __restrict__ bins, int64_t bins_stride, const float* __restrict__ weights,
+                  int64_t w_stride, const float* __restrict__ cdf_in, const float* __restrict__ u, int n, int nbins,
+                  int nsamp, int64_t* __restrict__ inds_out, float* __restrict__ samples) {
+  extern __shared__ float sm[];
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* s_bins = sm + (size_t)warp * 2 * nbins;
+  float* s_cdf = s_bins + nbins;
+  for (int r = blockIdx.x * SP_WARPS + warp; r < n; r += gridDim.x * SP_WARPS) {
+    const float* brow = bins + (int64_t)r * bins_stride;
+    for (int i = lane; i < nbins; i += 32) s_bins[i] = brow[i];
+    if (cdf_in != nullptr) {
+      for (int i = lane; i < nbins; i += 32) s_cdf[i] = cdf_in[(int64_t)r * nbins + i];
+      __syncwarp();
+    } else {
+      warp_build_cdf(weights + (int64_t)r * w_stride, nbins - 1, s_cdf, lane);
+    }
+    for (int j = lane; j < nsamp; j += 32) {
+      int ind;
+      float sv = invert_one(s_cdf, s_bins, nbins, u[(int64_t)r * nsamp + j], &ind);
+      samples[(int64_t)r * nsamp + j] = sv;
+      if (inds_out != nullptr) inds_out[(int64_t)r * nsamp + j] = ind;
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------- merge / sort
+__device__ __forceinline__ void warp_bitonic_sort(float* s, int npad, int lane) {
+  for (int k = 2; k <= npad; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = lane; t < (npad >> 1); t += 32) {
+        int i = ((t / j) * 2 * j) + (t % j);
+        int l = i + j;
+        bool up = ((i & k) == 0);
+        float a = s[i], b = s[l];
+        if ((a > b) == up) { s[i] = b; s[l] = a; }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+__host__ __device__ inline int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+__global__ void __launch_bounds__(SP_WARPS * 32)
+merge_sort_kernel(const float* __restrict__ za, const float* __restrict__ zb, int n, int sa, int sb, int npad,
+                  float* __restrict__ out) {
+  extern __shared__ float sm[];
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* s = sm + (size_t)warp * npad;
+  int tot = sa + sb;
+  for (int r = blockIdx.x * SP_WARPS + warp; r < n; r += gridDim.x * SP_WARPS) {
+    for (int i = lane; i < npad; i += 32)
+      s[i] = i < sa ? za[(int64_t)r * sa + i] : (i < tot ? zb[(int64_t)r * sb + (i - sa)] : __int_as_float(0x7f800000));
+    __syncwarp();
+    warp_bitonic_sort(s, npad, lane);
+    for (int i = lane; i < tot; i += 32) out[(int64_t)r * tot + i] = s[i];
+    __syncwarp();
+  }
+}
+
+// z mids -> cdf(weights[1:-1]) -> samples -> sort(cat(z, samples)); ibl_nerf_renderer.py:702-707
+__global__ void __launch_bounds__(SP_WARPS * 32)
+hierarchical_kernel(const float* __restrict__ z, const float* __restrict__ weights, const float* __restrict__ u, int n,
+                    int s0, int s1, int npad, float* __restrict__ z_samples, float* __restrict__ z_merged) {
+  extern __shared__ float sm[];
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int nbins = s0 - 1;
+  float* s_bins = sm + (size_t)warp * (2 * s0 + npad);
+  float* s_cdf = s_bins + s0;
+  float* s_sort = s_cdf + s0;
+  int tot = s0 + s1;
+  for (int r = blockIdx.x * SP_WARPS + warp; r < n; r += gridDim.x * SP_WARPS) {
+    const float* zr = z + (int64_t)r * s0;
+    for (int i = lane; i < s0; i += 32) {
+      float zi = zr[i];
+      s_sort[i] = zi;
+      if (i < nbins) s_bins[i] = __fmul_rn(0.5f, __fadd_rn(zr[i + 1], zi));
+    }
+    warp_build_cdf(weights + (int64_t)r * s0 + 1, nbins - 1, s_cdf, lane);
+    for (int j = lane; j < s1; j += 32) {
+      int ind;
+      float sv = invert_one(s_cdf, s_bins, nbins, u[(int64_t)r * s1 + j], &ind);
+      z_samples[(int64_t)r * s1 + j] = sv;
+      s_sort[s0 + j] = sv;
+    }
+    for (int i = tot + lane; i < npad; i += 32) s_sort[i] = __int_as_float(0x7f800000);
+    __syncwarp();
+    warp_bitonic_sort(s_sort, npad, lane);
+    for (int i = lane; i < tot; i += 32) z_merged[(int64_t)r * tot + i] = s_sort[i];
+    __syncwarp();
+  }
+}
+
+static int ray_grid(int n, int device, int warps, int ctas_per_sm) {
+  int need = (n + warps - 1) / warps;
+  int cap = num_sms(device) * ctas_per_sm;
+  return need < cap ? (need > 0 ? need : 1) : cap;
+}
+
+}  // namespace ibln
+
+using namespace ibln;
+
+extern "C" int ibln_stratified_z(const float* nearp, const float* farp, const float* t_rand, int n, int s,
+                                 int lindisp, float* z_out, int device, void* stream) {
+  if (n < 0 || s < 1 || !nearp || !farp || !z_out) return IBLN_EINVAL;
+  if (n == 0) return 0;
+  DeviceGuard g(device);
+  int64_t tot = (int64_t)n * s;
+  stratified_z_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(nearp, farp, t_rand, n, s, lindisp, z_out);
+  IBLN_RETURN_LAST();
+}
+
+static int launch_sample_pdf(const float* bins, int64_t bs, const float* w, int64_t ws, const float* cdf, const float* u,
+                             int n, int nbins, int nsamp, int64_t* inds, float* samples, int device, void* stream) {
+  if (n < 0 || nbins < 2 || nsamp < 1 || !bins || !u || !samples) return IBLN_EINVAL;
+  if (n == 0) return 0;
+  DeviceGuard g(device);
+  size_t smem = (size_t)SP_WARPS * 2 * nbins * sizeof(float);
+  if (smem > 200 * 1024) return IBLN_EINVAL;
+  if (smem > 48 * 1024) IBLN_CUDA(cudaFuncSetAttribute(sample_pdf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = ray_grid(n, device, SP_WARPS, 16);
+  sample_pdf_kernel<<<grid, SP_WARPS * 32, smem, (cudaStream_t)stream>>>(bins, bs, w, ws, cdf, u, n, nbins, nsamp, inds, samples);
+  IBLN_RETURN_LAST();
+}
+
+extern "C" int ibln_sample_pdf(const float* bins, int64_t bins_stride, const float* weights, int64_t w_stride,
+                               const float* u, int n, int nbins, int nsamp, float* samples, int device, void* stream) {
+  if (!weights) return IBLN_EINVAL;
+  return launch_sample_pdf(bins, bins_stride, weights, w_stride, nullptr, u, n, nbins, nsamp, nullptr, samples, device, stream);
+}
+
+extern "C" int ibln_inverse_cdf(const float* cdf, const float* bins, const float* u, int n, int nbins, int nsamp,
+                                int64_t* inds_out, float* samples, int device, void* stream) {
+  if (!cdf) return IBLN_EINVAL;
+  return launch_sample_pdf(bins, nbins, nullptr, 0, cdf, u, n, nbins, nsamp, inds_out, samples, device, stream);
+}
+
+extern "C" int ibln_merge_sort_z(const float* za, const float* zb, int n, int sa, int sb, float* z_out, int device,
+                                 void* stream) {
+  if (n < 0 || sa < 0 || sb < 0 || sa + sb < 1 || !z_out) return IBLN_EINVAL;
+  if (n == 0) return 0;
+  DeviceGuard g(device);
+  int npad = next_pow2(sa + sb);
+  if (npad < 2) npad = 2;
+  size_t smem = (size_t)SP_WARPS * npad * sizeof(float);
+  if (smem > 200 * 1024) return IBLN_EINVAL;
+  if (smem > 48 * 1024) IBLN_CUDA(cudaFuncSetAttribute(merge_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  merge_sort_kernel<<<ray_grid(n, device, SP_WARPS, 16), SP_WARPS * 32, smem, (cudaStream_t)stream>>>(za, zb, n, sa, sb, npad, z_out);
+  IBLN_RETURN_LAST();
+}
+
+extern "C" int ibln_hierarchical_sample(const float* z, const float* weights, const float* u, int n, int s0, int s1,
+                                        float* z_samples, float* z_merged, int device, void* stream) {
+  if (n < 0 || s0 < 4 || s1 < 1 || !z || !weights || !u || !z_samples || !z_merged) return IBLN_EINVAL;
+  if (n == 0) return 0;
+  DeviceGuard g(device);
+  int npad = next_pow2(s0 + s1);
+  size_t smem = (size_t)SP_WARPS * (2 * s0 + npad) * sizeof(float);
+  if (smem > 200 * 1024) return IBLN_EINVAL;
+  if (smem > 48 * 1024) IBLN_CUDA(cudaFuncSetAttribute(hierarchical_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  hierarchical_kernel<<<ray_grid(n, device, SP_WARPS, 16), SP_WARPS * 32, smem, (cudaStream_t)stream>>>(z, weights, u, n, s0, s1, npad, z_samples, z_merged);
+  IBLN_RETURN_LAST();
+}

@@ -1,0 +1,185 @@
+"""IBLNeRF module + network query functions (drop-in for reference nerf_models/ibl_nerf.py).
+
+`IBLNeRF` keeps the reference constructor signature, attribute names and state_dict keys
+(ibl_nerf.py:14-86) so checkpoints are interchangeable.  Its parameters are ordinary nn.Linear
+layers created in the reference's order, so `torch.manual_seed(s); IBLNeRF(...)` yields bit-identical
+initial weights.
+"""
+import ctypes
+
+import torch
+import torch.nn as nn
+
+from . import _lib, mlp
+from ._lib import call, f32c, ptr
+
+
+class IBLNeRF(nn.Module):
+    def __init__(self, D=8, W=256, input_ch=3, input_ch_views=3, skips=[4], use_illumination_feature_layer=False,
+                 use_instance_feature_layer=False, coarse_radiance_number=0, is_color_independent_to_direction=True):
+        super().__init__()
+        self.D, self.W = D, W
+        self.input_ch, self.input_ch_views = input_ch, input_ch_views
+        self.skips = skips
+        self.use_illumination_feature_layer = use_illumination_feature_layer
+        self.use_instance_feature_layer = use_instance_feature_layer
+        self.positions_linears = nn.ModuleList(
+            [nn.Linear(input_ch, W)] +
+            [nn.Linear(W, W) if i not in self.skips else nn.Linear(W + input_ch, W) for i in range(D - 1)])
+        self.views_linears = nn.ModuleList([nn.Linear(input_ch_views + W, W)])
+        self.feature_linear = nn.Linear(W, W)
+        self.sigma_linear = nn.Linear(W, 1)
+        self.albedo_feature_linear = nn.Linear(W, W // 2)
+        self.albedo_linear = nn.Linear(W // 2, 3)
+        self.roughness_linear = nn.Linear(W, 1)
+        self.irradiance_feature_linear = nn.Linear(W, W // 2)
+        self.irradiance_linear = nn.Linear(W // 2, 1)
+        self.radiance_linear = nn.Linear(W, 3)
+        self.coarse_radiance_number = coarse_radiance_number
+        self.additional_radiance_feature_linear = nn.ModuleList([nn.Linear(W, W // 2) for _ in range(coarse_radiance_number)])
+        self.additional_radiance_linear = nn.ModuleList([nn.Linear(W // 2, 3) for _ in range(coarse_radiance_number)])
+        self.is_color_independent_to_direction = is_color_independent_to_direction
+        self.freeze_radiance = False
+        self.freeze_roughness = False
+        self.precision = None          # None -> mlp.default_precision()
+        self._packed = None
+        self._packed_key = None
+
+    def __str__(self):
+        return "\n".join(["[NeRFDecomp", "\t- depth : {}".format(self.D), "\t- width : {}".format(self.W),
+                          "\t- input_ch : {}".format(self.input_ch),
+                          "\t- use_illumination_feature_layer : {}".format(self.use_illumination_feature_layer)])
+
+    # ------------------------------------------------------------------ helpers
+    def is_kitchen_arch(self):
+        """The fused kernels are specialised for the architecture every shipped config uses."""
+        return (self.D == 8 and self.W == 256 and self.input_ch == 63 and self.input_ch_views == 27 and
+                list(self.skips) == [4] and self.coarse_radiance_number == 3 and not self.is_color_independent_to_direction)
+
+    def ordered_params(self):
+        sd = dict(self.named_parameters())
+        out = []
+        for name, _, _ in mlp.PARAM_ORDER:
+            out += [sd[name + ".weight"], sd[name + ".bias"]]
+        return out
+
+    def effective_precision(self):
+        return self.precision or mlp.default_precision()
+
+    def packed_weights(self):
+        """bf16 chunk stream for the tensor-core kernel; re-packed whenever a parameter changed
+        (optimizer.step() bumps the tensors' version counters)."""
+        ps = self.ordered_params()
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if self._packed is None or self._packed_key != key or self._packed.device != ps[0].device:
+            dev = ps[0].device
+            if self._packed is None or self._packed.device != dev:
+                self._packed = torch.empty(_lib.lib().ibln_mlp_packed_bytes(), dtype=torch.uint8, device=dev)
+            arr = (ctypes.c_void_p * 46)(*[ctypes.c_void_p(f32c(p.detach()).data_ptr()) for p in ps])
+            call("ibln_mlp_pack_weights", dev, arr, ptr(self._packed))
+            self._packed_key = key
+        return self._packed
+
+    # ------------------------------------------------------------------ reference API
+    def forward(self, x):
+        """ibl_nerf.py:212-217 on EMBEDDED input ([P,90] or [P,63]); exact fp32 path."""
+        if not self.is_kitchen_arch():
+            raise NotImplementedError("IBLNeRF kernels are specialised for the kitchen architecture (D=8, W=256, 63/27, 3 coarse heads)")
+        shp = x.shape
+        x = f32c(x.reshape(-1, shp[-1]))
+        if shp[-1] == self.input_ch + self.input_ch_views:
+            x_pos, x_dir = x[:, :self.input_ch], x[:, self.input_ch:]
+        else:
+            x_pos, x_dir = x, None
+        flags = (bool(self.freeze_radiance), bool(self.freeze_roughness))
+        out = mlp._MLPFp32.apply(flags, x_pos, x_dir, *self.ordered_params())
+        return out.reshape(*shp[:-1], out.shape[-1])
+
+    # ------------------------------------------------------------------ fused queries
+    def _grad_needed(self):
+        return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+
+    def query_points(self, pts, viewdirs):
+        """run_network semantics: pts [N,S,3], viewdirs [N,3] or None -> [N,S,18] / [N,S,1]."""
+        n, s = pts.shape[0], pts.shape[1]
+        use_tc = self.effective_precision() == "bf16" and not self._grad_needed()
+        if use_tc:
+            pts = f32c(pts.detach())
+            out = torch.empty(n * s, 1 if viewdirs is None else 18, dtype=torch.float32, device=pts.device)
+            d = f32c(viewdirs.detach()) if viewdirs is not None else torch.zeros(n, 3, device=pts.device)
+            call("ibln_mlp_fwd", pts.device, ptr(self.packed_weights()), 0, ptr(pts), None, ptr(d), None, n, s, 0.0,
+                 int(viewdirs is None), ptr(out), None)
+            return out.reshape(n, s, -1)
+        flat = f32c(pts.reshape(-1, 3))
+        x_pos = mlp.encode(flat, 10)
+        x_dir = None
+        if viewdirs is not None:
+            x_dir = torch.empty(n * s, 27, dtype=torch.float32, device=pts.device)
+            call("ibln_encode_dirs", pts.device, ptr(f32c(viewdirs)), n, s, 4, ptr(x_dir), 27)
+        flags = (bool(self.freeze_radiance), bool(self.freeze_roughness))
+        out = mlp._MLPFp32.apply(flags, x_pos, x_dir, *self.ordered_params())
+        return out.reshape(n, s, -1)
+
+    def query_rays(self, rays_o, rays_d, z, sigma_only=False):
+        """Ray-march query: points o + d z generated inside the kernel (bf16 path)."""
+        n, s = z.shape
+        if self.effective_precision() == "bf16" and not self._grad_needed():
+            o, d, zz = f32c(rays_o.detach()), f32c(rays_d.detach()), f32c(z.detach())
+            out = torch.empty(n * s, 1 if sigma_only else 18, dtype=torch.float32, device=zz.device)
+            call("ibln_mlp_fwd", zz.device, ptr(self.packed_weights()), 1, None, ptr(o), ptr(d), ptr(zz), n, s, 0.0,
+                 int(sigma_only), ptr(out), None)
+            return out.reshape(n, s, -1)
+        pts = rays_o[:, None, :] + rays_d[:, None, :] * z[..., None]
+        return self.query_points(pts, None if sigma_only else rays_d)
+
+    def query_eps_sigma(self, rays_o, rays_d, z, eps):
+        """sigma at the 4 epsilon-shifted copies of the ray samples: [4N,S] (normal_from_depth.py:149-158)."""
+        n, s = z.shape
+        if self.effective_precision() == "bf16":
+            o, d, zz = f32c(rays_o.detach()), f32c(rays_d.detach()), f32c(z.detach())
+            out = torch.empty(4 * n * s, dtype=torch.float32, device=zz.device)
+            call("ibln_mlp_fwd", zz.device, ptr(self.packed_weights()), 2, None, ptr(o), ptr(d), ptr(zz), n, s, float(eps), 1,
+                 ptr(out), None)
+            return out.reshape(4 * n, s)
+        from . import ops
+        pts = ops.normal_eps_points(rays_o, rays_d, z, eps)
+        with torch.no_grad():
+            return self.query_points(pts, None)[..., 0]
+
+
+def batchify(fn, chunk):
+    """ibl_nerf.py:219-233."""
+    if chunk is None:
+        return fn
+
+    def ret(inputs):
+        return torch.cat([fn(inputs[i:i + chunk]) for i in range(0, inputs.shape[0], chunk)], 0)
+    return ret
+
+
+def run_network(inputs, viewdirs, fn, embed_fn, embeddirs_fn, netchunk=1024 * 64):
+    """ibl_nerf.py:236-252.  IBLNeRF + the standard embedders take the fused path; anything else
+    (aux PositionMLPs, custom callables) is embedded with the CUDA encoder and called as an opaque module."""
+    fused = (isinstance(fn, IBLNeRF) and fn.is_kitchen_arch() and getattr(embed_fn, "n_freqs", None) == 10 and
+             getattr(embeddirs_fn, "n_freqs", None) == 4 and inputs.dim() == 3 and inputs.is_cuda)
+    if fused:
+        return fn.query_points(inputs, viewdirs)
+    inputs_flat = torch.reshape(inputs, [-1, inputs.shape[-1]])
+    embedded = embed_fn(inputs_flat)
+    if viewdirs is not None:
+        input_dirs = viewdirs[:, None].expand(inputs.shape)
+        embedded = torch.cat([embedded, embeddirs_fn(torch.reshape(input_dirs, [-1, input_dirs.shape[-1]]))], -1)
+    outputs_flat = batchify(fn, netchunk)(embedded)
+    return torch.reshape(outputs_flat, list(inputs.shape[:-1]) + [outputs_flat.shape[-1]])
+
+
+class NetworkQuery:
+    """The `network_query_fn(inputs, viewdirs, network_fn)` closure of ibl_nerf.py:327-329 as an object,
+    so the renderer can recognise it and use the ray-march kernels directly."""
+
+    def __init__(self, embed_fn, embeddirs_fn, netchunk):
+        self.embed_fn, self.embeddirs_fn, self.netchunk = embed_fn, embeddirs_fn, netchunk
+        self.fusable = getattr(embed_fn, "n_freqs", None) == 10 and getattr(embeddirs_fn, "n_freqs", None) == 4
+
+    def __call__(self, inputs, viewdirs, network_fn):
+        return run_network(inputs, viewdirs, network_fn, self.embed_fn, self.embeddirs_fn, self.netchunk)

@@ -1,0 +1,200 @@
+/*
+ * iblnerf_b200.h -- C ABI of the B200-native IBL-NeRF per-ray hot path (libiblnerf_b200.so).
+ *
+ * The reference (changwoonchoi/IBL-NeRF) has no FFI of its own: its boundary is the Python module
+ * surface of src/nerf_models/*.  Every entry point below replaces the block of eager-PyTorch
+ * launches cited next to it (paths relative to the reference's src/).  The Python host package
+ * (ibl_nerf_b200/) binds these with ctypes and mirrors the reference API on top of them.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer to contiguous row-major data unless
+ *     the name ends in _host; float = IEEE fp32; "nullable" arguments may be NULL.
+ *   - every function returns 0 on success or a cudaError_t value (> 0); IBLN_EINVAL (-1) for bad
+ *     arguments.  Nothing throws, nothing allocates device memory: the caller owns all buffers.
+ *   - last two arguments are always the CUDA device ordinal and the cudaStream_t to launch on;
+ *     all entry points are re-entrant (PyTorch's autograd engine calls backward from its own thread).
+ */
+#ifndef IBLNERF_B200_H
+#define IBLNERF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IBLN_EINVAL (-1)
+#define IBLN_ABI_VERSION 1
+
+/* packed per-ray output of the compositing kernels: one row of IBLN_MAPS_STRIDE floats per ray */
+#define IBLN_MAPS_STRIDE 24
+#define IBLN_MAP_DEPTH 0      /* sum w z                      ibl_nerf_renderer.py:249 */
+#define IBLN_MAP_ACC 1        /* sum w                        :259 */
+#define IBLN_MAP_DISP 2       /* 1/max(1e-10, depth/acc)      :258 */
+#define IBLN_MAP_TEND 3       /* prod(1-alpha+1e-10)          :140-141 (visibility) */
+#define IBLN_MAP_ROUGH 4      /* sum wd sigmoid(raw4)         :284-285 */
+#define IBLN_MAP_IRR 5        /* sum wd sigmoid(raw5)         :287-288 */
+#define IBLN_MAP_ALBEDO 6     /* 3 floats                     :281-282 */
+#define IBLN_MAP_RAD 9        /* 3 floats, live weights       :305-306 */
+#define IBLN_MAP_COARSE 12    /* 3*n_coarse floats (<= 9)     :311-318 */
+
+/* packed per-ray output of the shading kernel */
+#define IBLN_SHADE_STRIDE 16
+#define IBLN_SH_NDV 0
+#define IBLN_SH_SPEC 1
+#define IBLN_SH_DIFF 4
+#define IBLN_SH_PRE 7
+#define IBLN_SH_COLOR 10
+
+int ibln_abi_version(void);
+const char* ibln_error_string(int code);
+
+/* ---- (1) sampling ------------------------------------------------------------------------- */
+
+/* Stratified depths. Replaces ibl_nerf_renderer.py:670-692 (linspace, lerp near/far, mids, jitter).
+ * near, far: [N]; t_rand: [N,S] uniforms or NULL (perturb == 0); z_out: [N,S]. */
+int ibln_stratified_z(const float* near, const float* far, const float* t_rand, int n_rays, int n_samples,
+                      int lindisp, float* z_out, int device, void* stream);
+
+/* Inverse-CDF sampling, full path.  Replaces nerf_renderer_helper.py:91-134 (sample_pdf) given the
+ * uniforms.  bins: row r at bins + r*bins_stride, nbins entries; weights: row r at weights +
+ * r*w_stride, nbins-1 entries (strides in floats, so the caller can pass weights[:,1:-1] views);
+ * u, samples: [N,nsamp]. */
+int ibln_sample_pdf(const float* bins, int64_t bins_stride, const float* weights, int64_t w_stride,
+                    const float* u, int n_rays, int nbins, int nsamp, float* samples, int device, void* stream);
+
+/* Inverse-CDF given an explicit CDF (the bit-exact entry: inds == torch.searchsorted(cdf,u,right=True),
+ * nerf_renderer_helper.py:117-132).  cdf, bins: [N,nbins]; inds_out: [N,nsamp] int64 (nullable). */
+int ibln_inverse_cdf(const float* cdf, const float* bins, const float* u, int n_rays, int nbins, int nsamp,
+                     int64_t* inds_out, float* samples, int device, void* stream);
+
+/* Fused hierarchical step of render_rays: z mids -> sample_pdf(weights[:,1:-1]) -> sort(cat(z, samples)).
+ * Replaces ibl_nerf_renderer.py:702-707.  z: [N,S0], weights: [N,S0], u: [N,S1];
+ * z_samples: [N,S1]; z_merged: [N,S0+S1] ascending. */
+int ibln_hierarchical_sample(const float* z, const float* weights, const float* u, int n_rays, int s0, int s1,
+                             float* z_samples, float* z_merged, int device, void* stream);
+
+/* sort(cat(za, zb)) along the last axis; ibl_nerf_renderer.py:707.  za [N,sa], zb [N,sb], out [N,sa+sb]. */
+int ibln_merge_sort_z(const float* za, const float* zb, int n_rays, int sa, int sb, float* z_out,
+                      int device, void* stream);
+
+/* ---- (4) alpha compositing ------------------------------------------------------------------ */
+
+/* raw2outputs compositing core, forward.  Replaces ibl_nerf_renderer.py:204-206,241-259,281-318.
+ * raw [N,S,C] (C >= 9+3*n_coarse), z [N,S], rays_d [N,3], noise [N,S] nullable.
+ * Outputs: weights [N,S]; maps [N,24] linear; maps_srgb [N,24] nullable = pow(x+1e-12,1/2.2) of the
+ * colour-like columns (rough/depth/acc/disp/tend copied unchanged; :485-510).
+ * radiance_sigmoid: 1 = sigmoid (kitchen), 0 = relu radiance/irradiance (use_radiance_linear). */
+int ibln_composite_fwd(const float* raw, const float* z, const float* rays_d, const float* noise,
+                       int n_rays, int n_samples, int n_ch, int n_coarse, int radiance_sigmoid,
+                       float* weights, float* maps, float* maps_srgb, int device, void* stream);
+
+/* Backward of the above: g_raw [N,S,C] (fully written).  g_weights [N,S], g_maps [N,24],
+ * g_maps_srgb [N,24] are each nullable.  Albedo/roughness/irradiance/coarse radiance use DETACHED
+ * weights (no gradient to sigma), radiance/depth/acc/disp/weights use live weights (:246,:282-315). */
+int ibln_composite_bwd(const float* raw, const float* z, const float* rays_d, const float* noise,
+                       const float* g_weights, const float* g_maps, const float* g_maps_srgb,
+                       int n_rays, int n_samples, int n_ch, int n_coarse, int radiance_sigmoid,
+                       float* g_raw, int device, void* stream);
+
+/* raw2outputs_simple (reflected ray, no grad): ibl_nerf_renderer.py:38-68.
+ * pre_out [N,1+n_coarse,3] = radiance, coarse radiance 1..n_coarse. */
+int ibln_composite_simple_fwd(const float* raw, const float* z, const float* dirs, int n_rays, int n_samples,
+                              int n_ch, int n_coarse, int radiance_sigmoid, float* pre_out, int device, void* stream);
+
+/* Depth-only compositing: raw2outputs_depth (:121-150) and raw2depth (normal_from_depth.py:164-169).
+ * sigma [reps*N, S] (row m uses z / rays_d of ray m % N), depth [reps*N]; weights [reps*N,S] and
+ * visibility [reps*N] nullable. */
+int ibln_depth_fwd(const float* sigma, const float* z, const float* rays_d, int reps, int n_rays, int n_samples,
+                   float* depth, float* weights, float* visibility, int device, void* stream);
+
+/* ---- (5) normals + split-sum shading --------------------------------------------------------- */
+
+/* Shifted sample points of the epsilon normal estimator: normal_from_depth.py:143-156.
+ * pts_out [4,N,S,3] = +eps*right, -eps*right, +eps*up, -eps*up. */
+int ibln_normal_eps_points(const float* rays_o, const float* rays_d, const float* z, int n_rays, int n_samples,
+                           float eps, float* pts_out, int device, void* stream);
+
+/* Tail of the estimator: normal_from_depth.py:177-183 plus the reflection of :439.
+ * depths4 [4,N] (right,left,up,down); normal [N,3]; refl [N,3] nullable. */
+int ibln_normal_eps_finish(const float* rays_d, const float* depths4, int n_rays, float eps,
+                           float* normal, float* refl, int device, void* stream);
+
+/* Split-sum shading forward: ibl_nerf_renderer.py:412-438,455-474 + microfacet.py:8-12.
+ * rays_d,normal,albedo [N,3]; rough,irr,mip_rough,depth,near,far [N]; prefiltered [N,n_pref,3];
+ * lut [lut_c,lut_h,lut_w] (channel 0 = scale, 1 = bias); lut_coef 0 = 'F', 1 = 'F0';
+ * out [N,16] linear; out_srgb [N,16] nullable (n.v column copied unchanged). */
+int ibln_shade_fwd(const float* rays_d, const float* normal, const float* albedo, const float* rough,
+                   const float* irr, const float* mip_rough, const float* depth, const float* near, const float* far,
+                   const float* prefiltered, int n_pref, const float* lut, int lut_h, int lut_w,
+                   int lut_coef, int correct_depth, int n_rays, float* out, float* out_srgb, int device, void* stream);
+
+/* Backward: gradients reach albedo, rough (also through the LUT row coordinate), irr and mip_rough.
+ * g_out, g_out_srgb [N,16] nullable; g_albedo [N,3], g_rough, g_irr, g_mip_rough [N] all written. */
+int ibln_shade_bwd(const float* rays_d, const float* normal, const float* albedo, const float* rough,
+                   const float* irr, const float* mip_rough, const float* depth, const float* near, const float* far,
+                   const float* prefiltered, int n_pref, const float* lut, int lut_h, int lut_w,
+                   int lut_coef, int correct_depth, int n_rays, const float* g_out, const float* g_out_srgb,
+                   float* g_albedo, float* g_rough, float* g_irr, float* g_mip_rough, int device, void* stream);
+
+/* ---- (2)+(3) positional encoding and the intrinsic-component MLP ----------------------------- */
+
+/* Point generators understood by the MLP kernels (so sample points never round-trip through HBM):
+ *   mode 0  explicit   : pts [P,3] (+ dirs [P/S,3] per ray)                  ibl_nerf.py:236-252
+ *   mode 1  ray march  : pts = o + d*z                                       ibl_nerf_renderer.py:200
+ *   mode 2  eps normal : 4 shifted copies of the ray march, sigma only       normal_from_depth.py:149-158
+ * Encoding: [x, sin(2^k x), cos(2^k x)] k<10 for points (63), k<4 for UN-normalised dirs (27),
+ *           positional_embedder.py:9-34. */
+
+/* fp32 exact path (SIMT): explicit encoding + one generic GEMM; used for stage-wise 1e-4 parity and
+ * as the high-precision mode of the normal estimator. */
+int ibln_encode(const float* x, int64_t n_pts, int n_freqs, float* out, int64_t ld_out, int device, void* stream);
+/* expand per-ray rows to per-sample rows while encoding: x [n_rays,3] -> out rows r*S+s */
+int ibln_encode_dirs(const float* dirs, int64_t n_rays, int n_samples, int n_freqs, float* out, int64_t ld_out,
+                     int device, void* stream);
+/* C[M,N] (ldc) = act(A[M,K] (lda) * op(B) + bias) (+ C if accumulate).  trans_b = 1: B is [N,K] (ldb)
+ * (a torch Linear weight, forward); trans_b = 0: B is [K,N] (ldb) (dgrad).  relu_mask nullable [M,N]
+ * (ld_mask): output is zeroed where mask <= 0 (dgrad through relu).  act 0 none, 1 relu. */
+int ibln_sgemm(const float* a, int64_t lda, const float* b, int64_t ldb, int trans_b, const float* bias,
+               float* c, int64_t ldc, int64_t m, int n, int k, int act, int accumulate,
+               const float* relu_mask, int64_t ld_mask, int device, void* stream);
+/* dW[N,K] (ldw) += dY[M,N]^T (ldy) * X[M,K] (ldx); db[N] += colsum(dY) (nullable).  Deterministic
+ * two-stage reduction; workspace >= ibln_wgrad_workspace_bytes(n, k) bytes. */
+int64_t ibln_wgrad_workspace_bytes(int n, int k);
+int ibln_sgemm_wgrad(const float* dy, int64_t ldy, const float* x, int64_t ldx, int64_t m, int n, int k,
+                     float* dw, int64_t ldw, float* db, int accumulate, void* workspace, int device, void* stream);
+
+/* bf16 tensor-core path (tcgen05 / TMEM / bulk-TMA weight streaming). */
+/* Size in bytes of the packed bf16 weight image of one IBLNeRF (kitchen architecture). */
+int64_t ibln_mlp_packed_bytes(void);
+/* Pack the 46 fp32 state-dict tensors into the kernel's pre-swizzled bf16 chunk stream + fp32 biases.
+ * params: HOST array of 46 DEVICE pointers in state-dict order (ibl_nerf.py:44-72):
+ * positions_linears.{0..7}.{weight,bias}, views_linears.0.*, feature_linear.*, sigma_linear.*,
+ * albedo_feature_linear.*, albedo_linear.*, roughness_linear.*, irradiance_feature_linear.*,
+ * irradiance_linear.*, radiance_linear.*, additional_radiance_feature_linear.{0,1,2}.*,
+ * additional_radiance_linear.{0,1,2}.*.  Call after every optimizer.step(). */
+int ibln_mlp_pack_weights(const float* const* params_host, void* packed, int device, void* stream);
+
+/* Fused encode + MLP forward.  mode per the table above; o,d [n_rays,3]; z [n_rays,S];
+ * pts nullable (mode 0: [n_rays*S,3]).  sigma_only: out [P] (P = n_rays*S, or 4*n_rays*S in mode 2),
+ * else out [P,18] fp32 straight from the fp32 accumulators.  saved (nullable): activation stash for
+ * the backward pass, >= ibln_mlp_saved_bytes(P) bytes. */
+int64_t ibln_mlp_saved_bytes(int64_t n_pts);
+int ibln_mlp_fwd(const void* packed, int mode, const float* pts, const float* rays_o, const float* rays_d,
+                 const float* z, int64_t n_rays, int n_samples, float eps, int sigma_only,
+                 float* out, void* saved, int device, void* stream);
+/* Backward: g_out [P,18]; accumulates into the flat fp32 gradient image flat_grad (798 994 floats,
+ * state-dict order, each tensor row-major).  workspace >= ibln_mlp_bwd_workspace_bytes(P). */
+int64_t ibln_mlp_bwd_workspace_bytes(int64_t n_pts);
+int ibln_mlp_bwd(const void* packed, const void* saved, const float* g_out, int64_t n_pts,
+                 float* flat_grad, void* workspace, int device, void* stream);
+
+/* Self-test of the tcgen05 building block: D[128,N] = A[128,K] * B[N,K]^T with bf16 inputs staged
+ * through the same swizzled shared-memory layout the MLP kernels use. a,b fp32 (rounded to bf16
+ * inside), d fp32.  variant selects descriptor hypotheses (0 = production). */
+int ibln_umma_selftest(const float* a, const float* b, float* d, int n, int k, int variant, int device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IBLNERF_B200_H */

@@ -1,0 +1,56 @@
+"""CPU suite: host-side mirror of the reference interface (module construction, state dict, kwargs)."""
+import numpy as np
+import torch
+
+import fixtures as fx
+import ibl_nerf_b200 as ib
+from util import G
+
+
+def test_same_seed_gives_reference_initialisation():
+    g = G("mlp.npz")
+    torch.manual_seed(0)
+    nets = {"c": ib.IBLNeRF(**fx.KITCHEN_ARCH), "f": ib.IBLNeRF(**fx.KITCHEN_ARCH)}
+    for tag, net in nets.items():
+        ck = fx.state_checksums(net)
+        assert len(ck) == 46
+        for k, v in ck.items():
+            ref = g["ck_%s_%s" % (tag, k.replace(".", "__"))].numpy()
+            assert np.allclose(v, ref, rtol=0, atol=1e-12), k
+    assert sum(p.numel() for p in nets["c"].parameters()) == 798994
+
+
+def test_state_dict_layout_and_param_order():
+    net = ib.IBLNeRF(**fx.KITCHEN_ARCH)
+    keys = list(net.state_dict().keys())
+    want = []
+    for name, o, i in ib.mlp.PARAM_ORDER:
+        want += [name + ".weight", name + ".bias"]
+        assert tuple(net.state_dict()[name + ".weight"].shape) == (o, i)
+    assert keys == want
+    assert net.is_kitchen_arch() and net.coarse_radiance_number == 3
+    assert not net.freeze_radiance and not net.freeze_roughness
+
+
+def test_sample_u_sources():
+    u = ib.helper.sample_u(5, 128, det=True)
+    assert torch.equal(u[0], torch.linspace(0., 1., 128)) and u.shape == (5, 128)
+    a = ib.helper.sample_u(5, 16, det=False, pytest=True)
+    np.random.seed(0)
+    assert torch.equal(a, torch.tensor(np.random.rand(5, 16), dtype=torch.float32))
+
+
+def test_get_rays_matches_numpy_variant():
+    K = np.array([[50., 0, 16], [0, 50., 12], [0, 0, 1]], np.float32)
+    c2w = np.eye(4, dtype=np.float32)[:3]
+    c2w[:, 3] = [1, 2, 3]
+    o, d = ib.helper.get_rays(24, 32, K, torch.tensor(c2w))
+    on, dn = ib.helper.get_rays_np(24, 32, K, c2w)
+    assert np.allclose(d.numpy(), dn, atol=1e-6) and np.allclose(o.numpy(), on)
+
+
+def test_step_program_chunk_table_is_consistent():
+    # 98 chunks of 16 KiB cover the 13 GEMM steps of the fused kernel exactly once (mirrors csrc/mlp_tc.cu)
+    steps = [(256, 1, 0, 0)] + [(256, 0, 4, 0)] * 4 + [(256, 1, 4, 0), (256, 0, 4, 0), (256, 0, 4, 0), (256, 0, 4, 0),
+                                                       (256, 0, 4, 0), (256, 0, 4, 1), (256, 0, 4, 0), (128, 0, 4, 0)]
+    assert sum((a + k + l) * (n // 128) for n, a, k, l in steps) == 98
