@@ -6,7 +6,7 @@
 
 namespace ibln {
 
-constexpr int CP_WARPS = 4;
+constexpr int CP_WARPS = 4;   // warps per CTA (fewer when one ray tile is large)
 constexpr int MAXCH = 32;
 
 __device__ __forceinline__ float head_act(float x, int sigm) { return sigm ? sigmoidf_fast(x) : fmaxf(x, 0.f); }
@@ -60,8 +60,9 @@ composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
   float* buf1 = buf0 + tile;
   float* s_out = buf1 + tile;   // 32 floats of per-ray results
   const bool vec_ok = (tile % 4 == 0) && ((reinterpret_cast<uintptr_t>(raw) & 15) == 0);
-  const int stride = gridDim.x * CP_WARPS;
-  int r = blockIdx.x * CP_WARPS + warp;
+  const int nwarps = blockDim.x >> 5;
+  const int stride = gridDim.x * nwarps;
+  int r = blockIdx.x * nwarps + warp;
   if (r < n) tile_load_async(buf0, raw + (int64_t)r * tile, tile, lane, vec_ok);
   int it = 0;
   for (; r < n; r += stride, ++it) {
@@ -167,7 +168,7 @@ composite_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
   float* s_g = s_dist + Sp;     // 24 combined per-ray gradients
   const bool vec_ok = (tile % 4 == 0) && ((reinterpret_cast<uintptr_t>(raw) & 15) == 0) &&
                       ((reinterpret_cast<uintptr_t>(g_raw) & 15) == 0);
-  for (int r = blockIdx.x * CP_WARPS + warp; r < n; r += gridDim.x * CP_WARPS) {
+  for (int r = blockIdx.x * (blockDim.x >> 5) + warp; r < n; r += gridDim.x * (blockDim.x >> 5)) {
     tile_load_async(cur, raw + (int64_t)r * tile, tile, lane, vec_ok);
     float dx = rays_d[3 * r], dy = rays_d[3 * r + 1], dz = rays_d[3 * r + 2];
     float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
@@ -343,8 +344,8 @@ depth_fwd_kernel(const float* __restrict__ sigma, const float* __restrict__ z, c
   }
 }
 
-static int comp_grid(int64_t n, int device, int ctas_per_sm) {
-  int64_t need = (n + CP_WARPS - 1) / CP_WARPS;
+static int comp_grid(int64_t n, int device, int ctas_per_sm, int warps = CP_WARPS) {
+  int64_t need = (n + warps - 1) / warps;
   int64_t cap = (int64_t)num_sms(device) * ctas_per_sm;
   return (int)(need < cap ? (need > 0 ? need : 1) : cap);
 }
@@ -359,14 +360,17 @@ static int launch_fwd(const float* raw, const float* z, const float* d, const fl
   if (n < 0 || S < 1 || C < 9 + 3 * nc || C > MAXCH || nc < 0 || nc > 3 || !raw || !z || !d) return IBLN_EINVAL;
   if (n == 0) return 0;
   DeviceGuard g(device);
-  size_t smem = (size_t)CP_WARPS * (2 * (size_t)S * C + 32) * sizeof(float);
+  int warps = CP_WARPS;
+  size_t per_warp = (2 * (size_t)S * C + 32) * sizeof(float);
+  while (warps > 1 && warps * per_warp > 220 * 1024) warps >>= 1;
+  size_t smem = warps * per_warp;
   if (smem > 220 * 1024) return IBLN_EINVAL;
   auto kern = composite_fwd_kernel<SIMPLE>;
   IBLN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = (int)((220 * 1024) / (smem + 1024));
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 8) per_sm = 8;
-  kern<<<comp_grid(n, device, per_sm), CP_WARPS * 32, smem, (cudaStream_t)stream>>>(raw, z, d, noise, n, S, C, nc, sigm,
+  kern<<<comp_grid(n, device, per_sm, warps), warps * 32, smem, (cudaStream_t)stream>>>(raw, z, d, noise, n, S, C, nc, sigm,
                                                                                    weights, maps, maps_srgb, pre);
   IBLN_RETURN_LAST();
 }
@@ -391,13 +395,16 @@ extern "C" int ibln_composite_bwd(const float* raw, const float* z, const float*
   if (n == 0) return 0;
   DeviceGuard g(device);
   int Sp = (S + 31) & ~31;
-  size_t smem = (size_t)CP_WARPS * ((size_t)S * C + 3 * Sp + 32) * sizeof(float);
+  int warps = CP_WARPS;
+  size_t per_warp = ((size_t)S * C + 3 * Sp + 32) * sizeof(float);
+  while (warps > 1 && warps * per_warp > 220 * 1024) warps >>= 1;
+  size_t smem = warps * per_warp;
   if (smem > 220 * 1024) return IBLN_EINVAL;
   IBLN_CUDA(cudaFuncSetAttribute(composite_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = (int)((220 * 1024) / (smem + 1024));
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 8) per_sm = 8;
-  composite_bwd_kernel<<<comp_grid(n, device, per_sm), CP_WARPS * 32, smem, (cudaStream_t)stream>>>(
+  composite_bwd_kernel<<<comp_grid(n, device, per_sm, warps), warps * 32, smem, (cudaStream_t)stream>>>(
       raw, z, rays_d, noise, g_weights, g_maps, g_maps_srgb, n, S, C, nc, sigm, g_raw);
   IBLN_RETURN_LAST();
 }

@@ -6,12 +6,13 @@
 namespace ibln {
 
 // ---------------------------------------------------------------- stratified z
-// torch.linspace(0,1,S) is evaluated symmetrically (start+step*i in the lower half, end-step*(S-1-i)
-// in the upper half); reproduce that and keep every op un-contracted so z is bit-identical to
+// torch.linspace(0,1,S) is evaluated symmetrically: start+step*i in the lower half and
+// end-step*(S-1-i) as ONE fused multiply-add in the upper half (both its CPU and CUDA kernels contract
+// it); reproduce that and keep every other op un-contracted so z is bit-identical to
 // ibl_nerf_renderer.py:670-692.
 __device__ __forceinline__ float linspace01(int i, int s) {
   float step = __fdiv_rn(1.0f, (float)(s - 1));
-  return (i < s / 2) ? __fmul_rn(step, (float)i) : __fsub_rn(1.0f, __fmul_rn(step, (float)(s - 1 - i)));
+  return (i < s / 2) ? __fmul_rn(step, (float)i) : __fmaf_rn(-step, (float)(s - 1 - i), 1.0f);
 }
 __device__ __forceinline__ float z_lin(float nr, float fr, int i, int s, int lindisp) {
   float t = linspace01(i, s);

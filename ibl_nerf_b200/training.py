@@ -1,0 +1,114 @@
+"""One IBL-NeRF training iteration through the reference-facing API (what src/train.py:223-498 does per
+iteration for the kitchen config), plus ray-sharded data parallelism over NCCL.
+
+step = render_decomp (coarse + fine, full-IBL phase) -> phase-B losses -> backward -> gradient
+all-reduce (world > 1) -> Adam.  Rays are independent, so the batch is sharded across ranks with
+replicated weights; the only collective is one all-reduce of the flattened gradients.
+"""
+import torch
+import torch.distributed as dist
+
+from .mlp import get_embedder
+from .model import IBLNeRF, NetworkQuery
+from .renderer import render_decomp
+
+KITCHEN_ARCH = dict(D=8, W=256, input_ch=63, input_ch_views=27, skips=[4], coarse_radiance_number=3,
+                    is_color_independent_to_direction=False)
+
+
+def kitchen_render_kwargs(coarse, fine, lut, near, far, perturb=1.0):
+    """The effective kitchen settings as render_decomp keyword arguments."""
+    q = NetworkQuery(get_embedder(10)[0], get_embedder(4)[0], 1024 * 64)
+    return dict(network_fn=coarse, network_fine=fine, network_query_fn=q, N_samples=64, N_importance=128,
+                perturb=perturb, raw_noise_std=0., lindisp=False, use_viewdirs=True, white_bkgd=False, brdf_lut=lut,
+                epsilon=0.01, gamma_correct=True, lut_coefficient="F", use_radiance_linear=False,
+                target_normal_map_for_radiance_calculation="normal_map_from_depth_gradient_epsilon",
+                correct_depth_for_prefiltered_radiance_infer=True, use_gradient_for_incident_radiance=False,
+                coarse_radiance_number=3, near=near, far=far)
+
+
+def phase_b_loss(result, targets):
+    """src/train.py:322-432 with the kitchen betas: radiance + 3 coarse radiance + colour, fine and coarse nets."""
+    mse = torch.nn.functional.mse_loss
+    loss = 0.
+    for key, tk in (("radiance_map", "rgb"), ("radiance_map_1", "rgb_1"), ("radiance_map_2", "rgb_2"),
+                    ("radiance_map_3", "rgb_3"), ("color_map", "rgb")):
+        for suffix in ("", "0"):
+            if key + suffix in result:
+                loss = loss + mse(result[key + suffix], targets[tk])
+    return loss
+
+
+class TrainStep:
+    def __init__(self, device, lut, near=0.5, far=8.0, lr=5e-4, seed=0, precision=None, approximate_radiance=True,
+                 chunk=1 << 20):
+        torch.manual_seed(seed)
+        self.coarse = IBLNeRF(**KITCHEN_ARCH).to(device)
+        self.fine = IBLNeRF(**KITCHEN_ARCH).to(device)
+        self.coarse.precision = self.fine.precision = precision
+        self.params = list(self.coarse.parameters()) + list(self.fine.parameters())
+        self.opt = torch.optim.Adam([{'params': self.coarse.parameters(), 'name': 'coarse'},
+                                     {'params': self.fine.parameters(), 'name': 'fine'}], lr=lr, betas=(0.9, 0.999),
+                                    fused=True if torch.device(device).type == "cuda" else None)
+        self.kw = kitchen_render_kwargs(self.coarse, self.fine, lut, near, far)
+        self.approx = approximate_radiance
+        self.chunk = chunk
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        if self.world > 1:       # identical replicas
+            for p in self.params:
+                dist.broadcast(p.data, 0)
+
+    def step(self, rays_o, rays_d, targets):
+        res = render_decomp(0, 0, None, chunk=self.chunk, rays=(rays_o, rays_d), gt_values=targets,
+                            approximate_radiance=self.approx, **self.kw)
+        loss = phase_b_loss(res, targets)
+        self.opt.zero_grad(set_to_none=True)
+        loss.backward()
+        if self.world > 1:
+            self.allreduce_grads()
+        self.opt.step()
+        return loss
+
+    def allreduce_grads(self):
+        """One NCCL all-reduce over the flattened gradients of both networks (2 x 798 994 fp32); the mean over
+        ranks equals the gradient of the global-batch mean loss (equal shards)."""
+        grads = [p.grad for p in self.params if p.grad is not None]
+        flat = torch._utils._flatten_dense_tensors(grads)
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        flat.div_(self.world)
+        for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
+            g.copy_(f)
+
+
+def shard_rows(n, rank, world):
+    """Contiguous equal row tiles for tile-sharded inference / ray-sharded training."""
+    per = (n + world - 1) // world
+    lo = min(n, rank * per)
+    return lo, min(n, lo + per)
+
+
+def render_image_sharded(H, W, K, c2w, render_kwargs, chunk=1 << 16, approximate_radiance=True, keys=None):
+    """Tile-sharded full-image render: each rank renders a contiguous block of rows, no collective until the
+    final all_gather of the output maps."""
+    from .helper import get_rays
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rays_o, rays_d = get_rays(H, W, K, c2w)
+    rays_o, rays_d = rays_o.reshape(-1, 3), rays_d.reshape(-1, 3)
+    lo, hi = shard_rows(H * W, rank, world)
+    with torch.no_grad():
+        res = render_decomp(H, W, K, chunk=chunk, rays=(rays_o[lo:hi], rays_d[lo:hi]),
+                            approximate_radiance=approximate_radiance, **render_kwargs)
+    keys = keys or sorted(res.keys())
+    if world == 1:
+        return {k: res[k] for k in keys}
+    per = (H * W + world - 1) // world
+    out = {}
+    for k in keys:
+        v = res[k].reshape(hi - lo, -1)
+        pad = torch.zeros(per, v.shape[1], device=v.device, dtype=v.dtype)
+        pad[:hi - lo] = v
+        parts = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(parts, pad)
+        out[k] = torch.cat(parts, 0)[:H * W].reshape(H * W, *res[k].shape[1:])
+    return out

@@ -25,6 +25,30 @@ def close(a, b, rtol=1e-4, atol=1e-6, name=""):
                              (name, (~ok).sum().item(), ok.numel(), d[~ok].max().item(), b[~torch.isnan(b)].abs().max().item()))
 
 
+def close_frac(a, b, rtol, atol, frac=0.9, name=""):
+    """For quantities that are ill-conditioned by construction (epsilon finite-difference normals of a
+    high-frequency field and everything shaded from them): at least `frac` of the entries within tolerance
+    and a small median error."""
+    a, b = torch.as_tensor(a).detach().cpu(), torch.as_tensor(b).detach().cpu()
+    assert a.shape == b.shape, (name, a.shape, b.shape)
+    ok = torch.isclose(a, b, rtol=rtol, atol=atol, equal_nan=True)
+    got = ok.float().mean().item()
+    med = (a - b).abs().nan_to_num().median().item()
+    assert got >= frac and med <= atol, "%s: only %.1f%% within tolerance, median abs err %g" % (name, 100 * got, med)
+
+
+def close_mostly(a, b, rtol, atol, outlier_frac=2e-3, outlier_atol=1e-2, name=""):
+    """Tight tolerance for all but a tiny fraction of entries, which must still be within `outlier_atol`
+    (inverse-CDF samples in bins whose CDF increment sits at the reference's 1e-5 threshold amplify the
+    1-ulp summation-order differences of the CDF)."""
+    a, b = torch.as_tensor(a).detach().cpu(), torch.as_tensor(b).detach().cpu()
+    assert a.shape == b.shape, (name, a.shape, b.shape)
+    ok = torch.isclose(a, b, rtol=rtol, atol=atol, equal_nan=True)
+    bad = (~ok).float().mean().item()
+    worst = (a - b).abs().nan_to_num().max().item()
+    assert bad <= outlier_frac and worst <= outlier_atol, "%s: %.3f%% outliers, worst abs err %g" % (name, 100 * bad, worst)
+
+
 def rel_l2(a, b):
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
     return ((a - b).norm() / (b.norm() + 1e-30)).item()
