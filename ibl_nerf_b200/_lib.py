@@ -46,6 +46,10 @@ _PLAIN = {  # no device/stream tail
 }
 
 _lib = None
+# kernels launched per entry point (for bench.py's gpu_launches); default 1
+KERNELS_PER_CALL = {"ibln_sgemm_wgrad": 2, "ibln_mlp_pack_weights": 2}
+# bench.py sets this to {} to collect per-entry launch counts, CUDA-event pairs and algorithmic FLOPs
+PROFILE = None
 
 
 class IblnError(RuntimeError):
@@ -87,12 +91,22 @@ def ptr(t):
     return c_p(t.data_ptr())
 
 
-def call(name, device, *args):
+def call(name, device, *args, flops=0.0):
     """Invoke an entry point on torch's current stream of `device`; raise on a non-zero status."""
     h = lib()
     dev = device.index if device.index is not None else torch.cuda.current_device()
     stream = torch.cuda.current_stream(dev).cuda_stream
-    rc = getattr(h, name)(*args, dev, c_p(stream))
+    if PROFILE is not None:
+        rec = PROFILE.setdefault(name, {"launches": 0, "events": [], "flops": 0.0})
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(torch.cuda.current_stream(dev))
+        rc = getattr(h, name)(*args, dev, c_p(stream))
+        e1.record(torch.cuda.current_stream(dev))
+        rec["launches"] += KERNELS_PER_CALL.get(name, 1)
+        rec["events"].append((e0, e1))
+        rec["flops"] += flops
+    else:
+        rc = getattr(h, name)(*args, dev, c_p(stream))
     if rc != 0:
         raise IblnError("%s failed: %s (%d)" % (name, h.ibln_error_string(rc).decode(), rc))
 

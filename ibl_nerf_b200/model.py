@@ -14,6 +14,10 @@ from . import _lib, mlp
 from ._lib import call, f32c, ptr
 
 
+# algorithmic FLOP per point evaluation (unpadded GEMMs)
+FLOP_FULL, FLOP_SIGMA = 1591552, 982528
+
+
 class IBLNeRF(nn.Module):
     def __init__(self, D=8, W=256, input_ch=3, input_ch_views=3, skips=[4], use_illumination_feature_layer=False,
                  use_instance_feature_layer=False, coarse_radiance_number=0, is_color_independent_to_direction=True):
@@ -108,7 +112,7 @@ class IBLNeRF(nn.Module):
             out = torch.empty(n * s, 1 if viewdirs is None else 18, dtype=torch.float32, device=pts.device)
             d = f32c(viewdirs.detach()) if viewdirs is not None else torch.zeros(n, 3, device=pts.device)
             call("ibln_mlp_fwd", pts.device, ptr(self.packed_weights()), 0, ptr(pts), None, ptr(d), None, n, s, 0.0,
-                 int(viewdirs is None), ptr(out), None)
+                 int(viewdirs is None), ptr(out), None, flops=n * s * (FLOP_SIGMA if viewdirs is None else FLOP_FULL))
             return out.reshape(n, s, -1)
         flat = f32c(pts.reshape(-1, 3))
         x_pos = mlp.encode(flat, 10)
@@ -127,7 +131,7 @@ class IBLNeRF(nn.Module):
             o, d, zz = f32c(rays_o.detach()), f32c(rays_d.detach()), f32c(z.detach())
             out = torch.empty(n * s, 1 if sigma_only else 18, dtype=torch.float32, device=zz.device)
             call("ibln_mlp_fwd", zz.device, ptr(self.packed_weights()), 1, None, ptr(o), ptr(d), ptr(zz), n, s, 0.0,
-                 int(sigma_only), ptr(out), None)
+                 int(sigma_only), ptr(out), None, flops=n * s * (FLOP_SIGMA if sigma_only else FLOP_FULL))
             return out.reshape(n, s, -1)
         pts = rays_o[:, None, :] + rays_d[:, None, :] * z[..., None]
         return self.query_points(pts, None if sigma_only else rays_d)
@@ -139,7 +143,7 @@ class IBLNeRF(nn.Module):
             o, d, zz = f32c(rays_o.detach()), f32c(rays_d.detach()), f32c(z.detach())
             out = torch.empty(4 * n * s, dtype=torch.float32, device=zz.device)
             call("ibln_mlp_fwd", zz.device, ptr(self.packed_weights()), 2, None, ptr(o), ptr(d), ptr(zz), n, s, float(eps), 1,
-                 ptr(out), None)
+                 ptr(out), None, flops=4 * n * s * FLOP_SIGMA)
             return out.reshape(4 * n, s)
         from . import ops
         pts = ops.normal_eps_points(rays_o, rays_d, z, eps)
