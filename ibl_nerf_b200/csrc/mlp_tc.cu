@@ -14,211 +14,10 @@
 //               albedo, irradiance, radiance x4) as fp32 dot products on the un-rounded accumulators
 // Activations never leave the SM; a tile of 128 points flows through all layers while the other
 // slot's epilogue overlaps its MMAs.
-#include "tc_common.cuh"
+#include "mlp_tc.cuh"
 
 namespace ibln {
 namespace mlp {
-
-using namespace tc;
-
-constexpr int TILE_M = 128;
-constexpr int KB_BYTES = 16384;          // one K-block of an operand tile: [128 rows][64 bf16]
-constexpr int N_STAGES = 4;
-constexpr int ACT_BYTES = 4 * KB_BYTES;  // 256-wide activation tile
-constexpr int AUX_BYTES = KB_BYTES;      // positional / view-direction encoding tile
-constexpr int SMEM_ACT = 0;
-constexpr int SMEM_AUX = 2 * ACT_BYTES;
-constexpr int SMEM_RING = SMEM_AUX + 2 * AUX_BYTES;
-constexpr int SMEM_BAR = SMEM_RING + N_STAGES * KB_BYTES;
-constexpr int SMEM_TOTAL = SMEM_BAR + 256;
-constexpr int SMEM_REQUEST = SMEM_TOTAL + 1024;   // slack for manual 1024-byte alignment
-constexpr int N_THREADS = 320;
-
-// ---------------------------------------------------------------- step program
-enum Epi : int { EPI_RELU_ACT = 0, EPI_L7 = 1, EPI_AF = 2, EPI_FEATURE = 3, EPI_VIEW = 4, EPI_ADD01 = 5, EPI_ADD2 = 6 };
-
-struct Step {
-  int n;            // output columns (128 or 256)
-  int aux_first;    // first K-block read from the aux tile (positional encoding, 64 wide)
-  int kb_act;       // K-blocks read from the activation tile
-  int aux_last;     // last K-block read from the aux tile (view encoding, 32 wide)
-  int epi;
-  int chunk_base;   // index of the step's first weight chunk in the packed stream
-};
-
-constexpr int N_STEPS_FULL = 13;
-constexpr int N_STEPS_SIGMA = 8;
-__host__ __device__ constexpr Step step_at(int s) {
-  // chunks per step = (#K-blocks) * (n/128)
-  return s == 0 ? Step{256, 1, 0, 0, EPI_RELU_ACT, 0}
-       : s <= 4 ? Step{256, 0, 4, 0, EPI_RELU_ACT, 2 + 8 * (s - 1)}
-       : s == 5 ? Step{256, 1, 4, 0, EPI_RELU_ACT, 34}
-       : s == 6 ? Step{256, 0, 4, 0, EPI_RELU_ACT, 44}
-       : s == 7 ? Step{256, 0, 4, 0, EPI_L7, 52}
-       : s == 8 ? Step{256, 0, 4, 0, EPI_AF, 60}
-       : s == 9 ? Step{256, 0, 4, 0, EPI_FEATURE, 68}
-       : s == 10 ? Step{256, 0, 4, 1, EPI_VIEW, 76}
-       : s == 11 ? Step{256, 0, 4, 0, EPI_ADD01, 86}
-                 : Step{128, 0, 4, 0, EPI_ADD2, 94};
-}
-constexpr int N_CHUNKS = 98;
-
-// fp32 constant section that follows the chunk stream (offsets in floats)
-constexpr int C_BIAS = 0;                    // [13][256]
-constexpr int C_SR = C_BIAS + 13 * 256;      // float2[256] {w_sigma, w_rough}, then {b_sigma, b_rough, 0, 0}
-constexpr int C_AF = C_SR + 512 + 4;         // float4[256] albedo(3)|irradiance(1) weights, then 4 biases
-constexpr int C_RAD = C_AF + 1024 + 4;       // float4[256] radiance weights, then 3 biases + pad
-constexpr int C_ADD = C_RAD + 1024 + 4;      // float4[384] coarse radiance weights, then 3x(3 biases + pad)
-constexpr int C_TOTAL = C_ADD + 1536 + 12;
-constexpr int64_t PACKED_BYTES = (int64_t)N_CHUNKS * KB_BYTES + (int64_t)C_TOTAL * 4;
-
-// ---------------------------------------------------------------- weight packing
-struct ChunkSrc { int param; int ld; int n0; int k0; int kvalid; };
-struct PackArgs { const float* p[46]; };
-
-__host__ __device__ inline ChunkSrc chunk_src(int chunk) {
-  // state-dict order: positions_linears.i -> 2i, views 16, feature 18, sigma 20, albedo_f 22, albedo 24,
-  // rough 26, irr_f 28, irr 30, rad 32, add_f.k 34+2k, add.k 40+2k
-  for (int s = 0; s < N_STEPS_FULL; ++s) {
-    Step st = step_at(s);
-    int nh_count = st.n / 128;
-    int nkb = st.aux_first + st.kb_act + st.aux_last;
-    int local = chunk - st.chunk_base;
-    if (local < 0 || local >= nkb * nh_count) continue;
-    int kbi = local / nh_count, nh = local % nh_count;
-    ChunkSrc c;
-    c.n0 = nh * 128;
-    c.kvalid = 64;
-    if (s <= 7) { c.param = 2 * s; c.ld = (s == 0) ? 63 : (s == 5 ? 319 : 256); }
-    if (s == 0) { c.k0 = 0; c.kvalid = 63; }
-    else if (s == 5) { if (kbi == 0) { c.k0 = 0; c.kvalid = 63; } else c.k0 = 63 + 64 * (kbi - 1); }
-    else if (s <= 7) c.k0 = 64 * kbi;
-    else if (s == 8) { c.param = nh == 0 ? 22 : 28; c.ld = 256; c.n0 = 0; c.k0 = 64 * kbi; }
-    else if (s == 9) { c.param = 18; c.ld = 256; c.k0 = 64 * kbi; }
-    else if (s == 10) { c.param = 16; c.ld = 283; c.k0 = 64 * kbi; if (kbi == 4) c.kvalid = 27; }
-    else if (s == 11) { c.param = nh == 0 ? 34 : 36; c.ld = 256; c.n0 = 0; c.k0 = 64 * kbi; }
-    else { c.param = 38; c.ld = 256; c.n0 = 0; c.k0 = 64 * kbi; }
-    return c;
-  }
-  return ChunkSrc{0, 0, 0, 0, 0};
-}
-
-__global__ void pack_chunks_kernel(PackArgs a, uint8_t* __restrict__ packed) {
-  int chunk = blockIdx.x;
-  ChunkSrc c = chunk_src(chunk);
-  const float* W = a.p[c.param];
-  for (int e = threadIdx.x; e < 128 * 8; e += blockDim.x) {
-    int row = e >> 3, c16 = e & 7;
-    uint32_t w[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      int k = c16 * 8 + 2 * j;
-      float lo = (k < c.kvalid) ? W[(int64_t)(c.n0 + row) * c.ld + c.k0 + k] : 0.f;
-      float hi = (k + 1 < c.kvalid) ? W[(int64_t)(c.n0 + row) * c.ld + c.k0 + k + 1] : 0.f;
-      w[j] = pack_bf16x2(lo, hi);
-    }
-    *reinterpret_cast<uint4*>(packed + (size_t)chunk * KB_BYTES + swz_offset(row, c16)) = make_uint4(w[0], w[1], w[2], w[3]);
-  }
-}
-
-__global__ void pack_consts_kernel(PackArgs a, float* __restrict__ cst) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= C_TOTAL) return;
-  float v = 0.f;
-  if (i < C_SR) {
-    int s = i / 256, col = i % 256;
-    if (s <= 7) v = a.p[2 * s + 1][col];
-    else if (s == 8) v = col < 128 ? a.p[23][col] : a.p[29][col - 128];
-    else if (s == 9) v = a.p[19][col];
-    else if (s == 10) v = a.p[17][col];
-    else if (s == 11) v = col < 128 ? a.p[35][col] : a.p[37][col - 128];
-    else v = col < 128 ? a.p[39][col] : 0.f;
-  } else if (i < C_AF) {
-    int j = i - C_SR;
-    if (j < 512) v = (j & 1) ? a.p[26][j >> 1] : a.p[20][j >> 1];
-    else if (j == 512) v = a.p[21][0];
-    else if (j == 513) v = a.p[27][0];
-  } else if (i < C_RAD) {
-    int j = i - C_AF;
-    if (j < 1024) {
-      int col = j >> 2, q = j & 3;
-      if (col < 128) v = q < 3 ? a.p[24][q * 128 + col] : 0.f;
-      else v = q == 0 ? a.p[30][col - 128] : 0.f;
-    } else {
-      int q = j - 1024;
-      v = q < 3 ? a.p[25][q] : a.p[31][0];
-    }
-  } else if (i < C_ADD) {
-    int j = i - C_RAD;
-    if (j < 1024) { int col = j >> 2, q = j & 3; v = q < 3 ? a.p[32][q * 256 + col] : 0.f; }
-    else { int q = j - 1024; v = q < 3 ? a.p[33][q] : 0.f; }
-  } else {
-    int j = i - C_ADD;
-    if (j < 1536) { int col = j >> 2, q = j & 3; int k = col / 128, cc = col % 128; v = q < 3 ? a.p[40 + 2 * k][q * 128 + cc] : 0.f; }
-    else { int q = j - 1536; int k = q / 4, c = q % 4; v = c < 3 ? a.p[41 + 2 * k][c] : 0.f; }
-  }
-  cst[i] = v;
-}
-
-// ---------------------------------------------------------------- point generation + encodings
-struct PointGen {
-  const float* pts; const float* o; const float* d; const float* z;
-  long long n_rays; int S; float eps; int mode; long long P;
-};
-
-__device__ __forceinline__ void gen_point(const PointGen& g, long long p, float x[3], float dir[3]) {
-  long long per = g.n_rays * g.S;
-  int q = 0;
-  long long rem = p;
-  if (g.mode == 2) { q = (int)(p / per); rem = p % per; }
-  long long ray = rem / g.S;
-  dir[0] = g.d[3 * ray]; dir[1] = g.d[3 * ray + 1]; dir[2] = g.d[3 * ray + 2];
-  if (g.mode == 0) { x[0] = g.pts[3 * p]; x[1] = g.pts[3 * p + 1]; x[2] = g.pts[3 * p + 2]; return; }
-  float zi = g.z[rem];
-#pragma unroll
-  for (int c = 0; c < 3; ++c) x[c] = __fadd_rn(g.o[3 * ray + c], __fmul_rn(dir[c], zi));
-  if (g.mode == 2) {   // normal_from_depth.py:143-156
-    float right[3] = {-dir[2], 0.f, dir[0]};
-    float up[3];
-    up[0] = __fsub_rn(__fmul_rn(right[1], dir[2]), __fmul_rn(right[2], dir[1]));
-    up[1] = __fsub_rn(__fmul_rn(right[2], dir[0]), __fmul_rn(right[0], dir[2]));
-    up[2] = __fsub_rn(__fmul_rn(right[0], dir[1]), __fmul_rn(right[1], dir[0]));
-    const float* v = (q < 2) ? right : up;
-    float sgn = (q & 1) ? -1.f : 1.f;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) x[c] = __fadd_rn(x[c], sgn * __fmul_rn(g.eps, v[c]));
-  }
-}
-
-// Write [x, sin(2^k x), cos(2^k x)]_{k<L} (zero padded to NCH*8) as bf16 into row `row` of a swizzled
-// tile.  sin/cos of the base angle are exact-ish (sincosf); higher octaves by the double-angle
-// recurrence (abs. error <= 2^k * 1e-7, far below bf16 resolution).
-template <int L, int NCH>
-__device__ __forceinline__ void write_encoding(uint8_t* tile, int row, const float x[3]) {
-  float e[NCH * 8];
-#pragma unroll
-  for (int i = 0; i < NCH * 8; ++i) e[i] = 0.f;
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    e[c] = x[c];
-    float s, co;
-    sincosf(x[c], &s, &co);
-#pragma unroll
-    for (int k = 0; k < L; ++k) {
-      e[3 + 6 * k + c] = s;
-      e[3 + 6 * k + 3 + c] = co;
-      float s2 = 2.f * s * co;
-      co = 1.f - 2.f * s * s;
-      s = s2;
-    }
-  }
-#pragma unroll
-  for (int ch = 0; ch < NCH; ++ch) {
-    uint4 v = make_uint4(pack_bf16x2(e[8 * ch], e[8 * ch + 1]), pack_bf16x2(e[8 * ch + 2], e[8 * ch + 3]),
-                         pack_bf16x2(e[8 * ch + 4], e[8 * ch + 5]), pack_bf16x2(e[8 * ch + 6], e[8 * ch + 7]));
-    *reinterpret_cast<uint4*>(tile + swz_offset(row, ch)) = v;
-  }
-}
 
 // ---------------------------------------------------------------- the fused forward kernel
 struct FwdParams {
@@ -226,6 +25,7 @@ struct FwdParams {
   PointGen gen;
   int sigma_only;
   float* out;                // [P] or [P,18]
+  uint8_t* saved;            // activation stash (SV_BYTES per tile) or nullptr
   long long n_tiles;
 };
 
@@ -329,7 +129,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_fwd_kernel(FwdParams prm) {
     const int row = quarter * 32 + lane;
     uint8_t* act = smem + SMEM_ACT + slot * ACT_BYTES;
     uint8_t* aux = smem + SMEM_AUX + slot * AUX_BYTES;
-    const float* cst = reinterpret_cast<const float*>(prm.packed + (size_t)N_CHUNKS * KB_BYTES);
+    const float* cst = reinterpret_cast<const float*>(prm.packed + PACKED_CONST_OFF);
     const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + slot * 256;
     uint32_t acc_phase = 0;
     for (long long k = slot; k < my_tiles; k += 2) {
@@ -338,7 +138,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_fwd_kernel(FwdParams prm) {
       const bool valid = p < prm.gen.P;
       float x[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 0.f};
       if (valid) gen_point(prm.gen, p, x, dir);
-      write_encoding<10, 8>(aux, row, x);
+      uint8_t* rec = prm.saved ? prm.saved + (size_t)tile * SV_BYTES : nullptr;
+      write_encoding<10, 8>(aux, row, x, rec ? rec + (size_t)SV_PE * KB_BYTES : nullptr);
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();
@@ -359,6 +160,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_fwd_kernel(FwdParams prm) {
         const float* bias = cst + C_BIAS + s * 256;
         const bool write_act = (st.epi == EPI_RELU_ACT) || (st.epi == EPI_FEATURE) || (st.epi == EPI_VIEW) ||
                                (st.epi == EPI_L7 && !prm.sigma_only);
+        // stash destination of this step's output tile and its relu-mask slot
+        const int sv_blk = s <= 7 ? SV_H(s) : s == 8 ? SV_AF : s == 9 ? SV_FEAT : s == 10 ? SV_HV : s == 11 ? SV_ADDF : SV_ADDF + 4;
+        const int sv_mask = s <= 7 ? s : s == 8 ? 8 : s == 10 ? 9 : s == 11 ? 10 : s == 12 ? 11 : -1;
+        uint32_t* mask_row = (rec && sv_mask >= 0)
+                                 ? reinterpret_cast<uint32_t*>(rec + (size_t)SV_MASK * KB_BYTES + sv_mask * 4096 + row * 32) : nullptr;
         for (int cc = 0; cc < st.n / 32; ++cc) {
           uint32_t v[32];
           tmem_ld32(t_lane + cc * 32, v);
@@ -372,18 +178,25 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_fwd_kernel(FwdParams prm) {
             h[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) + b.z;
             h[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) + b.w;
           }
+          if (mask_row != nullptr) {        // bit j = (pre-activation >= 0), gathered from the sign bits
+            uint32_t m = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) m = (m >> 1) | (__float_as_uint(h[j]) & 0x80000000u);
+            mask_row[cc] = ~m;
+          }
           if (st.epi != EPI_FEATURE) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) h[j] = fmaxf(h[j], 0.f);
           }
-          if (write_act) {
+          if (write_act || rec != nullptr) {
             const int kb = cc >> 1;                    // 64 columns per K-block
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const int c16 = (cc & 1) * 4 + q;
               uint4 pk = make_uint4(pack_bf16x2(h[8 * q], h[8 * q + 1]), pack_bf16x2(h[8 * q + 2], h[8 * q + 3]),
                                     pack_bf16x2(h[8 * q + 4], h[8 * q + 5]), pack_bf16x2(h[8 * q + 6], h[8 * q + 7]));
-              *reinterpret_cast<uint4*>(act + kb * KB_BYTES + swz_offset(row, c16)) = pk;
+              if (write_act) *reinterpret_cast<uint4*>(act + kb * KB_BYTES + swz_offset(row, c16)) = pk;
+              if (rec != nullptr) *reinterpret_cast<uint4*>(rec + (size_t)(sv_blk + kb) * KB_BYTES + swz_offset(row, c16)) = pk;
             }
           }
           if (st.epi == EPI_L7) {
@@ -414,7 +227,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_fwd_kernel(FwdParams prm) {
             else { o_rad[3][0] += r0; o_rad[3][1] += r1; o_rad[3][2] += r2; }
           }
         }
-        if (st.epi == EPI_FEATURE) write_encoding<4, 4>(aux, row, dir);   // view encoding for the next step
+        if (st.epi == EPI_FEATURE) write_encoding<4, 4>(aux, row, dir, rec ? rec + (size_t)SV_DE * KB_BYTES : nullptr);   // view encoding for the next step
         if (s + 1 < n_steps) {
           fence_proxy_async();
           tc_fence_before();
@@ -530,21 +343,23 @@ extern "C" int ibln_mlp_pack_weights(const float* const* params_host, void* pack
   PackArgs a;
   for (int i = 0; i < 46; ++i) { if (!params_host[i]) return IBLN_EINVAL; a.p[i] = params_host[i]; }
   pack_chunks_kernel<<<N_CHUNKS, 256, 0, (cudaStream_t)stream>>>(a, (uint8_t*)packed);
-  pack_consts_kernel<<<(C_TOTAL + 255) / 256, 256, 0, (cudaStream_t)stream>>>(a, (float*)((uint8_t*)packed + (size_t)N_CHUNKS * KB_BYTES));
+  pack_consts_kernel<<<(C_TOTAL + 255) / 256, 256, 0, (cudaStream_t)stream>>>(a, (float*)((uint8_t*)packed + PACKED_CONST_OFF));
+  int rc = launch_pack_bwd(a, (uint8_t*)packed, (cudaStream_t)stream);
+  if (rc != 0) return rc;
   IBLN_RETURN_LAST();
 }
 
-extern "C" int64_t ibln_mlp_saved_bytes(int64_t n_pts) { (void)n_pts; return 0; }
-extern "C" int64_t ibln_mlp_bwd_workspace_bytes(int64_t n_pts) { (void)n_pts; return 0; }
+extern "C" int64_t ibln_mlp_saved_bytes(int64_t n_pts) { return ((n_pts + TILE_M - 1) / TILE_M) * SV_BYTES; }
 
 extern "C" int ibln_mlp_fwd(const void* packed, int mode, const float* pts, const float* rays_o, const float* rays_d,
                             const float* z, int64_t n_rays, int n_samples, float eps, int sigma_only, float* out,
                             void* saved, int device, void* stream) {
-  (void)saved;
   if (!packed || !out || !rays_d || n_rays < 0 || n_samples < 1 || mode < 0 || mode > 2) return IBLN_EINVAL;
   if (mode == 0 && !pts) return IBLN_EINVAL;
   if (mode != 0 && (!rays_o || !z)) return IBLN_EINVAL;
   if (mode == 2 && !sigma_only) return IBLN_EINVAL;
+  if (saved && sigma_only) return IBLN_EINVAL;
+  if (saved && (reinterpret_cast<uintptr_t>(saved) & 15) != 0) return IBLN_EINVAL;
   if ((reinterpret_cast<uintptr_t>(packed) & 15) != 0) return IBLN_EINVAL;
   if (n_rays == 0) return 0;
   DeviceGuard g(device);
@@ -555,17 +370,12 @@ extern "C" int ibln_mlp_fwd(const void* packed, int mode, const float* pts, cons
   prm.gen.P = n_rays * n_samples * (mode == 2 ? 4 : 1);
   prm.sigma_only = sigma_only;
   prm.out = out;
+  prm.saved = (uint8_t*)saved;
   prm.n_tiles = (prm.gen.P + TILE_M - 1) / TILE_M;
   IBLN_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_REQUEST));
   long long grid = prm.n_tiles < (long long)num_sms(device) ? prm.n_tiles : (long long)num_sms(device);
   mlp_fwd_kernel<<<(unsigned)grid, N_THREADS, SMEM_REQUEST, (cudaStream_t)stream>>>(prm);
   IBLN_RETURN_LAST();
-}
-
-extern "C" int ibln_mlp_bwd(const void* packed, const void* saved, const float* g_out, int64_t n_pts, float* flat_grad,
-                            void* workspace, int device, void* stream) {
-  (void)packed; (void)saved; (void)g_out; (void)n_pts; (void)flat_grad; (void)workspace; (void)device; (void)stream;
-  return IBLN_EINVAL;   // tensor-core backward: see mlp_tc_bwd.cu (not linked yet)
 }
 
 extern "C" int ibln_umma_selftest(const float* a, const float* b, float* d, int n, int k, int variant, int device, void* stream) {

@@ -1,0 +1,241 @@
+// Shared definitions of the tensor-core MLP kernels (forward: mlp_tc.cu, backward: mlp_tc_bwd.cu):
+// tile geometry, the GEMM step programs, the packed weight image layout, point generation and the
+// positional-encoding tile writer.
+#pragma once
+#include "tc_common.cuh"
+
+namespace ibln {
+namespace mlp {
+
+using namespace tc;
+
+constexpr int TILE_M = 128;
+constexpr int KB_BYTES = 16384;          // one K-block of an operand tile: [128 rows][64 bf16]
+constexpr int N_STAGES = 4;
+constexpr int ACT_BYTES = 4 * KB_BYTES;  // 256-wide activation tile
+constexpr int AUX_BYTES = KB_BYTES;      // positional / view-direction encoding tile
+constexpr int SMEM_ACT = 0;
+constexpr int SMEM_AUX = 2 * ACT_BYTES;
+constexpr int SMEM_RING = SMEM_AUX + 2 * AUX_BYTES;
+constexpr int SMEM_BAR = SMEM_RING + N_STAGES * KB_BYTES;
+constexpr int SMEM_TOTAL = SMEM_BAR + 256;
+constexpr int SMEM_REQUEST = SMEM_TOTAL + 1024;   // slack for manual 1024-byte alignment
+constexpr int N_THREADS = 320;
+
+// ---------------------------------------------------------------- step program
+enum Epi : int { EPI_RELU_ACT = 0, EPI_L7 = 1, EPI_AF = 2, EPI_FEATURE = 3, EPI_VIEW = 4, EPI_ADD01 = 5, EPI_ADD2 = 6 };
+
+struct Step {
+  int n;            // output columns (128 or 256)
+  int aux_first;    // first K-block read from the aux tile (positional encoding, 64 wide)
+  int kb_act;       // K-blocks read from the activation tile
+  int aux_last;     // last K-block read from the aux tile (view encoding, 32 wide)
+  int epi;
+  int chunk_base;   // index of the step's first weight chunk in the packed stream
+};
+
+constexpr int N_STEPS_FULL = 13;
+constexpr int N_STEPS_SIGMA = 8;
+__host__ __device__ constexpr Step step_at(int s) {
+  // chunks per step = (#K-blocks) * (n/128)
+  return s == 0 ? Step{256, 1, 0, 0, EPI_RELU_ACT, 0}
+       : s <= 4 ? Step{256, 0, 4, 0, EPI_RELU_ACT, 2 + 8 * (s - 1)}
+       : s == 5 ? Step{256, 1, 4, 0, EPI_RELU_ACT, 34}
+       : s == 6 ? Step{256, 0, 4, 0, EPI_RELU_ACT, 44}
+       : s == 7 ? Step{256, 0, 4, 0, EPI_L7, 52}
+       : s == 8 ? Step{256, 0, 4, 0, EPI_AF, 60}
+       : s == 9 ? Step{256, 0, 4, 0, EPI_FEATURE, 68}
+       : s == 10 ? Step{256, 0, 4, 1, EPI_VIEW, 76}
+       : s == 11 ? Step{256, 0, 4, 0, EPI_ADD01, 86}
+                 : Step{128, 0, 4, 0, EPI_ADD2, 94};
+}
+constexpr int N_CHUNKS = 98;
+
+// fp32 constant section that follows the chunk stream (offsets in floats)
+constexpr int C_BIAS = 0;                    // [13][256]
+constexpr int C_SR = C_BIAS + 13 * 256;      // float2[256] {w_sigma, w_rough}, then {b_sigma, b_rough, 0, 0}
+constexpr int C_AF = C_SR + 512 + 4;         // float4[256] albedo(3)|irradiance(1) weights, then 4 biases
+constexpr int C_RAD = C_AF + 1024 + 4;       // float4[256] radiance weights, then 3 biases + pad
+constexpr int C_ADD = C_RAD + 1024 + 4;      // float4[384] coarse radiance weights, then 3x(3 biases + pad)
+constexpr int C_TOTAL = C_ADD + 1536 + 12;
+constexpr int N_CHUNKS_BWD = 92;             // transposed weight chunks of the dgrad chain (mlp_tc_bwd.cu)
+constexpr int64_t PACKED_CONST_OFF = (int64_t)N_CHUNKS * KB_BYTES;
+constexpr int64_t PACKED_BWD_OFF = PACKED_CONST_OFF + (int64_t)C_TOTAL * 4;
+constexpr int64_t PACKED_BYTES = PACKED_BWD_OFF + (int64_t)N_CHUNKS_BWD * KB_BYTES;
+static_assert(PACKED_BWD_OFF % 16 == 0, "bwd chunk stream must stay 16-byte aligned");
+
+// ---------------------------------------------------------------- activation stash (forward -> backward)
+// One record per 128-point tile, in units of 16 KB operand blocks ([128 rows][64 bf16], swizzled exactly
+// like the shared-memory tiles so the wgrad kernel can bulk-copy them straight into UMMA operands).
+constexpr int SV_PE = 0;                     // positional encoding (1 block)
+__host__ __device__ constexpr int SV_H(int l) { return 1 + 4 * l; }   // h0..h7, 4 blocks each
+constexpr int SV_AF = 33;                    // relu(albedo_feature | irradiance_feature)
+constexpr int SV_FEAT = 37;                  // feature_linear output (no relu)
+constexpr int SV_DE = 41;                    // view-direction encoding (32 of 64 columns used)
+constexpr int SV_HV = 42;                    // relu(views_linears.0)
+constexpr int SV_ADDF = 46;                  // relu(additional_radiance_feature_linear.{0,1,2}), 6 blocks
+constexpr int SV_MASK = 52;                  // relu bit masks: 12 x [128 rows][8 words] (h0..h7, AF, HV, ADD01, ADD2)
+constexpr int SV_BLOCKS = 55;
+constexpr int64_t SV_BYTES = (int64_t)SV_BLOCKS * KB_BYTES;
+// gradient record per tile written by the dgrad kernel for the wgrad kernel
+constexpr int DY_ADDF01 = 0, DY_ADDF2 = 4, DY_VIEW = 6, DY_FEAT = 10, DY_AF = 14;
+__host__ __device__ constexpr int DY_H(int l) { return 18 + 4 * (7 - l); }   // dY_7 .. dY_0
+constexpr int DY_G = 50;                     // g_raw as a bf16 [128][64] tile (18 columns used)
+constexpr int DY_BLOCKS = 51;
+constexpr int64_t DY_BYTES = (int64_t)DY_BLOCKS * KB_BYTES;
+
+// ---------------------------------------------------------------- weight packing
+struct ChunkSrc { int param; int ld; int n0; int k0; int kvalid; };
+struct PackArgs { const float* p[46]; };
+
+__host__ __device__ inline ChunkSrc chunk_src(int chunk) {
+  // state-dict order: positions_linears.i -> 2i, views 16, feature 18, sigma 20, albedo_f 22, albedo 24,
+  // rough 26, irr_f 28, irr 30, rad 32, add_f.k 34+2k, add.k 40+2k
+  for (int s = 0; s < N_STEPS_FULL; ++s) {
+    Step st = step_at(s);
+    int nh_count = st.n / 128;
+    int nkb = st.aux_first + st.kb_act + st.aux_last;
+    int local = chunk - st.chunk_base;
+    if (local < 0 || local >= nkb * nh_count) continue;
+    int kbi = local / nh_count, nh = local % nh_count;
+    ChunkSrc c;
+    c.n0 = nh * 128;
+    c.kvalid = 64;
+    if (s <= 7) { c.param = 2 * s; c.ld = (s == 0) ? 63 : (s == 5 ? 319 : 256); }
+    if (s == 0) { c.k0 = 0; c.kvalid = 63; }
+    else if (s == 5) { if (kbi == 0) { c.k0 = 0; c.kvalid = 63; } else c.k0 = 63 + 64 * (kbi - 1); }
+    else if (s <= 7) c.k0 = 64 * kbi;
+    else if (s == 8) { c.param = nh == 0 ? 22 : 28; c.ld = 256; c.n0 = 0; c.k0 = 64 * kbi; }
+    else if (s == 9) { c.param = 18; c.ld = 256; c.k0 = 64 * kbi; }
+    else if (s == 10) { c.param = 16; c.ld = 283; c.k0 = 64 * kbi; if (kbi == 4) c.kvalid = 27; }
+    else if (s == 11) { c.param = nh == 0 ? 34 : 36; c.ld = 256; c.n0 = 0; c.k0 = 64 * kbi; }
+    else { c.param = 38; c.ld = 256; c.n0 = 0; c.k0 = 64 * kbi; }
+    return c;
+  }
+  return ChunkSrc{0, 0, 0, 0, 0};
+}
+
+static __global__ void pack_chunks_kernel(PackArgs a, uint8_t* __restrict__ packed) {
+  int chunk = blockIdx.x;
+  ChunkSrc c = chunk_src(chunk);
+  const float* W = a.p[c.param];
+  for (int e = threadIdx.x; e < 128 * 8; e += blockDim.x) {
+    int row = e >> 3, c16 = e & 7;
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int k = c16 * 8 + 2 * j;
+      float lo = (k < c.kvalid) ? W[(int64_t)(c.n0 + row) * c.ld + c.k0 + k] : 0.f;
+      float hi = (k + 1 < c.kvalid) ? W[(int64_t)(c.n0 + row) * c.ld + c.k0 + k + 1] : 0.f;
+      w[j] = pack_bf16x2(lo, hi);
+    }
+    *reinterpret_cast<uint4*>(packed + (size_t)chunk * KB_BYTES + swz_offset(row, c16)) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+static __global__ void pack_consts_kernel(PackArgs a, float* __restrict__ cst) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C_TOTAL) return;
+  float v = 0.f;
+  if (i < C_SR) {
+    int s = i / 256, col = i % 256;
+    if (s <= 7) v = a.p[2 * s + 1][col];
+    else if (s == 8) v = col < 128 ? a.p[23][col] : a.p[29][col - 128];
+    else if (s == 9) v = a.p[19][col];
+    else if (s == 10) v = a.p[17][col];
+    else if (s == 11) v = col < 128 ? a.p[35][col] : a.p[37][col - 128];
+    else v = col < 128 ? a.p[39][col] : 0.f;
+  } else if (i < C_AF) {
+    int j = i - C_SR;
+    if (j < 512) v = (j & 1) ? a.p[26][j >> 1] : a.p[20][j >> 1];
+    else if (j == 512) v = a.p[21][0];
+    else if (j == 513) v = a.p[27][0];
+  } else if (i < C_RAD) {
+    int j = i - C_AF;
+    if (j < 1024) {
+      int col = j >> 2, q = j & 3;
+      if (col < 128) v = q < 3 ? a.p[24][q * 128 + col] : 0.f;
+      else v = q == 0 ? a.p[30][col - 128] : 0.f;
+    } else {
+      int q = j - 1024;
+      v = q < 3 ? a.p[25][q] : a.p[31][0];
+    }
+  } else if (i < C_ADD) {
+    int j = i - C_RAD;
+    if (j < 1024) { int col = j >> 2, q = j & 3; v = q < 3 ? a.p[32][q * 256 + col] : 0.f; }
+    else { int q = j - 1024; v = q < 3 ? a.p[33][q] : 0.f; }
+  } else {
+    int j = i - C_ADD;
+    if (j < 1536) { int col = j >> 2, q = j & 3; int k = col / 128, cc = col % 128; v = q < 3 ? a.p[40 + 2 * k][q * 128 + cc] : 0.f; }
+    else { int q = j - 1536; int k = q / 4, c = q % 4; v = c < 3 ? a.p[41 + 2 * k][c] : 0.f; }
+  }
+  cst[i] = v;
+}
+
+// defined in mlp_tc_bwd.cu: packs the transposed (dgrad) weight chunk stream at packed + PACKED_BWD_OFF
+int launch_pack_bwd(const PackArgs& a, uint8_t* packed, cudaStream_t stream);
+
+// ---------------------------------------------------------------- point generation + encodings
+struct PointGen {
+  const float* pts; const float* o; const float* d; const float* z;
+  long long n_rays; int S; float eps; int mode; long long P;
+};
+
+__device__ __forceinline__ void gen_point(const PointGen& g, long long p, float x[3], float dir[3]) {
+  long long per = g.n_rays * g.S;
+  int q = 0;
+  long long rem = p;
+  if (g.mode == 2) { q = (int)(p / per); rem = p % per; }
+  long long ray = rem / g.S;
+  dir[0] = g.d[3 * ray]; dir[1] = g.d[3 * ray + 1]; dir[2] = g.d[3 * ray + 2];
+  if (g.mode == 0) { x[0] = g.pts[3 * p]; x[1] = g.pts[3 * p + 1]; x[2] = g.pts[3 * p + 2]; return; }
+  float zi = g.z[rem];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) x[c] = __fadd_rn(g.o[3 * ray + c], __fmul_rn(dir[c], zi));
+  if (g.mode == 2) {   // normal_from_depth.py:143-156
+    float right[3] = {-dir[2], 0.f, dir[0]};
+    float up[3];
+    up[0] = __fsub_rn(__fmul_rn(right[1], dir[2]), __fmul_rn(right[2], dir[1]));
+    up[1] = __fsub_rn(__fmul_rn(right[2], dir[0]), __fmul_rn(right[0], dir[2]));
+    up[2] = __fsub_rn(__fmul_rn(right[0], dir[1]), __fmul_rn(right[1], dir[0]));
+    const float* v = (q < 2) ? right : up;
+    float sgn = (q & 1) ? -1.f : 1.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) x[c] = __fadd_rn(x[c], sgn * __fmul_rn(g.eps, v[c]));
+  }
+}
+
+// Write [x, sin(2^k x), cos(2^k x)]_{k<L} (zero padded to NCH*8) as bf16 into row `row` of a swizzled
+// tile.  sin/cos of the base angle are exact-ish (sincosf); higher octaves by the double-angle
+// recurrence (abs. error <= 2^k * 1e-7, far below bf16 resolution).
+template <int L, int NCH>
+__device__ __forceinline__ void write_encoding(uint8_t* tile, int row, const float x[3], uint8_t* gtile = nullptr) {
+  float e[NCH * 8];
+#pragma unroll
+  for (int i = 0; i < NCH * 8; ++i) e[i] = 0.f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    e[c] = x[c];
+    float s, co;
+    sincosf(x[c], &s, &co);
+#pragma unroll
+    for (int k = 0; k < L; ++k) {
+      e[3 + 6 * k + c] = s;
+      e[3 + 6 * k + 3 + c] = co;
+      float s2 = 2.f * s * co;
+      co = 1.f - 2.f * s * s;
+      s = s2;
+    }
+  }
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    uint4 v = make_uint4(pack_bf16x2(e[8 * ch], e[8 * ch + 1]), pack_bf16x2(e[8 * ch + 2], e[8 * ch + 3]),
+                         pack_bf16x2(e[8 * ch + 4], e[8 * ch + 5]), pack_bf16x2(e[8 * ch + 6], e[8 * ch + 7]));
+    *reinterpret_cast<uint4*>(tile + swz_offset(row, ch)) = v;
+    if (gtile != nullptr) *reinterpret_cast<uint4*>(gtile + swz_offset(row, ch)) = v;
+  }
+}
+
+
+}  // namespace mlp
+}  // namespace ibln

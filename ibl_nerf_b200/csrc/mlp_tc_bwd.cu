@@ -1,0 +1,642 @@
+// Tensor-core backward of the IBLNeRF MLP (north-star subsystem 3, gradients).
+//
+//  dgrad kernel : same warp-specialised structure as the forward kernel (bulk-TMA weight producer,
+//                 single-thread tcgen05.mma issuer, two ping-pong tile slots with 4 epilogue warps
+//                 each).  Walks the layers in reverse: dX = dY * W as M=128 x N=256 GEMMs against
+//                 the TRANSPOSED packed weight stream, applies the relu bit masks stashed by the
+//                 forward pass, keeps the running gradient tile in shared memory as the next A
+//                 operand, and writes every dY tile (bf16, operand layout) for the wgrad kernel.
+//                 The 18-channel head gradients enter as fp32 rank-<=3 updates on the CUDA cores.
+//  wgrad kernel : dW[out,in] += sum_points dY[pt,out] * X[pt,in] as a split-K tcgen05 GEMM whose
+//                 operands are the stashed tiles read as MN-major UMMA operands (no transposes);
+//                 fp32 accumulators live in TMEM for the whole K loop (all points of the CTA) and
+//                 are flushed once with red.global.add.f32 into the flat gradient image.
+#include "mlp_tc.cuh"
+
+namespace ibln {
+namespace mlp {
+
+// ---------------------------------------------------------------- dgrad step program
+constexpr int N_STEPS_BWD = 12;
+struct BStep { int nkb; int accumulate; int chunk_base; };
+__host__ __device__ constexpr BStep bstep_at(int t) {
+  return t == 0 ? BStep{4, 0, 0} : t == 1 ? BStep{2, 1, 8} : t == 4 ? BStep{4, 1, 28} : BStep{4, 0, 12 + 8 * (t - 2)};
+}
+static_assert(bstep_at(11).chunk_base + 8 == N_CHUNKS_BWD, "bwd chunk table");
+
+// chunk element (n, k) = W_src[row0 + k][col0 + n]
+struct BChunkSrc { int param; int ld; int row0; int col0; };
+__host__ __device__ inline BChunkSrc bchunk_src(int chunk) {
+  for (int t = 0; t < N_STEPS_BWD; ++t) {
+    BStep st = bstep_at(t);
+    int local = chunk - st.chunk_base;
+    if (local < 0 || local >= st.nkb * 2) continue;
+    int j = local >> 1, nh = local & 1;
+    BChunkSrc c;
+    c.col0 = nh * 128;
+    c.ld = 256;
+    c.row0 = 64 * j;
+    if (t == 0) { c.param = 34 + 2 * (j >> 1); c.row0 = 64 * (j & 1); }
+    else if (t == 1) c.param = 38;
+    else if (t == 2) { c.param = 16; c.ld = 283; }
+    else if (t == 3) c.param = 18;
+    else if (t == 4) { c.param = j < 2 ? 22 : 28; c.row0 = 64 * (j & 1); }
+    else {
+      int l = 12 - t;
+      c.param = 2 * l;
+      if (l == 5) { c.ld = 319; c.col0 += 63; }
+    }
+    return c;
+  }
+  return BChunkSrc{0, 0, 0, 0};
+}
+
+static __global__ void pack_bwd_chunks_kernel(PackArgs a, uint8_t* __restrict__ out) {
+  int chunk = blockIdx.x;
+  BChunkSrc c = bchunk_src(chunk);
+  const float* W = a.p[c.param];
+  for (int e = threadIdx.x; e < 128 * 8; e += blockDim.x) {
+    int n = e & 127, c16 = e >> 7;        // consecutive threads -> consecutive n (coalesced reads of W rows)
+    uint32_t w[4];
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      int k = c16 * 8 + 2 * jj;
+      float lo = W[(int64_t)(c.row0 + k) * c.ld + c.col0 + n];
+      float hi = W[(int64_t)(c.row0 + k + 1) * c.ld + c.col0 + n];
+      w[jj] = pack_bf16x2(lo, hi);
+    }
+    *reinterpret_cast<uint4*>(out + (size_t)chunk * KB_BYTES + swz_offset(n, c16)) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+int launch_pack_bwd(const PackArgs& a, uint8_t* packed, cudaStream_t stream) {
+  pack_bwd_chunks_kernel<<<N_CHUNKS_BWD, 256, 0, stream>>>(a, packed + PACKED_BWD_OFF);
+  return (int)cudaGetLastError();
+}
+
+// flat gradient image: state-dict order, weight [out,in] row-major then bias [out]
+struct FlatOff { int w[23]; int b[23]; };
+__host__ __device__ inline FlatOff flat_offsets() {
+  const int outs[23] = {256, 256, 256, 256, 256, 256, 256, 256, 256, 256, 1, 128, 3, 1, 128, 1, 3, 128, 128, 128, 3, 3, 3};
+  const int ins[23] = {63, 256, 256, 256, 256, 319, 256, 256, 283, 256, 256, 256, 128, 256, 256, 128, 256, 256, 256, 256, 128, 128, 128};
+  FlatOff f;
+  int off = 0;
+  for (int i = 0; i < 23; ++i) { f.w[i] = off; off += outs[i] * ins[i]; f.b[i] = off; off += outs[i]; }
+  return f;
+}
+// indices into the 23 Linear layers: 0..7 positions, 8 views, 9 feature, 10 sigma, 11 albedo_f, 12 albedo,
+// 13 rough, 14 irr_f, 15 irr, 16 rad, 17..19 add_f, 20..22 add
+constexpr int FLAT_TOTAL = 798994;
+
+// ---------------------------------------------------------------- dgrad kernel
+struct DgradParams {
+  const uint8_t* packed;
+  const uint8_t* saved;      // forward stash (masks)
+  const float* g_out;        // [P,18]
+  uint8_t* dy;               // DY_BYTES per tile
+  float* flat_grad;          // head-bias gradients are accumulated here directly
+  long long P;
+  long long n_tiles;
+};
+
+__device__ __forceinline__ void store_tile4(uint8_t* act, uint8_t* g, int kb, int row, int c16, uint4 pk) {
+  if (act != nullptr) *reinterpret_cast<uint4*>(act + kb * KB_BYTES + swz_offset(row, c16)) = pk;
+  *reinterpret_cast<uint4*>(g + (size_t)kb * KB_BYTES + swz_offset(row, c16)) = pk;
+}
+
+__global__ void __launch_bounds__(N_THREADS, 1) mlp_dgrad_kernel(DgradParams prm) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_BAR);
+  uint64_t* w_full = bars;
+  uint64_t* w_empty = bars + N_STAGES;
+  uint64_t* act_ready = bars + 2 * N_STAGES;
+  uint64_t* acc_ready = bars + 2 * N_STAGES + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * N_STAGES + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long my_tiles = (prm.n_tiles > (long long)blockIdx.x) ? (prm.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < N_STAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&act_ready[i], 4); mbar_init(&acc_ready[i], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint8_t* chunks = prm.packed + PACKED_BWD_OFF;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      long long rounds = (my_tiles + 1) / 2;
+      for (long long r = 0; r < rounds; ++r)
+        for (int t = 0; t < N_STEPS_BWD; ++t) {
+          const BStep st = bstep_at(t);
+          for (int slot = 0; slot < 2; ++slot) {
+            if (2 * r + slot >= my_tiles) continue;
+            for (int c = 0; c < st.nkb * 2; ++c) {
+              mbar_wait(&w_empty[stage], phase ^ 1);
+              mbar_arrive_expect_tx(&w_full[stage], KB_BYTES);
+              bulk_g2s(smem + SMEM_RING + stage * KB_BYTES, chunks + (size_t)(st.chunk_base + c) * KB_BYTES, KB_BYTES, &w_full[stage]);
+              if (++stage == N_STAGES) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t IDESC = make_idesc_bf16(128, 128, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t act_phase[2] = {0, 0};
+      long long rounds = (my_tiles + 1) / 2;
+      for (long long r = 0; r < rounds; ++r)
+        for (int t = 0; t < N_STEPS_BWD; ++t) {
+          const BStep st = bstep_at(t);
+          for (int slot = 0; slot < 2; ++slot) {
+            if (2 * r + slot >= my_tiles) continue;
+            mbar_wait(&act_ready[slot], act_phase[slot]);
+            act_phase[slot] ^= 1;
+            tc_fence_after();
+            const uint32_t act_addr = smem_u32(smem + SMEM_ACT + slot * ACT_BYTES);
+            const uint32_t d_tmem = tmem_base + slot * 256;
+            for (int kbi = 0; kbi < st.nkb; ++kbi)
+              for (int nh = 0; nh < 2; ++nh) {
+                mbar_wait(&w_full[stage], phase);
+                tc_fence_after();
+                const uint32_t b_addr = smem_u32(smem + SMEM_RING + stage * KB_BYTES);
+                for (int ks = 0; ks < 4; ++ks)
+                  umma_bf16(d_tmem + nh * 128, make_desc_kmajor_sw128(act_addr + kbi * KB_BYTES + ks * 32),
+                            make_desc_kmajor_sw128(b_addr + ks * 32), IDESC, (st.accumulate || kbi > 0 || ks > 0) ? 1u : 0u);
+                umma_commit(&w_empty[stage]);
+                if (++stage == N_STAGES) { stage = 0; phase ^= 1; }
+              }
+            umma_commit(&acc_ready[slot]);
+          }
+        }
+    }
+  } else {
+    const int slot = (warp - 2) >> 2;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    uint8_t* act = smem + SMEM_ACT + slot * ACT_BYTES;
+    const float* cst = reinterpret_cast<const float*>(prm.packed + PACKED_CONST_OFF);
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + slot * 256;
+    const FlatOff fo = flat_offsets();
+    uint32_t acc_phase = 0;
+    for (long long k = slot; k < my_tiles; k += 2) {
+      const long long tile = blockIdx.x + k * gridDim.x;
+      const long long p = tile * TILE_M + row;
+      const bool valid = p < prm.P;
+      uint8_t* dy = prm.dy + (size_t)tile * DY_BYTES;
+      const uint8_t* rec = prm.saved + (size_t)tile * SV_BYTES;
+      const uint32_t* masks = reinterpret_cast<const uint32_t*>(rec + (size_t)SV_MASK * KB_BYTES) + row * 8;   // + m * 1024 words
+      float g[18];
+#pragma unroll
+      for (int j = 0; j < 9; ++j) {
+        float2 v = valid ? __ldg(reinterpret_cast<const float2*>(prm.g_out + p * 18) + j) : make_float2(0.f, 0.f);
+        g[2 * j] = v.x; g[2 * j + 1] = v.y;
+      }
+      // ---- head-bias gradients: column sums of g over the warp's 32 rows
+      {
+        float s[18];
+#pragma unroll
+        for (int j = 0; j < 18; ++j) s[j] = warp_sum(g[j]);
+        if (lane == 0) {
+          atomicAdd(prm.flat_grad + fo.b[10], s[0]);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) atomicAdd(prm.flat_grad + fo.b[12] + c, s[1 + c]);
+          atomicAdd(prm.flat_grad + fo.b[13], s[4]);
+          atomicAdd(prm.flat_grad + fo.b[15], s[5]);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) atomicAdd(prm.flat_grad + fo.b[16] + c, s[6 + c]);
+#pragma unroll
+          for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) atomicAdd(prm.flat_grad + fo.b[20 + a] + c, s[9 + 3 * a + c]);
+        }
+      }
+      // ---- G tile: g_raw as bf16 [128][64] (columns 18.. zero) for the small-head wgrads
+      {
+        float e[64];
+#pragma unroll
+        for (int j = 0; j < 64; ++j) e[j] = j < 18 ? g[j] : 0.f;
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch)
+          store_tile4(nullptr, dy + (size_t)DY_G * KB_BYTES, 0, row, ch,
+                      make_uint4(pack_bf16x2(e[8 * ch], e[8 * ch + 1]), pack_bf16x2(e[8 * ch + 2], e[8 * ch + 3]),
+                                 pack_bf16x2(e[8 * ch + 4], e[8 * ch + 5]), pack_bf16x2(e[8 * ch + 6], e[8 * ch + 7])));
+      }
+      // ---- phase writers for the CUDA-core produced gradient tiles
+      // heads: 0 = coarse radiance 0|1 (256 cols), 1 = coarse radiance 2 (128 cols), 2 = albedo|irradiance features
+      auto write_head_tile = [&](int which) {
+        const int ncc = which == 1 ? 4 : 8;
+        const int mslot = which == 0 ? 10 : which == 1 ? 11 : 8;
+        const int dblk = which == 0 ? DY_ADDF01 : which == 1 ? DY_ADDF2 : DY_AF;
+        uint4 mw0 = __ldg(reinterpret_cast<const uint4*>(masks + mslot * 1024));
+        uint4 mw1 = __ldg(reinterpret_cast<const uint4*>(masks + mslot * 1024) + 1);
+        const uint32_t mw[8] = {mw0.x, mw0.y, mw0.z, mw0.w, mw1.x, mw1.y, mw1.z, mw1.w};
+        for (int cc = 0; cc < ncc; ++cc) {
+          float v[32];
+          if (which == 2) {
+            const float4* w = reinterpret_cast<const float4*>(cst + C_AF) + cc * 32;
+            if (cc < 4) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) { float4 ww = __ldg(w + j); v[j] = g[1] * ww.x + g[2] * ww.y + g[3] * ww.z; }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) { float4 ww = __ldg(w + j); v[j] = g[5] * ww.x; }
+            }
+          } else {
+            const int head = which == 1 ? 2 : (cc >> 2);
+            const float4* w = reinterpret_cast<const float4*>(cst + C_ADD) + head * 128 + (cc & 3) * 32;
+            const float g0 = g[9 + 3 * head], g1 = g[10 + 3 * head], g2 = g[11 + 3 * head];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { float4 ww = __ldg(w + j); v[j] = g0 * ww.x + g1 * ww.y + g2 * ww.z; }
+          }
+          const uint32_t m = mw[cc];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = ((m >> j) & 1u) ? v[j] : 0.f;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            store_tile4(act, dy + (size_t)dblk * KB_BYTES, cc >> 1, row, (cc & 1) * 4 + q,
+                        make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
+                                   pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7])));
+        }
+      };
+      auto publish = [&]() {
+        fence_proxy_async();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&act_ready[slot]);
+      };
+      write_head_tile(0);
+      publish();
+      for (int t = 0; t < N_STEPS_BWD; ++t) {
+        mbar_wait(&acc_ready[slot], acc_phase);
+        acc_phase ^= 1;
+        tc_fence_after();
+        if (t == 0) { write_head_tile(1); publish(); continue; }
+        if (t == 3) { write_head_tile(2); publish(); continue; }
+        // drain: t=1 -> dY_view (mask HV, + radiance term); t=2 -> dY_feat (no mask); t=4 -> dY_7 (+ sigma/rough terms);
+        // t>=5 -> dY_{11-t} (mask h_{11-t})
+        const int mslot = t == 1 ? 9 : t == 2 ? -1 : t == 4 ? 7 : 11 - t;
+        const int dblk = t == 1 ? DY_VIEW : t == 2 ? DY_FEAT : t == 4 ? DY_H(7) : DY_H(11 - t);
+        uint32_t mw[8];
+        if (mslot >= 0) {
+          uint4 mw0 = __ldg(reinterpret_cast<const uint4*>(masks + mslot * 1024));
+          uint4 mw1 = __ldg(reinterpret_cast<const uint4*>(masks + mslot * 1024) + 1);
+          mw[0] = mw0.x; mw[1] = mw0.y; mw[2] = mw0.z; mw[3] = mw0.w; mw[4] = mw1.x; mw[5] = mw1.y; mw[6] = mw1.z; mw[7] = mw1.w;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) mw[i] = 0xffffffffu;
+        }
+        const bool last = (t == N_STEPS_BWD - 1);
+        for (int cc = 0; cc < 8; ++cc) {
+          uint32_t raw[32];
+          tmem_ld32(t_lane + cc * 32, raw);
+          tmem_wait_ld();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+          if (t == 1) {
+            const float4* w = reinterpret_cast<const float4*>(cst + C_RAD) + cc * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { float4 ww = __ldg(w + j); v[j] += g[6] * ww.x + g[7] * ww.y + g[8] * ww.z; }
+          } else if (t == 4) {
+            const float2* w = reinterpret_cast<const float2*>(cst + C_SR) + cc * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { float2 ww = __ldg(w + j); v[j] += g[0] * ww.x + g[4] * ww.y; }
+          }
+          const uint32_t m = mw[cc];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = ((m >> j) & 1u) ? v[j] : 0.f;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            store_tile4(last ? nullptr : act, dy + (size_t)dblk * KB_BYTES, cc >> 1, row, (cc & 1) * 4 + q,
+                        make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
+                                   pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7])));
+        }
+        if (!last) publish();
+      }
+      tc_fence_before();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { __syncwarp(); tmem_dealloc(tmem_base, 512); }
+}
+
+// ---------------------------------------------------------------- wgrad kernel
+// D[m][n] += sum_pt A[pt][m] * B[pt][n] over the tiles of this CTA.  A = 2 adjacent 16 KB blocks of a record
+// (128 "m" columns), B = nb adjacent blocks (64*nb "n" columns, the last one possibly only n_last wide), both
+// read as MN-major SWIZZLE_128B operands.  Optional extra N=16 MMA against a constant ones tile gives the
+// column sums of A (bias gradient) in accumulator column 256.
+struct OutSpec { float* ptr; int m_lo, m_hi, n_lo, n_hi, stride_m, stride_n; };
+struct WgradParams {
+  const uint8_t* a_base; long long a_stride; int a_blk;     // record base / bytes per tile / first block of m-half 0
+  const uint8_t* b_base; long long b_stride; int b_blk;
+  int m_halves;          // 1 or 2: CTA class c handles blocks a_blk + 2c, a_blk + 2c + 1
+  int nb;                // B blocks (1..4)
+  int n_total;           // N of the main MMA (multiple of 16, <= 256)
+  int with_ones;
+  long long n_tiles;
+  OutSpec out[4];
+  int n_out;
+};
+
+constexpr int WG_STAGE_BYTES = 6 * KB_BYTES;     // A (2 blocks) + B (<= 4 blocks)
+constexpr int WG_SMEM_ONES = 2 * WG_STAGE_BYTES;
+constexpr int WG_SMEM_BAR = WG_SMEM_ONES + KB_BYTES;
+constexpr int WG_SMEM_REQUEST = WG_SMEM_BAR + 128 + 1024;
+constexpr int WG_THREADS = 192;                  // warp 0 producer, warp 1 MMA, warps 2-5 epilogue
+
+__global__ void __launch_bounds__(WG_THREADS, 1) mlp_wgrad_kernel(WgradParams prm) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WG_SMEM_BAR);
+  uint64_t* full = bars;        // [2]
+  uint64_t* empty = bars + 2;   // [2]
+  uint64_t* done = bars + 4;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 5);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cls = blockIdx.x % prm.m_halves;                    // m-half handled by this CTA
+  const int idx = blockIdx.x / prm.m_halves, per_cls = gridDim.x / prm.m_halves;
+  const long long my_tiles = (prm.n_tiles > idx) ? (prm.n_tiles - idx + per_cls - 1) / per_cls : 0;
+  const uint32_t b_bytes = (uint32_t)prm.nb * KB_BYTES;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, 512);
+  if (prm.with_ones) {      // ones tile: column 0 of every row = 1.0 (bf16), everything else 0
+    for (int e = threadIdx.x; e < 128 * 8; e += blockDim.x) {
+      int r = e >> 3, c16 = e & 7;
+      *reinterpret_cast<uint4*>(smem + WG_SMEM_ONES + swz_offset(r, c16)) = make_uint4(c16 == 0 ? 0x00003F80u : 0u, 0u, 0u, 0u);
+    }
+    fence_proxy_async();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      for (long long i = 0; i < my_tiles; ++i) {
+        const long long tile = idx + i * per_cls;
+        const int stage = (int)(i & 1);
+        const uint32_t ph = (uint32_t)((i >> 1) & 1);
+        mbar_wait(&empty[stage], ph ^ 1);
+        mbar_arrive_expect_tx(&full[stage], 2 * KB_BYTES + b_bytes);
+        uint8_t* dst = smem + stage * WG_STAGE_BYTES;
+        bulk_g2s(dst, prm.a_base + (size_t)tile * prm.a_stride + (size_t)(prm.a_blk + 2 * cls) * KB_BYTES, 2 * KB_BYTES, &full[stage]);
+        bulk_g2s(dst + 2 * KB_BYTES, prm.b_base + (size_t)tile * prm.b_stride + (size_t)prm.b_blk * KB_BYTES, b_bytes, &full[stage]);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_bf16(128, (uint32_t)prm.n_total, 1, 1);
+      const uint32_t idesc1 = make_idesc_bf16(128, 64, 1, 1);   // whole 64-wide swizzle atom; only column 0 is non-zero
+      const uint32_t ones_addr = smem_u32(smem + WG_SMEM_ONES);
+      for (long long i = 0; i < my_tiles; ++i) {
+        const int stage = (int)(i & 1);
+        const uint32_t ph = (uint32_t)((i >> 1) & 1);
+        mbar_wait(&full[stage], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + stage * WG_STAGE_BYTES);
+        const uint32_t b_addr = a_addr + 2 * KB_BYTES;
+        for (int ks = 0; ks < 8; ++ks) {       // 16 points per MMA
+          const uint32_t acc = (i > 0 || ks > 0) ? 1u : 0u;
+          const uint64_t da = make_desc_mnmajor_sw128(a_addr + ks * 2048, KB_BYTES);
+          umma_bf16(tmem_base, da, make_desc_mnmajor_sw128(b_addr + ks * 2048, KB_BYTES), idesc, acc);
+          if (prm.with_ones) umma_bf16(tmem_base + 256, da, make_desc_mnmajor_sw128(ones_addr + ks * 2048, KB_BYTES), idesc1, acc);
+        }
+        umma_commit(&empty[stage]);
+      }
+      umma_commit(done);
+    }
+  } else {
+    mbar_wait(done, 0);
+    tc_fence_after();
+    if (my_tiles > 0) {
+      const int quarter = warp & 3;
+      const int m = cls * 128 + quarter * 32 + lane;
+      const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+      const int ncols = prm.with_ones ? 288 : ((prm.n_total + 31) & ~31);
+      for (int c0 = 0; c0 < ncols; c0 += 32) {
+        if (c0 >= ((prm.n_total + 31) & ~31) && c0 < 256) continue;
+        uint32_t raw[32];
+        tmem_ld32(t_lane + c0, raw);
+        tmem_wait_ld();
+        for (int o = 0; o < prm.n_out; ++o) {
+          const OutSpec sp = prm.out[o];
+          if (m < sp.m_lo || m >= sp.m_hi) continue;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = c0 + j;
+            if (n >= sp.n_lo && n < sp.n_hi)
+              atomicAdd(sp.ptr + (long long)(m - sp.m_lo) * sp.stride_m + (long long)(n - sp.n_lo) * sp.stride_n, __uint_as_float(raw[j]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { __syncwarp(); tmem_dealloc(tmem_base, 512); }
+}
+
+}  // namespace mlp
+}  // namespace ibln
+
+using namespace ibln;
+using namespace ibln::mlp;
+
+extern "C" int64_t ibln_mlp_bwd_workspace_bytes(int64_t n_pts) { return ((n_pts + TILE_M - 1) / TILE_M) * DY_BYTES; }
+
+static int launch_wgrad(WgradParams& p, int device, cudaStream_t stream) {
+  int sms = num_sms(device);
+  int grid = (sms / p.m_halves) * p.m_halves;
+  long long need = p.n_tiles * p.m_halves;
+  if (need < grid) grid = (int)need;
+  mlp_wgrad_kernel<<<grid, WG_THREADS, WG_SMEM_REQUEST, stream>>>(p);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int ibln_mlp_bwd(const void* packed, const void* saved, const float* g_out, int64_t n_pts, float* flat_grad,
+                            void* workspace, int device, void* stream_) {
+  if (!packed || !saved || !g_out || !flat_grad || !workspace || n_pts < 0) return IBLN_EINVAL;
+  if (n_pts == 0) return 0;
+  DeviceGuard guard(device);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const long long n_tiles = (n_pts + TILE_M - 1) / TILE_M;
+  // ---- dgrad chain
+  DgradParams dp;
+  dp.packed = (const uint8_t*)packed; dp.saved = (const uint8_t*)saved; dp.g_out = g_out; dp.dy = (uint8_t*)workspace;
+  dp.flat_grad = flat_grad; dp.P = n_pts; dp.n_tiles = n_tiles;
+  IBLN_CUDA(cudaFuncSetAttribute(mlp_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_REQUEST));
+  long long grid = n_tiles < (long long)num_sms(device) ? n_tiles : (long long)num_sms(device);
+  mlp_dgrad_kernel<<<(unsigned)grid, N_THREADS, SMEM_REQUEST, stream>>>(dp);
+  IBLN_CUDA(cudaGetLastError());
+  // ---- wgrad jobs
+  IBLN_CUDA(cudaFuncSetAttribute(mlp_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_REQUEST));
+  const FlatOff fo = flat_offsets();
+  const uint8_t* SV = (const uint8_t*)saved;
+  const uint8_t* DY = (const uint8_t*)workspace;
+  auto job = [&](const uint8_t* a_base, long long a_stride, int a_blk, int m_halves, const uint8_t* b_base, long long b_stride,
+                 int b_blk, int nb, int n_total, int with_ones) {
+    WgradParams p;
+    p.a_base = a_base; p.a_stride = a_stride; p.a_blk = a_blk; p.b_base = b_base; p.b_stride = b_stride; p.b_blk = b_blk;
+    p.m_halves = m_halves; p.nb = nb; p.n_total = n_total; p.with_ones = with_ones; p.n_tiles = n_tiles; p.n_out = 0;
+    return p;
+  };
+  auto add_out = [&](WgradParams& p, float* ptr, int m_lo, int m_hi, int n_lo, int n_hi, int stride_m, int stride_n) {
+    OutSpec& o = p.out[p.n_out++];
+    o.ptr = ptr; o.m_lo = m_lo; o.m_hi = m_hi; o.n_lo = n_lo; o.n_hi = n_hi; o.stride_m = stride_m; o.stride_n = stride_n;
+  };
+  float* G = flat_grad;
+  int rc;
+  // trunk layers: dW_l = dY_l^T X_l (+ bias through the ones column)
+  for (int l = 0; l < 8; ++l) {
+    const int ld = l == 0 ? 63 : (l == 5 ? 319 : 256);
+    if (l == 0 || l == 5) {   // positional-encoding part (63 valid of 64 columns)
+      WgradParams p = job(DY, DY_BYTES, DY_H(l), 2, SV, SV_BYTES, SV_PE, 1, 64, l == 0);
+      add_out(p, G + fo.w[l], 0, 256, 0, 63, ld, 1);
+      if (l == 0) add_out(p, G + fo.b[l], 0, 256, 256, 257, 1, 0);
+      if ((rc = launch_wgrad(p, device, stream)) != 0) return rc;
+    }
+    if (l > 0) {
+      WgradParams p = job(DY, DY_BYTES, DY_H(l), 2, SV, SV_BYTES, SV_H(l - 1), 4, 256, 1);
+      add_out(p, G + fo.w[l] + (l == 5 ? 63 : 0), 0, 256, 0, 256, ld, 1);
+      add_out(p, G + fo.b[l], 0, 256, 256, 257, 1, 0);
+      if ((rc = launch_wgrad(p, device, stream)) != 0) return rc;
+    }
+  }
+  {   // feature_linear: dY_feat x h7
+    WgradParams p = job(DY, DY_BYTES, DY_FEAT, 2, SV, SV_BYTES, SV_H(7), 4, 256, 1);
+    add_out(p, G + fo.w[9], 0, 256, 0, 256, 256, 1);
+    add_out(p, G + fo.b[9], 0, 256, 256, 257, 1, 0);
+    if ((rc = launch_wgrad(p, device, stream)) != 0) return rc;
+  }
+  {   // albedo / irradiance feature linears: dY_af x h7 (rows 0..127 albedo_f, 128..255 irradiance_f)
+    WgradParams p = job(DY, DY_BYTES, DY_AF, 2, SV, SV_BYTES, SV_H(7), 4, 256, 1);
+    add_out(p, G + fo.w[11], 0, 128, 0, 256, 256, 1);
+    add_out(p, G + fo.w[14], 128, 256, 0, 256, 256, 1);
+    add_out(p, G + fo.b[11], 0, 128, 256, 257, 1, 0);
+    add_out(p, G + fo.b[14], 128, 256, 256, 257, 1, 0);
+    if ((rc = launch_wgrad(p, device, stream)) != 0) return rc;
+  }
+  {   // views_linears.0: dY_view x [feature | view encoding]
+    WgradParams p = job(DY, DY_BYTES, DY_VIEW, 2, SV, SV_BYTES, SV_FEAT, 4, 256, 1);
+    add_out(p, G + fo.w[8], 0, 256, 0, 256, 283, 1);
+    add_out(p, G + fo.b[8], 0, 256, 256, 257, 1, 0);
+    if ((rc = launch_wgrad(p, device, stream)) != 0) return rc;
+    WgradParams q = job(DY, DY_BYTES, DY_VIEW, 2, SV, SV_BYTES, SV_DE, 1, 64, 0);   // columns 27.. of the tile are unused
+    add_out(q, G + fo.w[8] + 256, 0, 256, 0, 27, 283, 1);
+    if ((rc = launch_wgrad(q, device, stream)) != 0) return rc;
+  }
+  {   // coarse-radiance feature linears: dY_addf x hv
+    WgradParams p = job(DY, DY_BYTES, DY_ADDF01, 2, SV, SV_BYTES, SV_HV, 4, 256, 1);
+    add_out(p, G + fo.w[17], 0, 128, 0, 256, 256, 1);
+    add_out(p, G + fo.w[18], 128, 256, 0, 256, 256, 1);
+    add_out(p, G + fo.b[17], 0, 128, 256, 257, 1, 0);
+    add_out(p, G + fo.b[18], 128, 256, 256, 257, 1, 0);
+    if ((rc = launch_wgrad(p, device, stream)) != 0) return rc;
+    WgradParams q = job(DY, DY_BYTES, DY_ADDF2, 1, SV, SV_BYTES, SV_HV, 4, 256, 1);
+    add_out(q, G + fo.w[19], 0, 128, 0, 256, 256, 1);
+    add_out(q, G + fo.b[19], 0, 128, 256, 257, 1, 0);
+    if ((rc = launch_wgrad(q, device, stream)) != 0) return rc;
+  }
+  // small heads: D[feature col][g channel] = X^T G
+  {   // sigma / roughness from h7
+    WgradParams p = job(SV, SV_BYTES, SV_H(7), 2, DY, DY_BYTES, DY_G, 1, 64, 0);
+    add_out(p, G + fo.w[10], 0, 256, 0, 1, 1, 0);
+    add_out(p, G + fo.w[13], 0, 256, 4, 5, 1, 0);
+    if ((rc = launch_wgrad(p, device, stream)) != 0) return rc;
+  }
+  {   // albedo (cols 0..127 x channels 1..3) / irradiance (cols 128..255 x channel 5) from AF
+    WgradParams p = job(SV, SV_BYTES, SV_AF, 2, DY, DY_BYTES, DY_G, 1, 64, 0);
+    add_out(p, G + fo.w[12], 0, 128, 1, 4, 1, 128);
+    add_out(p, G + fo.w[15], 128, 256, 5, 6, 1, 0);
+    if ((rc = launch_wgrad(p, device, stream)) != 0) return rc;
+  }
+  {   // radiance from hv
+    WgradParams p = job(SV, SV_BYTES, SV_HV, 2, DY, DY_BYTES, DY_G, 1, 64, 0);
+    add_out(p, G + fo.w[16], 0, 256, 6, 9, 1, 256);
+    if ((rc = launch_wgrad(p, device, stream)) != 0) return rc;
+  }
+  for (int k = 0; k < 3; ++k) {   // coarse radiance heads from ADDF block pair k
+    WgradParams p = job(SV, SV_BYTES, SV_ADDF + 2 * k, 1, DY, DY_BYTES, DY_G, 1, 64, 0);
+    add_out(p, G + fo.w[20 + k], 0, 128, 9 + 3 * k, 12 + 3 * k, 1, 128);
+    if ((rc = launch_wgrad(p, device, stream)) != 0) return rc;
+  }
+  return 0;
+}
+
+// MN-major operand self-test: D[128,N] = X^T Y with X [128 pts][128], Y [128 pts][N] staged as operand tiles.
+namespace ibln { namespace mlp {
+__global__ void __launch_bounds__(128, 1)
+umma_mn_selftest_kernel(const float* __restrict__ X, const float* __restrict__ Y, float* __restrict__ D, int N) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem;                       // 2 blocks
+  uint8_t* sB = smem + 2 * KB_BYTES;        // N/64 blocks
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sB + 4 * KB_BYTES);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+  __syncwarp();
+  if (warp == 0) tmem_alloc(tmem_ptr, 256);
+  auto stage = [&](uint8_t* dst, const float* src, int cols) {
+    for (int e = threadIdx.x; e < 128 * (cols / 8); e += blockDim.x) {
+      int row = e / (cols / 8), cg = e % (cols / 8);
+      const float* s = src + (size_t)row * cols + cg * 8;
+      *reinterpret_cast<uint4*>(dst + (size_t)(cg / 8) * KB_BYTES + swz_offset(row, cg % 8)) =
+          make_uint4(pack_bf16x2(s[0], s[1]), pack_bf16x2(s[2], s[3]), pack_bf16x2(s[4], s[5]), pack_bf16x2(s[6], s[7]));
+    }
+  };
+  stage(sA, X, 128);
+  stage(sB, Y, N);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  if (warp == 1 && elect_one()) {
+    const uint32_t idesc = make_idesc_bf16(128, (uint32_t)N, 1, 1);
+    for (int ks = 0; ks < 8; ++ks)
+      umma_bf16(tmem_base, make_desc_mnmajor_sw128(smem_u32(sA) + ks * 2048, KB_BYTES),
+                make_desc_mnmajor_sw128(smem_u32(sB) + ks * 2048, KB_BYTES), idesc, ks > 0 ? 1u : 0u);
+    umma_commit(bar);
+  }
+  mbar_wait(bar, 0);
+  tc_fence_after();
+  const int row = (warp & 3) * 32 + lane;
+  for (int cc = 0; cc < (N + 31) / 32; ++cc) {
+    uint32_t v[32];
+    tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + cc * 32, v);
+    tmem_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) if (cc * 32 + j < N) D[(size_t)row * N + cc * 32 + j] = __uint_as_float(v[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { __syncwarp(); tmem_dealloc(tmem_base, 256); }
+}
+}}  // namespace ibln::mlp
+
+extern "C" int ibln_umma_mn_selftest(const float* x, const float* y, float* d, int n, int device, void* stream) {
+  if (!x || !y || !d || n < 64 || n > 256 || n % 64 != 0) return IBLN_EINVAL;
+  DeviceGuard g(device);
+  int smem = 6 * KB_BYTES + 64 + 1024;
+  IBLN_CUDA(cudaFuncSetAttribute(umma_mn_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  umma_mn_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(x, y, d, n);
+  IBLN_RETURN_LAST();
+}

@@ -18,6 +18,48 @@ from ._lib import call, f32c, ptr
 FLOP_FULL, FLOP_SIGMA = 1591552, 982528
 
 
+FLAT_PARAMS = sum(o * i + o for _, o, i in mlp.PARAM_ORDER)      # 798 994
+
+
+class _MLPTc(torch.autograd.Function):
+    """Fused tcgen05 forward with activation stash + tensor-core backward (dgrad chain + split-K wgrad).
+    mode 0: explicit points [n*s,3] + per-ray dirs; mode 1: ray march (o, d, z)."""
+
+    @staticmethod
+    def forward(ctx, net, mode, pts, o, d, z, n, s, *params):
+        dev = d.device
+        P = n * s
+        h = _lib.lib()
+        out = torch.empty(P, 18, dtype=torch.float32, device=dev)
+        saved = torch.empty(h.ibln_mlp_saved_bytes(P), dtype=torch.uint8, device=dev)
+        packed = net.packed_weights()
+        call("ibln_mlp_fwd", dev, ptr(packed), mode, ptr(pts), ptr(o), ptr(d), ptr(z), n, s, 0.0, 0, ptr(out), ptr(saved),
+             flops=P * FLOP_FULL)
+        ctx.packed, ctx.stash, ctx.P = packed, saved, P
+        ctx.shapes = [p.shape for p in params]
+        ctx.need = [p.requires_grad for p in params]
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        dev = g_out.device
+        h = _lib.lib()
+        g_out = f32c(g_out)
+        flat = torch.zeros(FLAT_PARAMS, dtype=torch.float32, device=dev)
+        ws = torch.empty(h.ibln_mlp_bwd_workspace_bytes(ctx.P), dtype=torch.uint8, device=dev)
+        call("ibln_mlp_bwd", dev, ptr(ctx.packed), ptr(ctx.stash), ptr(g_out), ctx.P, ptr(flat), ptr(ws),
+             flops=2.0 * ctx.P * FLOP_FULL)
+        ctx.stash = None
+        grads, off = [], 0
+        for shp, need in zip(ctx.shapes, ctx.need):
+            k = 1
+            for x in shp:
+                k *= x
+            grads.append(flat[off:off + k].view(shp) if need else None)
+            off += k
+        return (None,) * 8 + tuple(grads)
+
+
 class IBLNeRF(nn.Module):
     def __init__(self, D=8, W=256, input_ch=3, input_ch_views=3, skips=[4], use_illumination_feature_layer=False,
                  use_instance_feature_layer=False, coarse_radiance_number=0, is_color_independent_to_direction=True):
@@ -103,6 +145,11 @@ class IBLNeRF(nn.Module):
     def _grad_needed(self):
         return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
 
+    def _tc_grad_ok(self):
+        """Gradient passes run on the tensor-core backward unless a freeze mode is active (forward_freezed,
+        ibl_nerf.py:88-152, trains only a few heads: handled by the fp32 path)."""
+        return self.effective_precision() == "bf16" and not self.freeze_radiance
+
     def query_points(self, pts, viewdirs):
         """run_network semantics: pts [N,S,3], viewdirs [N,3] or None -> [N,S,18] / [N,S,1]."""
         n, s = pts.shape[0], pts.shape[1]
@@ -114,6 +161,10 @@ class IBLNeRF(nn.Module):
             call("ibln_mlp_fwd", pts.device, ptr(self.packed_weights()), 0, ptr(pts), None, ptr(d), None, n, s, 0.0,
                  int(viewdirs is None), ptr(out), None, flops=n * s * (FLOP_SIGMA if viewdirs is None else FLOP_FULL))
             return out.reshape(n, s, -1)
+        if self._tc_grad_ok() and viewdirs is not None:
+            out = _MLPTc.apply(self, 0, f32c(pts.detach().reshape(-1, 3)), None, f32c(viewdirs.detach()), None, n, s,
+                               *self.ordered_params())
+            return out.reshape(n, s, 18)
         flat = f32c(pts.reshape(-1, 3))
         x_pos = mlp.encode(flat, 10)
         x_dir = None
@@ -133,6 +184,10 @@ class IBLNeRF(nn.Module):
             call("ibln_mlp_fwd", zz.device, ptr(self.packed_weights()), 1, None, ptr(o), ptr(d), ptr(zz), n, s, 0.0,
                  int(sigma_only), ptr(out), None, flops=n * s * (FLOP_SIGMA if sigma_only else FLOP_FULL))
             return out.reshape(n, s, -1)
+        if self._tc_grad_ok() and not sigma_only:
+            out = _MLPTc.apply(self, 1, None, f32c(rays_o.detach()), f32c(rays_d.detach()), f32c(z.detach()), n, s,
+                               *self.ordered_params())
+            return out.reshape(n, s, 18)
         pts = rays_o[:, None, :] + rays_d[:, None, :] * z[..., None]
         return self.query_points(pts, None if sigma_only else rays_d)
 

@@ -183,8 +183,10 @@ int64_t ibln_mlp_saved_bytes(int64_t n_pts);
 int ibln_mlp_fwd(const void* packed, int mode, const float* pts, const float* rays_o, const float* rays_d,
                  const float* z, int64_t n_rays, int n_samples, float eps, int sigma_only,
                  float* out, void* saved, int device, void* stream);
-/* Backward: g_out [P,18]; accumulates into the flat fp32 gradient image flat_grad (798 994 floats,
- * state-dict order, each tensor row-major).  workspace >= ibln_mlp_bwd_workspace_bytes(P). */
+/* Backward (dgrad chain kernel + split-K wgrad kernels): g_out [P,18]; ACCUMULATES (red.global.add) into the
+ * flat fp32 gradient image flat_grad (798 994 floats, state-dict order, each tensor row-major: weight then
+ * bias per Linear).  `saved` is the stash written by ibln_mlp_fwd for the same points;
+ * workspace >= ibln_mlp_bwd_workspace_bytes(P) (per-layer dY tiles). */
 int64_t ibln_mlp_bwd_workspace_bytes(int64_t n_pts);
 int ibln_mlp_bwd(const void* packed, const void* saved, const float* g_out, int64_t n_pts,
                  float* flat_grad, void* workspace, int device, void* stream);
@@ -193,6 +195,10 @@ int ibln_mlp_bwd(const void* packed, const void* saved, const float* g_out, int6
  * through the same swizzled shared-memory layout the MLP kernels use. a,b fp32 (rounded to bf16
  * inside), d fp32.  variant selects descriptor hypotheses (0 = production). */
 int ibln_umma_selftest(const float* a, const float* b, float* d, int n, int k, int variant, int device, void* stream);
+
+/* Self-test of the MN-major operand path used by the wgrad kernel: D[128,N] = X^T Y with X [128 points,128],
+ * Y [128 points,N] (N in {64,128,192,256}) staged as swizzled operand tiles and read as MN-major. */
+int ibln_umma_mn_selftest(const float* x, const float* y, float* d, int n, int device, void* stream);
 
 #ifdef __cplusplus
 }

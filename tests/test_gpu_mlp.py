@@ -133,3 +133,112 @@ def test_tc_repack_after_parameter_update():
         coarse.sigma_linear.bias.add_(1.0)
         b = coarse.query_rays(ro.to(DEV), rd.to(DEV), z.to(DEV))
     assert torch.allclose(b[..., 0], a[..., 0] + 1.0, atol=1e-4) and torch.equal(a[..., 1:], b[..., 1:])
+
+
+# ----------------------------------------------------------------------------- tensor-core backward
+def decode_blocks(buf, tile, rec_bytes, blk, nblk):
+    """Un-swizzle nblk 16 KB operand blocks of one tile record into a [128, 64*nblk] fp32 matrix."""
+    base = tile * rec_bytes + blk * 16384
+    raw = buf[base:base + nblk * 16384].view(torch.bfloat16).reshape(nblk, 128, 8, 8)      # block, row, chunk position, elem
+    rows = torch.arange(128, device=buf.device)
+    out = []
+    for b in range(nblk):
+        pos = torch.arange(8, device=buf.device)[None, :] ^ (rows[:, None] & 7)             # position of logical chunk c in row r
+        out.append(torch.gather(raw[b], 1, pos[:, :, None].expand(128, 8, 8)).reshape(128, 64))
+    return torch.cat(out, 1).float()
+
+
+@pytest.mark.parametrize("n", [64, 128, 256])
+def test_umma_mn_major_selftest(n):
+    gen = torch.Generator().manual_seed(n)
+    x = torch.randn(128, 128, generator=gen).to(DEV)
+    y = torch.randn(128, n, generator=gen).to(DEV)
+    d = torch.zeros(128, n, device=DEV)
+    call("ibln_umma_mn_selftest", x.device, ptr(x), ptr(y), ptr(d), n)
+    want = x.bfloat16().float().t() @ y.bfloat16().float()
+    close(d, want, rtol=1e-3, atol=1e-3, name="umma mn-major")
+
+
+def test_tc_stash_and_dgrad_tiles():
+    """Stage-level check of the backward: stashed activations and every per-layer dY tile against fp32 autograd."""
+    coarse, _ = build_nets(DEV, structured=True, precision="bf16")
+    n, s = 5, 64                                     # 320 points -> 3 tiles (last one partial)
+    ro, rd = fx.make_rays(n, seed=3)
+    z = fx.make_sorted_z(n, s, seed=4)
+    P = n * s
+    h = _lib.lib()
+    out = torch.empty(P, 18, device=DEV)
+    stash = torch.zeros(h.ibln_mlp_saved_bytes(P), dtype=torch.uint8, device=DEV)
+    packed = coarse.packed_weights()
+    call("ibln_mlp_fwd", out.device, ptr(packed), 1, None, ptr(ro.to(DEV)), ptr(rd.to(DEV)), ptr(z.to(DEV)), n, s, 0.0, 0, ptr(out), ptr(stash))
+    # fp32 reference with intermediates (CPU autograd)
+    sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in coarse.state_dict().items()}
+    pts = (ro[:, None] + rd[:, None] * z[..., None]).reshape(-1, 3)
+    xp = orc.embed(pts, 10)
+    xd = orc.embed(rd[:, None, :].expand(n, s, 3).reshape(-1, 3), 4)
+    lin = lambda name, x: x @ sd[name + ".weight"].t() + sd[name + ".bias"]
+    inter = {}
+    hcur = xp
+    for i in range(8):
+        pre = lin("positions_linears.%d" % i, hcur); pre.retain_grad(); inter["pre%d" % i] = pre
+        hcur = torch.relu(pre); inter["h%d" % i] = hcur
+        if i == 4:
+            hcur = torch.cat([xp, hcur], -1)
+    h7 = inter["h7"]
+    af_pre = torch.cat([lin("albedo_feature_linear", h7), lin("irradiance_feature_linear", h7)], -1); af_pre.retain_grad()
+    af = torch.relu(af_pre)
+    feat = lin("feature_linear", h7); feat.retain_grad()
+    hv_pre = lin("views_linears.0", torch.cat([feat, xd], -1)); hv_pre.retain_grad()
+    hv = torch.relu(hv_pre)
+    addf_pre = torch.cat([lin("additional_radiance_feature_linear.%d" % k, hv) for k in range(3)], -1); addf_pre.retain_grad()
+    addf = torch.relu(addf_pre)
+    raw = torch.cat([lin("sigma_linear", h7), lin("albedo_linear", af[:, :128]), lin("roughness_linear", h7),
+                     lin("irradiance_linear", af[:, 128:]), lin("radiance_linear", hv)] +
+                    [lin("additional_radiance_linear.%d" % k, addf[:, 128 * k:128 * k + 128]) for k in range(3)], -1)
+    g = torch.randn(P, 18, generator=torch.Generator().manual_seed(8))
+    (raw * g).sum().backward()
+    SV, DYB = 55 * 16384, 51 * 16384
+
+    def gather(buf, rec, blk, nblk, cols):
+        return torch.cat([decode_blocks(buf, t, rec, blk, nblk) for t in range(3)], 0)[:P, :cols].cpu()
+    # stash: bf16-level agreement with the fp32 activations
+    for name, blk, nblk, cols, ref in (("pe", 0, 1, 63, xp), ("h0", 1, 4, 256, inter["h0"]), ("h4", 17, 4, 256, inter["h4"]),
+                                       ("h7", 29, 4, 256, h7), ("af", 33, 4, 256, af), ("feat", 37, 4, 256, feat),
+                                       ("de", 41, 1, 27, xd), ("hv", 42, 4, 256, hv), ("addf", 46, 6, 384, addf)):
+        got = gather(stash, SV, blk, nblk, cols)
+        assert rel_l2(got, ref.detach()) < 2e-2, (name, rel_l2(got, ref.detach()))
+    # backward
+    flat = torch.zeros(798994, device=DEV)
+    ws = torch.zeros(h.ibln_mlp_bwd_workspace_bytes(P), dtype=torch.uint8, device=DEV)
+    call("ibln_mlp_bwd", out.device, ptr(packed), ptr(stash), ptr(g.to(DEV)), P, ptr(flat), ptr(ws))
+    torch.cuda.synchronize()
+    for name, blk, nblk, cols, ref in (("addf01", 0, 4, 256, addf_pre.grad[:, :256]), ("addf2", 4, 2, 128, addf_pre.grad[:, 256:]),
+                                       ("view", 6, 4, 256, hv_pre.grad), ("feat", 10, 4, 256, feat.grad), ("af", 14, 4, 256, af_pre.grad),
+                                       ("dY7", 18, 4, 256, inter["pre7"].grad), ("dY6", 22, 4, 256, inter["pre6"].grad),
+                                       ("dY4", 30, 4, 256, inter["pre4"].grad), ("dY0", 46, 4, 256, inter["pre0"].grad),
+                                       ("G", 50, 1, 18, g)):
+        got = gather(ws, DYB, blk, nblk, cols)
+        assert rel_l2(got, ref) < 4e-2, (name, rel_l2(got, ref))
+    # parameter gradients (stated tolerance for the bf16 path: 4e-2 relative L2 per tensor)
+    off = 0
+    for name, o, i in ib.mlp.PARAM_ORDER:
+        for suffix, cnt in ((".weight", o * i), (".bias", o)):
+            got = flat[off:off + cnt].cpu()
+            ref = sd[name + suffix].grad.reshape(-1)
+            assert rel_l2(got, ref) < 4e-2, (name + suffix, rel_l2(got, ref))
+            off += cnt
+    assert off == 798994
+
+
+def test_tc_autograd_matches_fp32_path():
+    ro, rd = fx.make_rays(300, seed=5)
+    z = fx.make_sorted_z(300, 64, seed=6)
+    cot = torch.randn(300, 64, 18, generator=torch.Generator().manual_seed(7)).to(DEV)
+    grads = {}
+    for prec in ("fp32", "bf16"):
+        coarse, _ = build_nets(DEV, structured=True, precision=prec)
+        out = coarse.query_rays(ro.to(DEV), rd.to(DEV), z.to(DEV))
+        (out * cot).sum().backward()
+        grads[prec] = {k: p.grad.clone() for k, p in coarse.named_parameters()}
+    for k in grads["fp32"]:
+        assert rel_l2(grads["bf16"][k], grads["fp32"][k]) < 4e-2, (k, rel_l2(grads["bf16"][k], grads["fp32"][k]))
