@@ -240,6 +240,8 @@ def main():
                 "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
                 "gpu_launches": launches,
                 "kernel_launches_by_entry": {k: v["launches"] for k, v in sorted(prof.items())},
+                "ms_per_step_by_entry": {k: round(sum(a.elapsed_time(b) for a, b in v["events"]) / args.steps, 4)
+                                         for k, v in sorted(prof.items())},
                 "roofline": roof}
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
