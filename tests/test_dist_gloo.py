@@ -1,0 +1,62 @@
+"""CPU suite: the N>1 host logic (row sharding, flattened gradient all-reduce) with world_size 2 on gloo."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ibl_nerf_b200 import training
+    # (1) contiguous row tiles cover [0, n) exactly once
+    n = 1001
+    lo, hi = training.shard_rows(n, rank, world)
+    cover = torch.zeros(n)
+    cover[lo:hi] = 1
+    dist.all_reduce(cover)
+    ok_cover = bool((cover == 1).all())
+    # (2) flattened gradient all-reduce == mean of per-rank gradients (TrainStep.allreduce_grads without a GPU)
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.zeros(5, 3)), torch.nn.Parameter(torch.zeros(7))]
+    for i, p in enumerate(params):
+        p.grad = torch.full_like(p, float(rank + 1 + i))
+    ts = training.TrainStep.__new__(training.TrainStep)
+    ts.params, ts.world = params, world
+    ts.allreduce_grads()
+    want = [sum(r + 1 + i for r in range(world)) / world for i in range(2)]
+    ok_grad = all(torch.allclose(p.grad, torch.full_like(p, w)) for p, w in zip(params, want))
+    q.put((rank, ok_cover, ok_grad))
+    dist.destroy_process_group()
+
+
+def test_shard_rows_and_flat_allreduce_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 1000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert len(res) == 2 and all(a and b for _, a, b in res), res
+
+
+def test_shard_rows_edge_cases():
+    sys.path.insert(0, ROOT)
+    from ibl_nerf_b200 import training
+    for n in (0, 1, 7, 8, 4096):
+        for w in (1, 2, 4, 8):
+            seen = []
+            for r in range(w):
+                lo, hi = training.shard_rows(n, r, w)
+                assert 0 <= lo <= hi <= n
+                seen += list(range(lo, hi))
+            assert seen == list(range(n))
