@@ -243,6 +243,10 @@ def main():
                 "ms_per_step_by_entry": {k: round(sum(a.elapsed_time(b) for a, b in v["events"]) / args.steps, 4)
                                          for k, v in sorted(prof.items())},
                 "roofline": roof}
+        if mlp and mlp["events"] and len(mlp["events"]) % args.steps == 0:
+            per = len(mlp["events"]) // args.steps
+            line["mlp_fwd_launch_ms"] = [round(sum(mlp["events"][i * per + j][0].elapsed_time(mlp["events"][i * per + j][1])
+                                                   for i in range(args.steps)) / args.steps, 4) for j in range(per)]
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             sample = 256

@@ -23,7 +23,6 @@ namespace mlp {
 struct FwdParams {
   const uint8_t* packed;     // chunk stream + const section
   PointGen gen;
-  int sigma_only;
   float* out;                // [P] or [P,18]
   uint8_t* saved;            // activation stash (SV_BYTES per tile) or nullptr
   long long n_tiles;
@@ -31,9 +30,127 @@ struct FwdParams {
 
 __device__ __forceinline__ int n_chunks_of(const Step& st) { return (st.aux_first + st.kb_act + st.aux_last) * (st.n / 128); }
 
+// per-thread epilogue state
+struct Heads {
+  float sigma, rough, irr, alb[3], rad[4][3];
+};
+struct EpiCtx {
+  uint8_t* act;            // activation tile of the slot (A operand of the next step)
+  const float* bias_s;     // smem: bias row of the current step
+  const float* heads_s;    // smem (the slot's idle encoding tile): small-head weight table of the current step
+  const float* cst;        // global const section
+  uint8_t* rec;            // stash record of the tile (STASH only)
+  uint32_t off[8];         // swizzled byte offset of logical 16-byte chunk c in this thread's row
+  uint32_t t_lane;         // TMEM address of this thread's lane, column 0 of the slot accumulator
+  int row;
+};
+
+enum Kind : int { K_RELU_ACT, K_L7_SIGMA, K_L7_FULL, K_AF, K_FEATURE, K_VIEW, K_ADD01, K_ADD2 };
+
+// One 32-column chunk of the accumulator: bias, activation, pack, store, small-head dot products.
+template <int KIND, bool STASH>
+__device__ __forceinline__ void process_chunk(const EpiCtx& c, Heads& hd, const uint32_t (&v)[32], int cc, int sv_blk,
+                                              uint32_t& mask_word) {
+  float h[32];
+  const float4* b4 = reinterpret_cast<const float4*>(c.bias_s + cc * 32);
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) {
+    const float4 b = b4[j4];
+    const float2 r0 = fadd2(make_float2(__uint_as_float(v[4 * j4]), __uint_as_float(v[4 * j4 + 1])), make_float2(b.x, b.y));
+    const float2 r1 = fadd2(make_float2(__uint_as_float(v[4 * j4 + 2]), __uint_as_float(v[4 * j4 + 3])), make_float2(b.z, b.w));
+    h[4 * j4] = r0.x; h[4 * j4 + 1] = r0.y; h[4 * j4 + 2] = r1.x; h[4 * j4 + 3] = r1.y;
+  }
+  if (STASH && KIND != K_FEATURE) {      // relu bit mask from the sign bits of the pre-activation
+    uint32_t m = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) m = (m >> 1) | (__float_as_uint(h[j]) & 0x80000000u);
+    mask_word = ~m;
+  }
+  constexpr bool kWriteAct = KIND == K_RELU_ACT || KIND == K_L7_FULL || KIND == K_FEATURE || KIND == K_VIEW;
+  constexpr bool kNeedF32Relu = KIND != K_RELU_ACT && KIND != K_FEATURE;     // heads consume fp32 relu(h)
+  if (kNeedF32Relu) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) h[j] = fmaxf(h[j], 0.f);
+  }
+  if (kWriteAct || (STASH && KIND != K_L7_SIGMA)) {
+    const int kb = cc >> 1;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint4 pk;
+      if (KIND == K_RELU_ACT)
+        pk = make_uint4(pack_bf16x2_relu(h[8 * q], h[8 * q + 1]), pack_bf16x2_relu(h[8 * q + 2], h[8 * q + 3]),
+                        pack_bf16x2_relu(h[8 * q + 4], h[8 * q + 5]), pack_bf16x2_relu(h[8 * q + 6], h[8 * q + 7]));
+      else
+        pk = make_uint4(pack_bf16x2(h[8 * q], h[8 * q + 1]), pack_bf16x2(h[8 * q + 2], h[8 * q + 3]),
+                        pack_bf16x2(h[8 * q + 4], h[8 * q + 5]), pack_bf16x2(h[8 * q + 6], h[8 * q + 7]));
+      const uint32_t o = c.off[(cc & 1) * 4 + q];
+      if (kWriteAct) *reinterpret_cast<uint4*>(c.act + kb * KB_BYTES + o) = pk;
+      else *reinterpret_cast<uint4*>(c.rec + (size_t)(sv_blk + kb) * KB_BYTES + o) = pk;   // STASH only (AF / ADD): no smem copy exists
+    }
+  }
+  if (KIND == K_L7_SIGMA) {
+    const float4* w = reinterpret_cast<const float4*>(c.heads_s) + cc * 8;
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) {
+      const float4 ww = w[j4];
+      hd.sigma = fmaf(h[4 * j4], ww.x, hd.sigma); hd.sigma = fmaf(h[4 * j4 + 1], ww.y, hd.sigma);
+      hd.sigma = fmaf(h[4 * j4 + 2], ww.z, hd.sigma); hd.sigma = fmaf(h[4 * j4 + 3], ww.w, hd.sigma);
+    }
+  } else if (KIND == K_L7_FULL) {
+    const float2* w = reinterpret_cast<const float2*>(c.heads_s) + cc * 32;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { const float2 ww = w[j]; hd.sigma = fmaf(h[j], ww.x, hd.sigma); hd.rough = fmaf(h[j], ww.y, hd.rough); }
+  } else if (KIND == K_AF) {
+    const float4* w = reinterpret_cast<const float4*>(c.heads_s) + cc * 32;
+    if (cc < 4) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { const float4 ww = w[j]; hd.alb[0] = fmaf(h[j], ww.x, hd.alb[0]); hd.alb[1] = fmaf(h[j], ww.y, hd.alb[1]); hd.alb[2] = fmaf(h[j], ww.z, hd.alb[2]); }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { const float4 ww = w[j]; hd.irr = fmaf(h[j], ww.x, hd.irr); }
+    }
+  } else if (KIND == K_VIEW) {
+    const float4* w = reinterpret_cast<const float4*>(c.heads_s) + cc * 32;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { const float4 ww = w[j]; hd.rad[0][0] = fmaf(h[j], ww.x, hd.rad[0][0]); hd.rad[0][1] = fmaf(h[j], ww.y, hd.rad[0][1]); hd.rad[0][2] = fmaf(h[j], ww.z, hd.rad[0][2]); }
+  } else if (KIND == K_ADD01 || KIND == K_ADD2) {
+    const int head = (KIND == K_ADD2) ? 2 : (cc >> 2);
+    const float4* w = reinterpret_cast<const float4*>(c.heads_s) + cc * 32;     // table holds exactly this step's heads
+    float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { const float4 ww = w[j]; r0 = fmaf(h[j], ww.x, r0); r1 = fmaf(h[j], ww.y, r1); r2 = fmaf(h[j], ww.z, r2); }
+    hd.rad[1 + head][0] += r0; hd.rad[1 + head][1] += r1; hd.rad[1 + head][2] += r2;
+  }
+}
+
+// Drain NCHUNK*32 accumulator columns with the TMEM loads software-pipelined one chunk ahead.
+template <int KIND, bool STASH, int NCHUNK>
+__device__ __forceinline__ void drain(const EpiCtx& c, Heads& hd, int sv_blk, int sv_mask) {
+  uint32_t mw[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) mw[i] = 0;
+  uint32_t va[32], vb[32];
+  tmem_ld32(c.t_lane, va);
+#pragma unroll
+  for (int cc = 0; cc < NCHUNK; cc += 2) {
+    tmem_wait_ld();
+    tmem_ld32(c.t_lane + (cc + 1) * 32, vb);
+    process_chunk<KIND, STASH>(c, hd, va, cc, sv_blk, mw[cc]);
+    tmem_wait_ld();
+    if (cc + 2 < NCHUNK) tmem_ld32(c.t_lane + (cc + 2) * 32, va);
+    process_chunk<KIND, STASH>(c, hd, vb, cc + 1, sv_blk, mw[cc + 1]);
+  }
+  if (STASH && KIND != K_FEATURE) {      // one full 32-byte sector per row: [mask slot][row][8 words]
+    uint4* dst = reinterpret_cast<uint4*>(c.rec + (size_t)SV_MASK * KB_BYTES + sv_mask * 4096 + c.row * 32);
+    dst[0] = make_uint4(mw[0], mw[1], mw[2], mw[3]);
+    dst[1] = make_uint4(mw[4], mw[5], mw[6], mw[7]);
+  }
+}
+
+template <bool SIGMA_ONLY, bool STASH>
 __global__ void __launch_bounds__(N_THREADS, 1) mlp_fwd_kernel(FwdParams prm) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_BAR);
   uint64_t* w_full = bars;                 // [N_STAGES]
   uint64_t* w_empty = bars + N_STAGES;     // [N_STAGES]
@@ -42,7 +159,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_fwd_kernel(FwdParams prm) {
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * N_STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_steps = prm.sigma_only ? N_STEPS_SIGMA : N_STEPS_FULL;
+  constexpr int n_steps = SIGMA_ONLY ? N_STEPS_SIGMA : N_STEPS_FULL;
   // tiles of this CTA: t = blockIdx.x + k * gridDim.x, k-th tile goes to slot k & 1
   const long long my_tiles = (prm.n_tiles > (long long)blockIdx.x) ? (prm.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
@@ -127,138 +244,132 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_fwd_kernel(FwdParams prm) {
     const int slot = (warp - 2) >> 2;
     const int quarter = warp & 3;                   // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;
-    uint8_t* act = smem + SMEM_ACT + slot * ACT_BYTES;
+    const int gtid = threadIdx.x - 64 - slot * 128; // 0..127 inside the group
     uint8_t* aux = smem + SMEM_AUX + slot * AUX_BYTES;
-    const float* cst = reinterpret_cast<const float*>(prm.packed + PACKED_CONST_OFF);
-    const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + slot * 256;
+    float* bias_s = reinterpret_cast<float*>(smem + SMEM_BIAS + slot * 1024);
+    EpiCtx c;
+    c.act = smem + SMEM_ACT + slot * ACT_BYTES;
+    c.bias_s = bias_s;
+    c.heads_s = reinterpret_cast<const float*>(aux);
+    c.cst = reinterpret_cast<const float*>(prm.packed + PACKED_CONST_OFF);
+    c.rec = nullptr;
+    c.row = row;
+    c.t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + slot * 256;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) c.off[q] = swz_offset(row, q);
     uint32_t acc_phase = 0;
+    // bias row of step `s` -> smem (each thread 2 floats); consumed after the group barrier of that step
+    auto load_bias = [&](int s) {
+      reinterpret_cast<float2*>(bias_s)[gtid] = __ldg(reinterpret_cast<const float2*>(c.cst + C_BIAS + s * 256) + gtid);
+    };
+    // small-head weight table of a head step -> the slot's encoding tile, which is idle during every head epilogue
+    // (positional encoding is dead after L5, the view encoding after the view GEMM)
+    auto load_heads = [&](int s) {
+      const int off = SIGMA_ONLY ? C_SIG : (s == 7 ? C_SR : s == 8 ? C_AF : s == 10 ? C_RAD : s == 11 ? C_ADD : C_ADD + 1024);
+      const int n4 = SIGMA_ONLY ? 64 : (s == 7 ? 128 : s == 12 ? 128 : 256);
+      const float4* src = reinterpret_cast<const float4*>(c.cst + off);
+      float4* dst = reinterpret_cast<float4*>(aux);
+      for (int i = gtid; i < n4; i += 128) dst[i] = __ldg(src + i);
+    };
+    auto publish = [&]() {
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&act_ready[slot]);
+    };
+    // STASH: a finished shared-memory tile goes to the stash record as ONE bulk (TMA) store issued by one thread
+    // after the group barrier; the tile may only be overwritten after cp.async.bulk.wait_group.read
+    auto stash_tile = [&](const uint8_t* tile_smem, int blk, int nblk) {
+      if (gtid == 0) { bulk_s2g(c.rec + (size_t)blk * KB_BYTES, tile_smem, (uint32_t)nblk * KB_BYTES); bulk_commit(); }
+    };
     for (long long k = slot; k < my_tiles; k += 2) {
       const long long tile = blockIdx.x + k * gridDim.x;
       const long long p = tile * TILE_M + row;
       const bool valid = p < prm.gen.P;
       float x[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 0.f};
       if (valid) gen_point(prm.gen, p, x, dir);
-      uint8_t* rec = prm.saved ? prm.saved + (size_t)tile * SV_BYTES : nullptr;
-      write_encoding<10, 8>(aux, row, x, rec ? rec + (size_t)SV_PE * KB_BYTES : nullptr);
-      fence_proxy_async();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&act_ready[slot]);
+      if (STASH) c.rec = prm.saved + (size_t)tile * SV_BYTES;
+      load_bias(0);
+      write_encoding<10, 8>(aux, row, x);
+      if (STASH) {
+        fence_proxy_async();
+        named_bar_sync(1 + slot, 128);
+        stash_tile(aux, SV_PE, 1);
+      }
+      publish();
 
-      float o_sigma = 0.f, o_rough = 0.f, o_alb[3] = {0.f, 0.f, 0.f}, o_irr = 0.f;
-      float o_rad[4][3];
+      Heads hd;
+      hd.sigma = hd.rough = hd.irr = 0.f;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) hd.alb[a] = 0.f;
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int c = 0; c < 3; ++c) o_rad[a][c] = 0.f;
+        for (int q = 0; q < 3; ++q) hd.rad[a][q] = 0.f;
 
+#pragma unroll 1
       for (int s = 0; s < n_steps; ++s) {
-        const Step st = step_at(s);
         mbar_wait(&acc_ready[slot], acc_phase);
         acc_phase ^= 1;
         tc_fence_after();
-        const float* bias = cst + C_BIAS + s * 256;
-        const bool write_act = (st.epi == EPI_RELU_ACT) || (st.epi == EPI_FEATURE) || (st.epi == EPI_VIEW) ||
-                               (st.epi == EPI_L7 && !prm.sigma_only);
-        // stash destination of this step's output tile and its relu-mask slot
-        const int sv_blk = s <= 7 ? SV_H(s) : s == 8 ? SV_AF : s == 9 ? SV_FEAT : s == 10 ? SV_HV : s == 11 ? SV_ADDF : SV_ADDF + 4;
-        const int sv_mask = s <= 7 ? s : s == 8 ? 8 : s == 10 ? 9 : s == 11 ? 10 : s == 12 ? 11 : -1;
-        uint32_t* mask_row = (rec && sv_mask >= 0)
-                                 ? reinterpret_cast<uint32_t*>(rec + (size_t)SV_MASK * KB_BYTES + sv_mask * 4096 + row * 32) : nullptr;
-        for (int cc = 0; cc < st.n / 32; ++cc) {
-          uint32_t v[32];
-          tmem_ld32(t_lane + cc * 32, v);
-          tmem_wait_ld();
-          float h[32];
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            float4 b = __ldg(reinterpret_cast<const float4*>(bias + cc * 32 + 4 * j4));
-            h[4 * j4 + 0] = __uint_as_float(v[4 * j4 + 0]) + b.x;
-            h[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) + b.y;
-            h[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) + b.z;
-            h[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) + b.w;
-          }
-          if (mask_row != nullptr) {        // bit j = (pre-activation >= 0), gathered from the sign bits
-            uint32_t m = 0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) m = (m >> 1) | (__float_as_uint(h[j]) & 0x80000000u);
-            mask_row[cc] = ~m;
-          }
-          if (st.epi != EPI_FEATURE) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) h[j] = fmaxf(h[j], 0.f);
-          }
-          if (write_act || rec != nullptr) {
-            const int kb = cc >> 1;                    // 64 columns per K-block
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int c16 = (cc & 1) * 4 + q;
-              uint4 pk = make_uint4(pack_bf16x2(h[8 * q], h[8 * q + 1]), pack_bf16x2(h[8 * q + 2], h[8 * q + 3]),
-                                    pack_bf16x2(h[8 * q + 4], h[8 * q + 5]), pack_bf16x2(h[8 * q + 6], h[8 * q + 7]));
-              if (write_act) *reinterpret_cast<uint4*>(act + kb * KB_BYTES + swz_offset(row, c16)) = pk;
-              if (rec != nullptr) *reinterpret_cast<uint4*>(rec + (size_t)(sv_blk + kb) * KB_BYTES + swz_offset(row, c16)) = pk;
-            }
-          }
-          if (st.epi == EPI_L7) {
-            const float2* w = reinterpret_cast<const float2*>(cst + C_SR) + cc * 32;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) { float2 ww = __ldg(w + j); o_sigma = fmaf(h[j], ww.x, o_sigma); o_rough = fmaf(h[j], ww.y, o_rough); }
-          } else if (st.epi == EPI_AF) {
-            const float4* w = reinterpret_cast<const float4*>(cst + C_AF) + cc * 32;
-            if (cc < 4) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) { float4 ww = __ldg(w + j); o_alb[0] = fmaf(h[j], ww.x, o_alb[0]); o_alb[1] = fmaf(h[j], ww.y, o_alb[1]); o_alb[2] = fmaf(h[j], ww.z, o_alb[2]); }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) { float4 ww = __ldg(w + j); o_irr = fmaf(h[j], ww.x, o_irr); }
-            }
-          } else if (st.epi == EPI_VIEW) {
-            const float4* w = reinterpret_cast<const float4*>(cst + C_RAD) + cc * 32;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) { float4 ww = __ldg(w + j); o_rad[0][0] = fmaf(h[j], ww.x, o_rad[0][0]); o_rad[0][1] = fmaf(h[j], ww.y, o_rad[0][1]); o_rad[0][2] = fmaf(h[j], ww.z, o_rad[0][2]); }
-          } else if (st.epi == EPI_ADD01 || st.epi == EPI_ADD2) {
-            const int head = (st.epi == EPI_ADD2) ? 2 : (cc >> 2);       // 128 columns per head
-            const float4* w = reinterpret_cast<const float4*>(cst + C_ADD) + head * 128 + (cc & 3) * 32;
-            float r0 = 0.f, r1 = 0.f, r2 = 0.f;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) { float4 ww = __ldg(w + j); r0 = fmaf(h[j], ww.x, r0); r1 = fmaf(h[j], ww.y, r1); r2 = fmaf(h[j], ww.z, r2); }
-            if (head == 0) { o_rad[1][0] += r0; o_rad[1][1] += r1; o_rad[1][2] += r2; }
-            else if (head == 1) { o_rad[2][0] += r0; o_rad[2][1] += r1; o_rad[2][2] += r2; }
-            else { o_rad[3][0] += r0; o_rad[3][1] += r1; o_rad[3][2] += r2; }
-          }
+        if (STASH && gtid == 0) bulk_wait_read0();    // earlier bulk stores have finished reading act / aux
+        if (!SIGMA_ONLY && s == 10) { if (STASH) named_bar_sync(1 + slot, 128); load_heads(10); }   // view encoding consumed: reuse its tile
+        named_bar_sync(1 + slot, 128);       // bias row (+ head table) of this step are in smem
+        switch (s) {
+          case 7:
+            if (SIGMA_ONLY) drain<K_L7_SIGMA, false, 8>(c, hd, 0, 0);
+            else drain<K_L7_FULL, STASH, 8>(c, hd, SV_H(7), 7);
+            break;
+          case 8: drain<K_AF, STASH, 8>(c, hd, SV_AF, 8); break;
+          case 9:
+            drain<K_FEATURE, STASH, 8>(c, hd, SV_FEAT, 0);
+            write_encoding<4, 4>(aux, row, dir);   // view encoding for step 10
+            break;
+          case 10: drain<K_VIEW, STASH, 8>(c, hd, SV_HV, 9); break;
+          case 11: drain<K_ADD01, STASH, 8>(c, hd, SV_ADDF, 10); break;
+          case 12: drain<K_ADD2, STASH, 4>(c, hd, SV_ADDF + 4, 11); break;
+          default: drain<K_RELU_ACT, STASH, 8>(c, hd, SV_H(s), s); break;
         }
-        if (st.epi == EPI_FEATURE) write_encoding<4, 4>(aux, row, dir, rec ? rec + (size_t)SV_DE * KB_BYTES : nullptr);   // view encoding for the next step
         if (s + 1 < n_steps) {
-          fence_proxy_async();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&act_ready[slot]);
+          if (STASH) fence_proxy_async();    // this step's tile writes -> visible to the bulk-store (async) proxy
+          named_bar_sync(1 + slot, 128);     // everyone is done reading this step's bias row / head table
+          if (STASH) {
+            if (s <= 7) stash_tile(c.act, SV_H(s), 4);
+            else if (s == 9) { stash_tile(c.act, SV_FEAT, 4); stash_tile(aux, SV_DE, 1); }
+            else if (s == 10) stash_tile(c.act, SV_HV, 4);
+          }
+          load_bias(s + 1);
+          if (s + 1 == 7 || (!SIGMA_ONLY && (s + 1 == 8 || s + 1 == 11 || s + 1 == 12))) load_heads(s + 1);
+          publish();
         }
       }
       // ---- outputs
       if (valid) {
-        o_sigma += __ldg(cst + C_SR + 512);
-        if (prm.sigma_only) {
-          prm.out[p] = o_sigma;
+        hd.sigma += __ldg(c.cst + C_SR + 512);
+        if (SIGMA_ONLY) {
+          prm.out[p] = hd.sigma;
         } else {
           float r[18];
-          r[0] = o_sigma;
-          r[1] = o_alb[0] + __ldg(cst + C_AF + 1024); r[2] = o_alb[1] + __ldg(cst + C_AF + 1025); r[3] = o_alb[2] + __ldg(cst + C_AF + 1026);
-          r[4] = o_rough + __ldg(cst + C_SR + 513);
-          r[5] = o_irr + __ldg(cst + C_AF + 1027);
+          r[0] = hd.sigma;
+          r[1] = hd.alb[0] + __ldg(c.cst + C_AF + 1024); r[2] = hd.alb[1] + __ldg(c.cst + C_AF + 1025); r[3] = hd.alb[2] + __ldg(c.cst + C_AF + 1026);
+          r[4] = hd.rough + __ldg(c.cst + C_SR + 513);
+          r[5] = hd.irr + __ldg(c.cst + C_AF + 1027);
 #pragma unroll
-          for (int c = 0; c < 3; ++c) r[6 + c] = o_rad[0][c] + __ldg(cst + C_RAD + 1024 + c);
+          for (int q = 0; q < 3; ++q) r[6 + q] = hd.rad[0][q] + __ldg(c.cst + C_RAD + 1024 + q);
 #pragma unroll
           for (int a = 0; a < 3; ++a)
 #pragma unroll
-            for (int c = 0; c < 3; ++c) r[9 + 3 * a + c] = o_rad[1 + a][c] + __ldg(cst + C_ADD + 1536 + 4 * a + c);
+            for (int q = 0; q < 3; ++q) r[9 + 3 * a + q] = hd.rad[1 + a][q] + __ldg(c.cst + C_ADD + 1536 + 4 * a + q);
           float2* dst = reinterpret_cast<float2*>(prm.out + p * 18);
 #pragma unroll
           for (int j = 0; j < 9; ++j) dst[j] = make_float2(r[2 * j], r[2 * j + 1]);
         }
       }
+      if (STASH && gtid == 0) bulk_wait_read0();
+      named_bar_sync(1 + slot, 128);         // last step's bias row no longer needed (next tile overwrites it)
       tc_fence_before();   // order this tile's TMEM reads before the next tile's act_ready arrival
     }
+    if (STASH && gtid == 0) bulk_wait0();    // all stash writes complete before the CTA exits
   }
   tc_fence_before();
   __syncthreads();
@@ -368,14 +479,19 @@ extern "C" int ibln_mlp_fwd(const void* packed, int mode, const float* pts, cons
   prm.gen.pts = pts; prm.gen.o = rays_o; prm.gen.d = rays_d; prm.gen.z = z;
   prm.gen.n_rays = n_rays; prm.gen.S = n_samples; prm.gen.eps = eps; prm.gen.mode = mode;
   prm.gen.P = n_rays * n_samples * (mode == 2 ? 4 : 1);
-  prm.sigma_only = sigma_only;
   prm.out = out;
   prm.saved = (uint8_t*)saved;
   prm.n_tiles = (prm.gen.P + TILE_M - 1) / TILE_M;
-  IBLN_CUDA(cudaFuncSetAttribute(mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_REQUEST));
   long long grid = prm.n_tiles < (long long)num_sms(device) ? prm.n_tiles : (long long)num_sms(device);
-  mlp_fwd_kernel<<<(unsigned)grid, N_THREADS, SMEM_REQUEST, (cudaStream_t)stream>>>(prm);
-  IBLN_RETURN_LAST();
+  auto launch = [&](auto kern) -> int {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_REQUEST);
+    if (e != cudaSuccess) return (int)e;
+    kern<<<(unsigned)grid, N_THREADS, SMEM_REQUEST, (cudaStream_t)stream>>>(prm);
+    return (int)cudaGetLastError();
+  };
+  if (sigma_only) return launch(mlp_fwd_kernel<true, false>);
+  if (saved) return launch(mlp_fwd_kernel<false, true>);
+  return launch(mlp_fwd_kernel<false, false>);
 }
 
 extern "C" int ibln_umma_selftest(const float* a, const float* b, float* d, int n, int k, int variant, int device, void* stream) {

@@ -17,9 +17,11 @@ constexpr int AUX_BYTES = KB_BYTES;      // positional / view-direction encoding
 constexpr int SMEM_ACT = 0;
 constexpr int SMEM_AUX = 2 * ACT_BYTES;
 constexpr int SMEM_RING = SMEM_AUX + 2 * AUX_BYTES;
-constexpr int SMEM_BAR = SMEM_RING + N_STAGES * KB_BYTES;
+constexpr int SMEM_BIAS = SMEM_RING + N_STAGES * KB_BYTES;   // per-slot fp32 bias row of the current step (2 x 1 KB)
+constexpr int SMEM_BAR = SMEM_BIAS + 2 * 1024;
 constexpr int SMEM_TOTAL = SMEM_BAR + 256;
-constexpr int SMEM_REQUEST = SMEM_TOTAL + 1024;   // slack for manual 1024-byte alignment
+constexpr int SMEM_REQUEST = SMEM_TOTAL;          // dynamic smem starts 1024-aligned (checked at kernel entry)
+static_assert(SMEM_REQUEST <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
 constexpr int N_THREADS = 320;
 
 // ---------------------------------------------------------------- step program
@@ -57,7 +59,8 @@ constexpr int C_SR = C_BIAS + 13 * 256;      // float2[256] {w_sigma, w_rough}, 
 constexpr int C_AF = C_SR + 512 + 4;         // float4[256] albedo(3)|irradiance(1) weights, then 4 biases
 constexpr int C_RAD = C_AF + 1024 + 4;       // float4[256] radiance weights, then 3 biases + pad
 constexpr int C_ADD = C_RAD + 1024 + 4;      // float4[384] coarse radiance weights, then 3x(3 biases + pad)
-constexpr int C_TOTAL = C_ADD + 1536 + 12;
+constexpr int C_SIG = C_ADD + 1536 + 12;     // float[256] sigma weights alone (sigma-only path, float4 loads)
+constexpr int C_TOTAL = C_SIG + 256;
 constexpr int N_CHUNKS_BWD = 92;             // transposed weight chunks of the dgrad chain (mlp_tc_bwd.cu)
 constexpr int64_t PACKED_CONST_OFF = (int64_t)N_CHUNKS * KB_BYTES;
 constexpr int64_t PACKED_BWD_OFF = PACKED_CONST_OFF + (int64_t)C_TOTAL * 4;
@@ -164,6 +167,8 @@ static __global__ void pack_consts_kernel(PackArgs a, float* __restrict__ cst) {
     int j = i - C_RAD;
     if (j < 1024) { int col = j >> 2, q = j & 3; v = q < 3 ? a.p[32][q * 256 + col] : 0.f; }
     else { int q = j - 1024; v = q < 3 ? a.p[33][q] : 0.f; }
+  } else if (i >= C_SIG) {
+    v = a.p[20][i - C_SIG];
   } else {
     int j = i - C_ADD;
     if (j < 1536) { int col = j >> 2, q = j & 3; int k = col / 128, cc = col % 128; v = q < 3 ? a.p[40 + 2 * k][q * 128 + cc] : 0.f; }

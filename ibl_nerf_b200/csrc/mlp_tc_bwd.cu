@@ -99,14 +99,13 @@ struct DgradParams {
   long long n_tiles;
 };
 
-__device__ __forceinline__ void store_tile4(uint8_t* act, uint8_t* g, int kb, int row, int c16, uint4 pk) {
-  if (act != nullptr) *reinterpret_cast<uint4*>(act + kb * KB_BYTES + swz_offset(row, c16)) = pk;
-  *reinterpret_cast<uint4*>(g + (size_t)kb * KB_BYTES + swz_offset(row, c16)) = pk;
+__device__ __forceinline__ void store_tile4(uint8_t* tile, int kb, uint32_t swz, uint4 pk) {
+  *reinterpret_cast<uint4*>(tile + (size_t)kb * KB_BYTES + swz) = pk;
 }
 
 __global__ void __launch_bounds__(N_THREADS, 1) mlp_dgrad_kernel(DgradParams prm) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_BAR);
   uint64_t* w_full = bars;
   uint64_t* w_empty = bars + N_STAGES;
@@ -188,6 +187,23 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_dgrad_kernel(DgradParams prm
     const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + slot * 256;
     const FlatOff fo = flat_offsets();
     uint32_t acc_phase = 0;
+    // small-head weight tables -> the slot's (otherwise unused) encoding tile, once per kernel:
+    // [coarse radiance 0..2: 384 float4][albedo|irradiance: 256 float4][radiance: 256 float4][sigma,rough: 128 float4]
+    const float* tab = reinterpret_cast<const float*>(smem + SMEM_AUX + slot * AUX_BYTES);
+    const float* T_ADD = tab; const float* T_AF = tab + 1536; const float* T_RAD = tab + 2560; const float* T_SR = tab + 3584;
+    const int gtid = threadIdx.x - 64 - slot * 128;
+    {
+      float4* dst = reinterpret_cast<float4*>(smem + SMEM_AUX + slot * AUX_BYTES);
+      for (int i = gtid; i < 1024; i += 128) {
+        const float* src = i < 384 ? cst + C_ADD + 4 * i : i < 640 ? cst + C_AF + 4 * (i - 384)
+                         : i < 896 ? cst + C_RAD + 4 * (i - 640) : cst + C_SR + 4 * (i - 896);
+        dst[i] = __ldg(reinterpret_cast<const float4*>(src));
+      }
+      named_bar_sync(1 + slot, 128);
+    }
+    uint32_t off[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) off[q] = swz_offset(row, q);
     for (long long k = slot; k < my_tiles; k += 2) {
       const long long tile = blockIdx.x + k * gridDim.x;
       const long long p = tile * TILE_M + row;
@@ -227,7 +243,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_dgrad_kernel(DgradParams prm
         for (int j = 0; j < 64; ++j) e[j] = j < 18 ? g[j] : 0.f;
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch)
-          store_tile4(nullptr, dy + (size_t)DY_G * KB_BYTES, 0, row, ch,
+          store_tile4(dy + (size_t)DY_G * KB_BYTES, 0, swz_offset(row, ch),
                       make_uint4(pack_bf16x2(e[8 * ch], e[8 * ch + 1]), pack_bf16x2(e[8 * ch + 2], e[8 * ch + 3]),
                                  pack_bf16x2(e[8 * ch + 4], e[8 * ch + 5]), pack_bf16x2(e[8 * ch + 6], e[8 * ch + 7])));
       }
@@ -243,45 +259,57 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_dgrad_kernel(DgradParams prm
         for (int cc = 0; cc < ncc; ++cc) {
           float v[32];
           if (which == 2) {
-            const float4* w = reinterpret_cast<const float4*>(cst + C_AF) + cc * 32;
+            const float4* w = reinterpret_cast<const float4*>(T_AF) + cc * 32;
             if (cc < 4) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) { float4 ww = __ldg(w + j); v[j] = g[1] * ww.x + g[2] * ww.y + g[3] * ww.z; }
+              for (int j = 0; j < 32; ++j) { float4 ww = w[j]; v[j] = g[1] * ww.x + g[2] * ww.y + g[3] * ww.z; }
             } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) { float4 ww = __ldg(w + j); v[j] = g[5] * ww.x; }
+              for (int j = 0; j < 32; ++j) { float4 ww = w[j]; v[j] = g[5] * ww.x; }
             }
           } else {
             const int head = which == 1 ? 2 : (cc >> 2);
-            const float4* w = reinterpret_cast<const float4*>(cst + C_ADD) + head * 128 + (cc & 3) * 32;
+            const float4* w = reinterpret_cast<const float4*>(T_ADD) + head * 128 + (cc & 3) * 32;
             const float g0 = g[9 + 3 * head], g1 = g[10 + 3 * head], g2 = g[11 + 3 * head];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) { float4 ww = __ldg(w + j); v[j] = g0 * ww.x + g1 * ww.y + g2 * ww.z; }
+            for (int j = 0; j < 32; ++j) { float4 ww = w[j]; v[j] = g0 * ww.x + g1 * ww.y + g2 * ww.z; }
           }
           const uint32_t m = mw[cc];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = ((m >> j) & 1u) ? v[j] : 0.f;
 #pragma unroll
           for (int q = 0; q < 4; ++q)
-            store_tile4(act, dy + (size_t)dblk * KB_BYTES, cc >> 1, row, (cc & 1) * 4 + q,
+            store_tile4(act, cc >> 1, off[(cc & 1) * 4 + q],
                         make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
                                    pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7])));
         }
       };
-      auto publish = [&]() {
+      // finished gradient tile in `act`: one bulk (TMA) store to the dY record, then hand it to the MMA issuer
+      auto publish = [&](int dblk, int nblk, bool arrive) {
         fence_proxy_async();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&act_ready[slot]);
+        named_bar_sync(1 + slot, 128);
+        if (gtid == 0) { bulk_s2g(dy + (size_t)dblk * KB_BYTES, act, (uint32_t)nblk * KB_BYTES); bulk_commit(); }
+        if (arrive) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&act_ready[slot]);
+        }
       };
+      // before overwriting `act`: the previous bulk store must have finished reading it
+      auto pre_write = [&]() {
+        if (gtid == 0) bulk_wait_read0();
+        named_bar_sync(1 + slot, 128);
+      };
+      pre_write();
       write_head_tile(0);
-      publish();
+      publish(DY_ADDF01, 4, true);
       for (int t = 0; t < N_STEPS_BWD; ++t) {
         mbar_wait(&acc_ready[slot], acc_phase);
         acc_phase ^= 1;
         tc_fence_after();
-        if (t == 0) { write_head_tile(1); publish(); continue; }
-        if (t == 3) { write_head_tile(2); publish(); continue; }
+        pre_write();
+        if (t == 0) { write_head_tile(1); publish(DY_ADDF2, 2, true); continue; }
+        if (t == 3) { write_head_tile(2); publish(DY_AF, 4, true); continue; }
         // drain: t=1 -> dY_view (mask HV, + radiance term); t=2 -> dY_feat (no mask); t=4 -> dY_7 (+ sigma/rough terms);
         // t>=5 -> dY_{11-t} (mask h_{11-t})
         const int mslot = t == 1 ? 9 : t == 2 ? -1 : t == 4 ? 7 : 11 - t;
@@ -296,35 +324,44 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_dgrad_kernel(DgradParams prm
           for (int i = 0; i < 8; ++i) mw[i] = 0xffffffffu;
         }
         const bool last = (t == N_STEPS_BWD - 1);
-        for (int cc = 0; cc < 8; ++cc) {
-          uint32_t raw[32];
-          tmem_ld32(t_lane + cc * 32, raw);
-          tmem_wait_ld();
+        auto chunk = [&](const uint32_t (&raw)[32], int cc) {
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
           if (t == 1) {
-            const float4* w = reinterpret_cast<const float4*>(cst + C_RAD) + cc * 32;
+            const float4* w = reinterpret_cast<const float4*>(T_RAD) + cc * 32;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) { float4 ww = __ldg(w + j); v[j] += g[6] * ww.x + g[7] * ww.y + g[8] * ww.z; }
+            for (int j = 0; j < 32; ++j) { float4 ww = w[j]; v[j] += g[6] * ww.x + g[7] * ww.y + g[8] * ww.z; }
           } else if (t == 4) {
-            const float2* w = reinterpret_cast<const float2*>(cst + C_SR) + cc * 32;
+            const float2* w = reinterpret_cast<const float2*>(T_SR) + cc * 32;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) { float2 ww = __ldg(w + j); v[j] += g[0] * ww.x + g[4] * ww.y; }
+            for (int j = 0; j < 32; ++j) { float2 ww = w[j]; v[j] += g[0] * ww.x + g[4] * ww.y; }
           }
           const uint32_t m = mw[cc];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = ((m >> j) & 1u) ? v[j] : 0.f;
 #pragma unroll
           for (int q = 0; q < 4; ++q)
-            store_tile4(last ? nullptr : act, dy + (size_t)dblk * KB_BYTES, cc >> 1, row, (cc & 1) * 4 + q,
+            store_tile4(act, cc >> 1, off[(cc & 1) * 4 + q],
                         make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
                                    pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7])));
+        };
+        uint32_t ra[32], rb[32];
+        tmem_ld32(t_lane, ra);
+#pragma unroll
+        for (int cc = 0; cc < 8; cc += 2) {
+          tmem_wait_ld();
+          tmem_ld32(t_lane + (cc + 1) * 32, rb);
+          chunk(ra, cc);
+          tmem_wait_ld();
+          if (cc + 2 < 8) tmem_ld32(t_lane + (cc + 2) * 32, ra);
+          chunk(rb, cc + 1);
         }
-        if (!last) publish();
+        publish(dblk, 4, !last);
       }
       tc_fence_before();
     }
+    if (gtid == 0) bulk_wait0();     // all dY stores complete before the CTA exits
   }
   tc_fence_before();
   __syncthreads();
