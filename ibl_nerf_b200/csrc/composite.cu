@@ -1,7 +1,7 @@
 // raw2outputs alpha compositing, forward and backward (north-star subsystem 4).
-// One warp per ray.  The ray's raw[S,C] tile is brought into shared memory with 16-byte cp.async
-// (fully coalesced, double buffered per warp); the transmittance scan is a warp shuffle product scan
-// with a carry across 32-sample rows; per-sample state lives in registers / shared memory only.
+// One warp per ray.  The ray's raw[S,C] block is streamed through shared memory in rows of 32 samples with
+// 16-byte cp.async (fully coalesced, double buffered per warp); the transmittance scan is a warp shuffle
+// product scan with a carry across rows; per-sample state lives in registers / shared memory only.
 #include "common.cuh"
 
 namespace ibln {
@@ -47,34 +47,47 @@ __device__ __forceinline__ RayAlpha row_alpha(float sig, float dist, bool valid,
   return r;
 }
 
+// Row streaming: a ray's raw[S,C] block is consumed in rows of 32 samples (32*C contiguous floats).  Each warp
+// double-buffers rows with 16-byte cp.async and treats (ray, row) as one flat stream, so the next row -- of this
+// ray or of the warp's next ray -- is always in flight while the current one is processed.  ~4.7 KB of shared
+// memory per warp keeps 32+ warps resident per SM, which is what hides the MUFU / shuffle latency.
+constexpr int ROW = 32;
+
+__device__ __forceinline__ void row_load_async(float* dst, const float* __restrict__ raw, int64_t r, int k, int S, int C,
+                                               int lane, bool vec_ok) {
+  const int n_float = min(ROW, S - k * ROW) * C;
+  const float* src = raw + ((int64_t)r * S + (int64_t)k * ROW) * C;
+  if (vec_ok) {
+    for (int i = lane; i < (n_float >> 2); i += 32) cp_async16(dst + 4 * i, src + 4 * i);
+  } else {
+    for (int i = lane; i < n_float; i += 32) dst[i] = src[i];
+  }
+  cp_async_commit();
+}
+
 template <bool SIMPLE>
-__global__ void __launch_bounds__(CP_WARPS * 32)
+__global__ void __launch_bounds__(256)
 composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays_d,
                      const float* __restrict__ noise, int n, int S, int C, int nc, int sigm,
                      float* __restrict__ weights, float* __restrict__ maps, float* __restrict__ maps_srgb,
                      float* __restrict__ pre_out) {
   extern __shared__ __align__(16) float sm[];
-  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = S * C;
-  float* buf0 = sm + (size_t)warp * (2 * tile + 32);
-  float* buf1 = buf0 + tile;
-  float* s_out = buf1 + tile;   // 32 floats of per-ray results
-  const bool vec_ok = (tile % 4 == 0) && ((reinterpret_cast<uintptr_t>(raw) & 15) == 0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rowf = ROW * C;
+  float* buf = sm + (size_t)warp * (2 * rowf + 32);
+  float* s_out = buf + 2 * rowf;
+  // rows must start 16-byte aligned: C*32*4 bytes per row always is; the ray base needs S*C*4 % 16 == 0
+  const bool vec_ok = (((int64_t)S * C) % 4 == 0) && ((reinterpret_cast<uintptr_t>(raw) & 15) == 0);
   const int nwarps = blockDim.x >> 5;
   const int stride = gridDim.x * nwarps;
+  const int nrows = (S + ROW - 1) / ROW;
   int r = blockIdx.x * nwarps + warp;
-  if (r < n) tile_load_async(buf0, raw + (int64_t)r * tile, tile, lane, vec_ok);
+  if (r >= n) return;
+  row_load_async(buf, raw, r, 0, S, C, lane, vec_ok);
   int it = 0;
-  for (; r < n; r += stride, ++it) {
-    float* cur = (it & 1) ? buf1 : buf0;
-    float* nxt = (it & 1) ? buf0 : buf1;
-    int rn = r + stride;
-    if (rn < n) { tile_load_async(nxt, raw + (int64_t)rn * tile, tile, lane, vec_ok); cp_async_wait<1>(); }
-    else cp_async_wait<0>();
-    __syncwarp();
-
-    float dx = rays_d[3 * r], dy = rays_d[3 * r + 1], dz = rays_d[3 * r + 2];
-    float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
+  for (; r < n; r += stride) {
+    const float dx = rays_d[3 * r], dy = rays_d[3 * r + 1], dz = rays_d[3 * r + 2];
+    const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
     const float* zr = z + (int64_t)r * S;
     float carry = 1.0f;
     float a_depth = 0.f, a_acc = 0.f, a_rough = 0.f, a_irr = 0.f;
@@ -82,13 +95,22 @@ composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
 #pragma unroll
     for (int c = 0; c < 15; ++c) a_col[c] = 0.f;   // albedo 0..2, radiance 3..5, coarse 6..14
 
-    for (int base = 0; base < S; base += 32) {
-      int i = base + lane;
-      bool valid = i < S;
-      float zi = valid ? zr[i] : 0.f;
+    for (int k = 0; k < nrows; ++k, ++it) {
+      float* cur = buf + (it & 1) * rowf;
+      float* nxt = buf + ((it + 1) & 1) * rowf;
+      // prefetch the next row of the stream
+      const bool more_rows = k + 1 < nrows;
+      const int rn = more_rows ? r : r + stride;
+      if (rn < n) { row_load_async(nxt, raw, rn, more_rows ? k + 1 : 0, S, C, lane, vec_ok); cp_async_wait<1>(); }
+      else cp_async_wait<0>();
+      __syncwarp();
+
+      const int i = k * ROW + lane;
+      const bool valid = i < S;
+      const float zi = valid ? zr[i] : 0.f;
       float dist = (valid && i < S - 1) ? (zr[i + 1] - zi) : 1e10f;
       dist *= dnorm;
-      const float* px = cur + (size_t)(valid ? i : 0) * C;
+      const float* px = cur + (size_t)(valid ? lane : 0) * C;
       float sig = px[0];
       if (noise != nullptr && valid) sig += noise[(int64_t)r * S + i];
       RayAlpha ra = row_alpha(sig, dist, valid, carry, lane);
@@ -105,12 +127,13 @@ composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
 #pragma unroll
         for (int c = 0; c < 3; ++c) a_col[3 + c] += ra.w * head_act(px[6 + c], sigm);
 #pragma unroll
-        for (int k = 0; k < 3; ++k)
-          if (k < nc) {
+        for (int kk = 0; kk < 3; ++kk)
+          if (kk < nc) {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) a_col[6 + 3 * k + c] += ra.w * head_act(px[9 + 3 * k + c], sigm);
+            for (int c = 0; c < 3; ++c) a_col[6 + 3 * kk + c] += ra.w * head_act(px[9 + 3 * kk + c], sigm);
           }
       }
+      __syncwarp();      // everyone is done with `cur` before it becomes the prefetch target of the next iteration
     }
     // reductions
     if (!SIMPLE) {
@@ -149,164 +172,180 @@ composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
   }
 }
 
-// Backward.  Pass 1 recomputes the forward scan (alpha, T kept in shared memory) and the maps the
-// non-linear outputs need (depth, acc, colour maps for the sRGB derivative); pass 2 walks the ray in
-// reverse for the suffix sum  sum_{k>i} gw_k w_k  and writes g_raw through the staging tile.
-__global__ void __launch_bounds__(CP_WARPS * 32)
+// Backward.  Pass 1 streams the ray's rows forward, recomputing alpha / T (kept in shared memory, 3 floats per
+// sample) and the maps the non-linear outputs need; pass 2 streams the rows again in reverse (L2 hits) for the
+// suffix sum  sum_{k>i} gw_k w_k, builds each row of g_raw in place in the row buffer and writes it out with
+// coalesced 16-byte stores.
+__global__ void __launch_bounds__(256)
 composite_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays_d,
                      const float* __restrict__ noise, const float* __restrict__ g_weights,
                      const float* __restrict__ g_maps, const float* __restrict__ g_srgb, int n, int S, int C, int nc,
                      int sigm, float* __restrict__ g_raw) {
   extern __shared__ __align__(16) float sm[];
-  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = S * C;
-  const int Sp = (S + 31) & ~31;
-  float* cur = sm + (size_t)warp * (tile + 3 * Sp + 32);
-  float* s_alpha = cur + tile;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rowf = ROW * C;
+  const int nrows = (S + ROW - 1) / ROW;
+  const int Sp = nrows * ROW;
+  float* buf = sm + (size_t)warp * (2 * rowf + 3 * Sp + 32);
+  float* s_alpha = buf + 2 * rowf;
   float* s_T = s_alpha + Sp;
   float* s_dist = s_T + Sp;
   float* s_g = s_dist + Sp;     // 24 combined per-ray gradients
-  const bool vec_ok = (tile % 4 == 0) && ((reinterpret_cast<uintptr_t>(raw) & 15) == 0) &&
+  const bool vec_ok = (((int64_t)S * C) % 4 == 0) && ((reinterpret_cast<uintptr_t>(raw) & 15) == 0) &&
                       ((reinterpret_cast<uintptr_t>(g_raw) & 15) == 0);
-  for (int r = blockIdx.x * (blockDim.x >> 5) + warp; r < n; r += gridDim.x * (blockDim.x >> 5)) {
-    tile_load_async(cur, raw + (int64_t)r * tile, tile, lane, vec_ok);
-    float dx = rays_d[3 * r], dy = rays_d[3 * r + 1], dz = rays_d[3 * r + 2];
-    float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
+  const int nwarps = blockDim.x >> 5;
+  const int stride = gridDim.x * nwarps;
+  int r = blockIdx.x * nwarps + warp;
+  if (r >= n) return;
+  // flat task stream per ray: t in [0, 2*nrows): row(t) = t < nrows ? t : 2*nrows-1-t
+  row_load_async(buf, raw, r, 0, S, C, lane, vec_ok);
+  int it = 0;
+  for (; r < n; r += stride) {
+    const float dx = rays_d[3 * r], dy = rays_d[3 * r + 1], dz = rays_d[3 * r + 2];
+    const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
     const float* zr = z + (int64_t)r * S;
-    cp_async_wait<0>();
-    __syncwarp();
-    // ---- pass 1
     float carry = 1.0f;
     float a_depth = 0.f, a_acc = 0.f, a_irr = 0.f;
     float a_col[15];
 #pragma unroll
     for (int c = 0; c < 15; ++c) a_col[c] = 0.f;
-    for (int base = 0; base < S; base += 32) {
-      int i = base + lane;
-      bool valid = i < S;
-      float zi = valid ? zr[i] : 0.f;
-      float dist = (valid && i < S - 1) ? (zr[i + 1] - zi) : 1e10f;
-      dist *= dnorm;
-      const float* px = cur + (size_t)(valid ? i : 0) * C;
-      float sig = px[0];
-      if (noise != nullptr && valid) sig += noise[(int64_t)r * S + i];
-      RayAlpha ra = row_alpha(sig, dist, valid, carry, lane);
-      s_alpha[i] = ra.alpha; s_T[i] = ra.T; s_dist[i] = (sig > 0.f) ? dist : 0.f;
-      if (valid) {
-        a_depth += ra.w * zi; a_acc += ra.w;
-        if (g_srgb != nullptr) {
-          a_irr += ra.w * head_act(px[5], sigm);
+    float gdepth = 0.f, gacc = 0.f, suffix = 0.f;
+
+    for (int t = 0; t < 2 * nrows; ++t, ++it) {
+      float* cur = buf + (it & 1) * rowf;
+      float* nxt = buf + ((it + 1) & 1) * rowf;
+      const bool more = t + 1 < 2 * nrows;
+      const int rn = more ? r : r + stride;
+      const int tn = more ? t + 1 : 0;
+      if (rn < n) { row_load_async(nxt, raw, rn, tn < nrows ? tn : 2 * nrows - 1 - tn, S, C, lane, vec_ok); cp_async_wait<1>(); }
+      else cp_async_wait<0>();
+      __syncwarp();
+      const int k = t < nrows ? t : 2 * nrows - 1 - t;
+      const int i = k * ROW + lane;
+      const bool valid = i < S;
+      const float zi = valid ? zr[i] : 0.f;
+      float* px = cur + (size_t)(valid ? lane : 0) * C;
+
+      if (t < nrows) {
+        // ---- pass 1
+        float dist = (valid && i < S - 1) ? (zr[i + 1] - zi) : 1e10f;
+        dist *= dnorm;
+        float sig = px[0];
+        if (noise != nullptr && valid) sig += noise[(int64_t)r * S + i];
+        RayAlpha ra = row_alpha(sig, dist, valid, carry, lane);
+        s_alpha[i] = ra.alpha; s_T[i] = ra.T; s_dist[i] = (sig > 0.f) ? dist : 0.f;
+        if (valid) {
+          a_depth += ra.w * zi; a_acc += ra.w;
+          if (g_srgb != nullptr) {
+            a_irr += ra.w * head_act(px[5], sigm);
 #pragma unroll
-          for (int c = 0; c < 3; ++c) a_col[c] += ra.w * sigmoidf_fast(px[1 + c]);
+            for (int c = 0; c < 3; ++c) a_col[c] += ra.w * sigmoidf_fast(px[1 + c]);
 #pragma unroll
-          for (int c = 0; c < 3; ++c) a_col[3 + c] += ra.w * head_act(px[6 + c], sigm);
+            for (int c = 0; c < 3; ++c) a_col[3 + c] += ra.w * head_act(px[6 + c], sigm);
 #pragma unroll
-          for (int k = 0; k < 3; ++k)
-            if (k < nc) {
+            for (int kk = 0; kk < 3; ++kk)
+              if (kk < nc) {
 #pragma unroll
-              for (int c = 0; c < 3; ++c) a_col[6 + 3 * k + c] += ra.w * head_act(px[9 + 3 * k + c], sigm);
+                for (int c = 0; c < 3; ++c) a_col[6 + 3 * kk + c] += ra.w * head_act(px[9 + 3 * kk + c], sigm);
+              }
+          }
+        }
+        if (t == nrows - 1) {
+          // ---- end of pass 1: combined per-ray gradients wrt the LINEAR maps
+          a_depth = warp_sum(a_depth); a_acc = warp_sum(a_acc);
+          if (g_srgb != nullptr) {
+            a_irr = warp_sum(a_irr);
+#pragma unroll
+            for (int c = 0; c < 15; ++c) a_col[c] = warp_sum(a_col[c]);
+          }
+          if (lane < IBLN_MAPS_STRIDE) {
+            float g = g_maps ? g_maps[(int64_t)r * IBLN_MAPS_STRIDE + lane] : 0.f;
+            if (g_srgb != nullptr) {
+              float gs = g_srgb[(int64_t)r * IBLN_MAPS_STRIDE + lane];
+              bool colour = (lane == IBLN_MAP_IRR) || (lane >= IBLN_MAP_ALBEDO && lane < IBLN_MAP_COARSE + 9);
+              if (colour) {
+                float lin = (lane == IBLN_MAP_IRR) ? a_irr : 0.f;
+#pragma unroll
+                for (int c = 0; c < 15; ++c) if (lane == IBLN_MAP_ALBEDO + c) lin = a_col[c];
+                g += gs * dsrgbf(lin);
+              } else {
+                g += gs;
+              }
             }
-        }
-      }
-    }
-    a_depth = warp_sum(a_depth); a_acc = warp_sum(a_acc);
-    if (g_srgb != nullptr) {
-      a_irr = warp_sum(a_irr);
-#pragma unroll
-      for (int c = 0; c < 15; ++c) a_col[c] = warp_sum(a_col[c]);
-    }
-    // combined per-ray gradients wrt the LINEAR maps
-    if (lane < IBLN_MAPS_STRIDE) {
-      float g = g_maps ? g_maps[(int64_t)r * IBLN_MAPS_STRIDE + lane] : 0.f;
-      if (g_srgb != nullptr) {
-        float gs = g_srgb[(int64_t)r * IBLN_MAPS_STRIDE + lane];
-        bool colour = (lane == IBLN_MAP_IRR) || (lane >= IBLN_MAP_ALBEDO && lane < IBLN_MAP_COARSE + 9);
-        if (colour) {
-          float lin = (lane == IBLN_MAP_IRR) ? a_irr : 0.f;
-#pragma unroll
-          for (int c = 0; c < 15; ++c) if (lane == IBLN_MAP_ALBEDO + c) lin = a_col[c];
-          g += gs * dsrgbf(lin);
-        } else {
-          g += gs;
-        }
-      }
-      s_g[lane] = g;
-    }
-    __syncwarp();
-    float gdepth = s_g[IBLN_MAP_DEPTH], gacc = s_g[IBLN_MAP_ACC], gdisp = s_g[IBLN_MAP_DISP];
-    if (gdisp != 0.f) {
-      float q = a_depth / a_acc;
-      if (q > 1e-10f) {     // disp = 1/q : d/d depth = -1/(q^2 acc), d/d acc = depth/(q^2 acc^2)
-        float iq2 = 1.0f / (q * q);
-        gdepth += gdisp * (-iq2 / a_acc);
-        gacc += gdisp * (iq2 * a_depth / (a_acc * a_acc));
-      }
-    }
-    // d T_end / d alpha_i = -T_end / om_i  -> folds into the suffix term as an extra "sample" at the end
-    float g_tend = s_g[IBLN_MAP_TEND] * carry;
-    // ---- pass 2 (reverse)
-    float suffix = g_tend;
-    for (int base = (Sp - 32); base >= 0; base -= 32) {
-      int i = base + lane;
-      bool valid = i < S;
-      float* px = cur + (size_t)(valid ? i : 0) * C;
-      float alpha = s_alpha[i], T = s_T[i], w = alpha * T;
-      float zi = valid ? zr[i] : 0.f;
-      float gw = 0.f;
-      float go[18];
-#pragma unroll
-      for (int c = 0; c < 18; ++c) go[c] = 0.f;
-      if (valid) {
-        gw = (g_weights ? g_weights[(int64_t)r * S + i] : 0.f) + gdepth * zi + gacc;
-        // radiance (live weights)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          float x = px[6 + c], y = head_act(x, sigm), gm = s_g[IBLN_MAP_RAD + c];
-          gw += gm * y;
-          go[6 + c] = w * gm * head_dact(x, y, sigm);
-        }
-        // detached-weight heads
-#pragma unroll
-        for (int c = 0; c < 3; ++c) { float x = px[1 + c], y = sigmoidf_fast(x); go[1 + c] = w * s_g[IBLN_MAP_ALBEDO + c] * y * (1.f - y); }
-        { float x = px[4], y = sigmoidf_fast(x); go[4] = w * s_g[IBLN_MAP_ROUGH] * y * (1.f - y); }
-        { float x = px[5], y = head_act(x, sigm); go[5] = w * s_g[IBLN_MAP_IRR] * head_dact(x, y, sigm); }
-#pragma unroll
-        for (int k = 0; k < 3; ++k)
-          if (k < nc) {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              float x = px[9 + 3 * k + c], y = head_act(x, sigm);
-              go[9 + 3 * k + c] = w * s_g[IBLN_MAP_COARSE + 3 * k + c] * head_dact(x, y, sigm);
+            s_g[lane] = g;
+          }
+          __syncwarp();
+          gdepth = s_g[IBLN_MAP_DEPTH]; gacc = s_g[IBLN_MAP_ACC];
+          const float gdisp = s_g[IBLN_MAP_DISP];
+          if (gdisp != 0.f) {
+            float q = a_depth / a_acc;
+            if (q > 1e-10f) {     // disp = 1/q : d/d depth = -1/(q^2 acc), d/d acc = depth/(q^2 acc^2)
+              float iq2 = 1.0f / (q * q);
+              gdepth += gdisp * (-iq2 / a_acc);
+              gacc += gdisp * (iq2 * a_depth / (a_acc * a_acc));
             }
           }
-      }
-      // inclusive suffix scan of gw*w over the row (towards higher lanes)
-      float t = valid ? gw * w : 0.f;
-      float p = t;
+          // d T_end / d alpha_i = -T_end / om_i : enters the suffix term as an extra "sample" past the end
+          suffix = s_g[IBLN_MAP_TEND] * carry;
+        }
+      } else {
+        // ---- pass 2 (reverse)
+        const float alpha = s_alpha[i], T = s_T[i], w = alpha * T;
+        float gw = 0.f;
+        float go[18];
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        float v = __shfl_down_sync(FULL, p, o);
-        if (lane + o < 32) p += v;
-      }
-      float excl = p - t + suffix;          // sum over k > i
-      suffix += __shfl_sync(FULL, p, 0);
-      if (valid) {
-        float om = (1.0f - alpha) + 1e-10f;
-        float galpha = gw * T - excl / om;
-        go[0] = galpha * s_dist[i] * (1.0f - alpha);   // d alpha/d sigma = dist * exp(-sigma dist), 0 where sigma <= 0
+        for (int c = 0; c < 18; ++c) go[c] = 0.f;
+        if (valid) {
+          gw = (g_weights ? g_weights[(int64_t)r * S + i] : 0.f) + gdepth * zi + gacc;
 #pragma unroll
-        for (int c = 0; c < 18; ++c) if (c < C) px[c] = go[c];
-        for (int c = 18; c < C; ++c) px[c] = 0.f;
+          for (int c = 0; c < 3; ++c) {   // radiance (live weights)
+            float x = px[6 + c], y = head_act(x, sigm), gm = s_g[IBLN_MAP_RAD + c];
+            gw += gm * y;
+            go[6 + c] = w * gm * head_dact(x, y, sigm);
+          }
+#pragma unroll
+          for (int c = 0; c < 3; ++c) { float x = px[1 + c], y = sigmoidf_fast(x); go[1 + c] = w * s_g[IBLN_MAP_ALBEDO + c] * y * (1.f - y); }
+          { float x = px[4], y = sigmoidf_fast(x); go[4] = w * s_g[IBLN_MAP_ROUGH] * y * (1.f - y); }
+          { float x = px[5], y = head_act(x, sigm); go[5] = w * s_g[IBLN_MAP_IRR] * head_dact(x, y, sigm); }
+#pragma unroll
+          for (int kk = 0; kk < 3; ++kk)
+            if (kk < nc) {
+#pragma unroll
+              for (int c = 0; c < 3; ++c) {
+                float x = px[9 + 3 * kk + c], y = head_act(x, sigm);
+                go[9 + 3 * kk + c] = w * s_g[IBLN_MAP_COARSE + 3 * kk + c] * head_dact(x, y, sigm);
+              }
+            }
+        }
+        // inclusive suffix scan of gw*w over the row (towards higher lanes)
+        const float tv = valid ? gw * w : 0.f;
+        float p = tv;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          float v = __shfl_down_sync(FULL, p, o);
+          if (lane + o < 32) p += v;
+        }
+        const float excl = p - tv + suffix;          // sum over k > i
+        suffix += __shfl_sync(FULL, p, 0);
+        if (valid) {
+          const float om = (1.0f - alpha) + 1e-10f;
+          const float galpha = gw * T - excl / om;
+          go[0] = galpha * s_dist[i] * (1.0f - alpha);   // d alpha/d sigma = dist * exp(-sigma dist), 0 where sigma <= 0
+#pragma unroll
+          for (int c = 0; c < 18; ++c) if (c < C) px[c] = go[c];
+          for (int c = 18; c < C; ++c) px[c] = 0.f;
+        }
+        __syncwarp();
+        const int n_float = min(ROW, S - k * ROW) * C;
+        float* dst = g_raw + ((int64_t)r * S + (int64_t)k * ROW) * C;
+        if (vec_ok) {
+          for (int e = lane; e < (n_float >> 2); e += 32) reinterpret_cast<float4*>(dst)[e] = reinterpret_cast<float4*>(cur)[e];
+        } else {
+          for (int e = lane; e < n_float; e += 32) dst[e] = cur[e];
+        }
       }
+      __syncwarp();
     }
-    __syncwarp();
-    float* dst = g_raw + (int64_t)r * tile;
-    if (vec_ok) {
-      for (int i = lane; i < (tile >> 2); i += 32) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<float4*>(cur)[i];
-    } else {
-      for (int i = lane; i < tile; i += 32) dst[i] = cur[i];
-    }
-    __syncwarp();
   }
 }
 
@@ -360,16 +399,13 @@ static int launch_fwd(const float* raw, const float* z, const float* d, const fl
   if (n < 0 || S < 1 || C < 9 + 3 * nc || C > MAXCH || nc < 0 || nc > 3 || !raw || !z || !d) return IBLN_EINVAL;
   if (n == 0) return 0;
   DeviceGuard g(device);
-  int warps = CP_WARPS;
-  size_t per_warp = (2 * (size_t)S * C + 32) * sizeof(float);
-  while (warps > 1 && warps * per_warp > 220 * 1024) warps >>= 1;
-  size_t smem = warps * per_warp;
-  if (smem > 220 * 1024) return IBLN_EINVAL;
+  const int warps = 8;
+  size_t smem = (size_t)warps * (2 * (size_t)ROW * C + 32) * sizeof(float);
   auto kern = composite_fwd_kernel<SIMPLE>;
   IBLN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int per_sm = (int)((220 * 1024) / (smem + 1024));
+  int per_sm = (int)((200 * 1024) / (smem + 1024));
   if (per_sm < 1) per_sm = 1;
-  if (per_sm > 8) per_sm = 8;
+  if (per_sm > 6) per_sm = 6;
   kern<<<comp_grid(n, device, per_sm, warps), warps * 32, smem, (cudaStream_t)stream>>>(raw, z, d, noise, n, S, C, nc, sigm,
                                                                                    weights, maps, maps_srgb, pre);
   IBLN_RETURN_LAST();
@@ -395,15 +431,15 @@ extern "C" int ibln_composite_bwd(const float* raw, const float* z, const float*
   if (n == 0) return 0;
   DeviceGuard g(device);
   int Sp = (S + 31) & ~31;
-  int warps = CP_WARPS;
-  size_t per_warp = ((size_t)S * C + 3 * Sp + 32) * sizeof(float);
-  while (warps > 1 && warps * per_warp > 220 * 1024) warps >>= 1;
+  int warps = 8;
+  size_t per_warp = (2 * (size_t)ROW * C + 3 * (size_t)Sp + 32) * sizeof(float);
+  while (warps > 1 && warps * per_warp > 200 * 1024) warps >>= 1;
   size_t smem = warps * per_warp;
   if (smem > 220 * 1024) return IBLN_EINVAL;
   IBLN_CUDA(cudaFuncSetAttribute(composite_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int per_sm = (int)((220 * 1024) / (smem + 1024));
+  int per_sm = (int)((200 * 1024) / (smem + 1024));
   if (per_sm < 1) per_sm = 1;
-  if (per_sm > 8) per_sm = 8;
+  if (per_sm > 6) per_sm = 6;
   composite_bwd_kernel<<<comp_grid(n, device, per_sm, warps), warps * 32, smem, (cudaStream_t)stream>>>(
       raw, z, rays_d, noise, g_weights, g_maps, g_maps_srgb, n, S, C, nc, sigm, g_raw);
   IBLN_RETURN_LAST();
