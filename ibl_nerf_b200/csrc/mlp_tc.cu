@@ -31,9 +31,19 @@ struct FwdParams {
 __device__ __forceinline__ int n_chunks_of(const Step& st) { return (st.aux_first + st.kb_act + st.aux_last) * (st.n / 128); }
 
 // per-thread epilogue state
-struct Heads {
-  float sigma, rough, irr, alb[3], rad[4][3];
+struct Heads {     // fp32x2 accumulators (even / odd columns); summed at the end
+  float2 sigma, rough, irr, alb[3], rad[4][3];
 };
+// acc += sum over the chunk's 32 columns of h[col] * row[col], as 16 packed FMAs
+__device__ __forceinline__ void dot32(float2& acc, const float (&h)[32], const float* row) {
+  const float4* w = reinterpret_cast<const float4*>(row);
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) {
+    const float4 ww = w[j4];
+    acc = ffma2(make_float2(h[4 * j4], h[4 * j4 + 1]), make_float2(ww.x, ww.y), acc);
+    acc = ffma2(make_float2(h[4 * j4 + 2], h[4 * j4 + 3]), make_float2(ww.z, ww.w), acc);
+  }
+}
 struct EpiCtx {
   uint8_t* act;            // activation tile of the slot (A operand of the next step)
   const float* bias_s;     // smem: bias row of the current step
@@ -88,38 +98,33 @@ __device__ __forceinline__ void process_chunk(const EpiCtx& c, Heads& hd, const 
       else *reinterpret_cast<uint4*>(c.rec + (size_t)(sv_blk + kb) * KB_BYTES + o) = pk;   // STASH only (AF / ADD): no smem copy exists
     }
   }
+  const float* T = c.heads_s;     // this step's head rows (staged in the idle encoding tile)
   if (KIND == K_L7_SIGMA) {
-    const float4* w = reinterpret_cast<const float4*>(c.heads_s) + cc * 8;
-#pragma unroll
-    for (int j4 = 0; j4 < 8; ++j4) {
-      const float4 ww = w[j4];
-      hd.sigma = fmaf(h[4 * j4], ww.x, hd.sigma); hd.sigma = fmaf(h[4 * j4 + 1], ww.y, hd.sigma);
-      hd.sigma = fmaf(h[4 * j4 + 2], ww.z, hd.sigma); hd.sigma = fmaf(h[4 * j4 + 3], ww.w, hd.sigma);
-    }
+    dot32(hd.sigma, h, T + cc * 32);
   } else if (KIND == K_L7_FULL) {
-    const float2* w = reinterpret_cast<const float2*>(c.heads_s) + cc * 32;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) { const float2 ww = w[j]; hd.sigma = fmaf(h[j], ww.x, hd.sigma); hd.rough = fmaf(h[j], ww.y, hd.rough); }
+    dot32(hd.sigma, h, T + cc * 32);
+    dot32(hd.rough, h, T + 256 + cc * 32);
   } else if (KIND == K_AF) {
-    const float4* w = reinterpret_cast<const float4*>(c.heads_s) + cc * 32;
     if (cc < 4) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) { const float4 ww = w[j]; hd.alb[0] = fmaf(h[j], ww.x, hd.alb[0]); hd.alb[1] = fmaf(h[j], ww.y, hd.alb[1]); hd.alb[2] = fmaf(h[j], ww.z, hd.alb[2]); }
+      for (int q = 0; q < 3; ++q) dot32(hd.alb[q], h, T + q * 128 + cc * 32);
     } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) { const float4 ww = w[j]; hd.irr = fmaf(h[j], ww.x, hd.irr); }
+      dot32(hd.irr, h, T + 384 + (cc - 4) * 32);
     }
   } else if (KIND == K_VIEW) {
-    const float4* w = reinterpret_cast<const float4*>(c.heads_s) + cc * 32;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) { const float4 ww = w[j]; hd.rad[0][0] = fmaf(h[j], ww.x, hd.rad[0][0]); hd.rad[0][1] = fmaf(h[j], ww.y, hd.rad[0][1]); hd.rad[0][2] = fmaf(h[j], ww.z, hd.rad[0][2]); }
-  } else if (KIND == K_ADD01 || KIND == K_ADD2) {
-    const int head = (KIND == K_ADD2) ? 2 : (cc >> 2);
-    const float4* w = reinterpret_cast<const float4*>(c.heads_s) + cc * 32;     // table holds exactly this step's heads
-    float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+    for (int q = 0; q < 3; ++q) dot32(hd.rad[0][q], h, T + q * 256 + cc * 32);
+  } else if (KIND == K_ADD01) {
+    if (cc < 4) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) { const float4 ww = w[j]; r0 = fmaf(h[j], ww.x, r0); r1 = fmaf(h[j], ww.y, r1); r2 = fmaf(h[j], ww.z, r2); }
-    hd.rad[1 + head][0] += r0; hd.rad[1 + head][1] += r1; hd.rad[1 + head][2] += r2;
+      for (int q = 0; q < 3; ++q) dot32(hd.rad[1][q], h, T + q * 128 + cc * 32);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 3; ++q) dot32(hd.rad[2][q], h, T + 384 + q * 128 + (cc - 4) * 32);
+    }
+  } else if (KIND == K_ADD2) {
+#pragma unroll
+    for (int q = 0; q < 3; ++q) dot32(hd.rad[3][q], h, T + q * 128 + cc * 32);
   }
 }
 
@@ -265,8 +270,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_fwd_kernel(FwdParams prm) {
     // small-head weight table of a head step -> the slot's encoding tile, which is idle during every head epilogue
     // (positional encoding is dead after L5, the view encoding after the view GEMM)
     auto load_heads = [&](int s) {
-      const int off = SIGMA_ONLY ? C_SIG : (s == 7 ? C_SR : s == 8 ? C_AF : s == 10 ? C_RAD : s == 11 ? C_ADD : C_ADD + 1024);
-      const int n4 = SIGMA_ONLY ? 64 : (s == 7 ? 128 : s == 12 ? 128 : 256);
+      const int off = s == 7 ? C_SR : s == 8 ? C_AF : s == 10 ? C_RAD : s == 11 ? C_ADD : C_ADD + 768;
+      const int n4 = SIGMA_ONLY ? 64 : (s == 7 ? 128 : s == 8 ? 128 : s == 12 ? 96 : 192);
       const float4* src = reinterpret_cast<const float4*>(c.cst + off);
       float4* dst = reinterpret_cast<float4*>(aux);
       for (int i = gtid; i < n4; i += 128) dst[i] = __ldg(src + i);
@@ -299,13 +304,14 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_fwd_kernel(FwdParams prm) {
       publish();
 
       Heads hd;
-      hd.sigma = hd.rough = hd.irr = 0.f;
+      const float2 zero2 = make_float2(0.f, 0.f);
+      hd.sigma = hd.rough = hd.irr = zero2;
 #pragma unroll
-      for (int a = 0; a < 3; ++a) hd.alb[a] = 0.f;
+      for (int a = 0; a < 3; ++a) hd.alb[a] = zero2;
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int q = 0; q < 3; ++q) hd.rad[a][q] = 0.f;
+        for (int q = 0; q < 3; ++q) hd.rad[a][q] = zero2;
 
 #pragma unroll 1
       for (int s = 0; s < n_steps; ++s) {
@@ -345,21 +351,23 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_fwd_kernel(FwdParams prm) {
       }
       // ---- outputs
       if (valid) {
-        hd.sigma += __ldg(c.cst + C_SR + 512);
+        auto sum2 = [](float2 v) { return v.x + v.y; };
+        const float sigma = sum2(hd.sigma) + __ldg(c.cst + C_SR + 512);
         if (SIGMA_ONLY) {
-          prm.out[p] = hd.sigma;
+          prm.out[p] = sigma;
         } else {
           float r[18];
-          r[0] = hd.sigma;
-          r[1] = hd.alb[0] + __ldg(c.cst + C_AF + 1024); r[2] = hd.alb[1] + __ldg(c.cst + C_AF + 1025); r[3] = hd.alb[2] + __ldg(c.cst + C_AF + 1026);
-          r[4] = hd.rough + __ldg(c.cst + C_SR + 513);
-          r[5] = hd.irr + __ldg(c.cst + C_AF + 1027);
+          r[0] = sigma;
 #pragma unroll
-          for (int q = 0; q < 3; ++q) r[6 + q] = hd.rad[0][q] + __ldg(c.cst + C_RAD + 1024 + q);
+          for (int q = 0; q < 3; ++q) r[1 + q] = sum2(hd.alb[q]) + __ldg(c.cst + C_AF + 512 + q);
+          r[4] = sum2(hd.rough) + __ldg(c.cst + C_SR + 513);
+          r[5] = sum2(hd.irr) + __ldg(c.cst + C_AF + 515);
+#pragma unroll
+          for (int q = 0; q < 3; ++q) r[6 + q] = sum2(hd.rad[0][q]) + __ldg(c.cst + C_RAD + 768 + q);
 #pragma unroll
           for (int a = 0; a < 3; ++a)
 #pragma unroll
-            for (int q = 0; q < 3; ++q) r[9 + 3 * a + q] = hd.rad[1 + a][q] + __ldg(c.cst + C_ADD + 1536 + 4 * a + q);
+            for (int q = 0; q < 3; ++q) r[9 + 3 * a + q] = sum2(hd.rad[1 + a][q]) + __ldg(c.cst + C_ADD + 1152 + 4 * a + q);
           float2* dst = reinterpret_cast<float2*>(prm.out + p * 18);
 #pragma unroll
           for (int j = 0; j < 9; ++j) dst[j] = make_float2(r[2 * j], r[2 * j + 1]);

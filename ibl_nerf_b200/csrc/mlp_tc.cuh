@@ -55,12 +55,14 @@ constexpr int N_CHUNKS = 98;
 
 // fp32 constant section that follows the chunk stream (offsets in floats)
 constexpr int C_BIAS = 0;                    // [13][256]
-constexpr int C_SR = C_BIAS + 13 * 256;      // float2[256] {w_sigma, w_rough}, then {b_sigma, b_rough, 0, 0}
-constexpr int C_AF = C_SR + 512 + 4;         // float4[256] albedo(3)|irradiance(1) weights, then 4 biases
-constexpr int C_RAD = C_AF + 1024 + 4;       // float4[256] radiance weights, then 3 biases + pad
-constexpr int C_ADD = C_RAD + 1024 + 4;      // float4[384] coarse radiance weights, then 3x(3 biases + pad)
-constexpr int C_SIG = C_ADD + 1536 + 12;     // float[256] sigma weights alone (sigma-only path, float4 loads)
-constexpr int C_TOTAL = C_SIG + 256;
+// small-head weights, channel-major exactly like the nn.Linear weights (rows of `in` floats), so the epilogues
+// can run packed fp32x2 FMAs over column pairs:
+constexpr int C_SR = C_BIAS + 13 * 256;      // sigma row [256], roughness row [256], then {b_sigma, b_rough, 0, 0}
+constexpr int C_AF = C_SR + 512 + 4;         // albedo [3][128], irradiance [128], then {b_alb0..2, b_irr}
+constexpr int C_RAD = C_AF + 512 + 4;        // radiance [3][256], then {b0, b1, b2, 0}
+constexpr int C_ADD = C_RAD + 768 + 4;       // coarse radiance k: [3][128] each (k = 0..2), then 3 x {b0, b1, b2, 0}
+constexpr int C_TOTAL = C_ADD + 1152 + 12;
+static_assert(C_SR % 4 == 0 && C_AF % 4 == 0 && C_RAD % 4 == 0 && C_ADD % 4 == 0 && C_TOTAL % 4 == 0, "float4 alignment");
 constexpr int N_CHUNKS_BWD = 92;             // transposed weight chunks of the dgrad chain (mlp_tc_bwd.cu)
 constexpr int64_t PACKED_CONST_OFF = (int64_t)N_CHUNKS * KB_BYTES;
 constexpr int64_t PACKED_BWD_OFF = PACKED_CONST_OFF + (int64_t)C_TOTAL * 4;
@@ -150,29 +152,23 @@ static __global__ void pack_consts_kernel(PackArgs a, float* __restrict__ cst) {
     else v = col < 128 ? a.p[39][col] : 0.f;
   } else if (i < C_AF) {
     int j = i - C_SR;
-    if (j < 512) v = (j & 1) ? a.p[26][j >> 1] : a.p[20][j >> 1];
+    if (j < 256) v = a.p[20][j];
+    else if (j < 512) v = a.p[26][j - 256];
     else if (j == 512) v = a.p[21][0];
     else if (j == 513) v = a.p[27][0];
   } else if (i < C_RAD) {
     int j = i - C_AF;
-    if (j < 1024) {
-      int col = j >> 2, q = j & 3;
-      if (col < 128) v = q < 3 ? a.p[24][q * 128 + col] : 0.f;
-      else v = q == 0 ? a.p[30][col - 128] : 0.f;
-    } else {
-      int q = j - 1024;
-      v = q < 3 ? a.p[25][q] : a.p[31][0];
-    }
+    if (j < 384) v = a.p[24][j];
+    else if (j < 512) v = a.p[30][j - 384];
+    else v = (j - 512) < 3 ? a.p[25][j - 512] : a.p[31][0];
   } else if (i < C_ADD) {
     int j = i - C_RAD;
-    if (j < 1024) { int col = j >> 2, q = j & 3; v = q < 3 ? a.p[32][q * 256 + col] : 0.f; }
-    else { int q = j - 1024; v = q < 3 ? a.p[33][q] : 0.f; }
-  } else if (i >= C_SIG) {
-    v = a.p[20][i - C_SIG];
+    if (j < 768) v = a.p[32][j];
+    else v = (j - 768) < 3 ? a.p[33][j - 768] : 0.f;
   } else {
     int j = i - C_ADD;
-    if (j < 1536) { int col = j >> 2, q = j & 3; int k = col / 128, cc = col % 128; v = q < 3 ? a.p[40 + 2 * k][q * 128 + cc] : 0.f; }
-    else { int q = j - 1536; int k = q / 4, c = q % 4; v = c < 3 ? a.p[41 + 2 * k][c] : 0.f; }
+    if (j < 1152) v = a.p[40 + 2 * (j / 384)][j % 384];
+    else { int q = j - 1152; v = (q % 4) < 3 ? a.p[41 + 2 * (q / 4)][q % 4] : 0.f; }
   }
   cst[i] = v;
 }

@@ -99,6 +99,19 @@ struct DgradParams {
   long long n_tiles;
 };
 
+// v[0..31] += a * row[0..31] as 16 packed fp32x2 FMAs
+__device__ __forceinline__ void axpy32(float (&v)[32], float a, const float* row) {
+  const float4* w = reinterpret_cast<const float4*>(row);
+  const float2 aa = make_float2(a, a);
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) {
+    const float4 ww = w[j4];
+    const float2 r0 = ffma2(aa, make_float2(ww.x, ww.y), make_float2(v[4 * j4], v[4 * j4 + 1]));
+    const float2 r1 = ffma2(aa, make_float2(ww.z, ww.w), make_float2(v[4 * j4 + 2], v[4 * j4 + 3]));
+    v[4 * j4] = r0.x; v[4 * j4 + 1] = r0.y; v[4 * j4 + 2] = r1.x; v[4 * j4 + 3] = r1.y;
+  }
+}
+
 __device__ __forceinline__ void store_tile4(uint8_t* tile, int kb, uint32_t swz, uint4 pk) {
   *reinterpret_cast<uint4*>(tile + (size_t)kb * KB_BYTES + swz) = pk;
 }
@@ -188,15 +201,15 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_dgrad_kernel(DgradParams prm
     const FlatOff fo = flat_offsets();
     uint32_t acc_phase = 0;
     // small-head weight tables -> the slot's (otherwise unused) encoding tile, once per kernel:
-    // [coarse radiance 0..2: 384 float4][albedo|irradiance: 256 float4][radiance: 256 float4][sigma,rough: 128 float4]
+    // channel-major rows: [coarse radiance k: 3x128 each, 1152][albedo 3x128 | irradiance 128: 512][radiance 3x256: 768][sigma, rough: 512]
     const float* tab = reinterpret_cast<const float*>(smem + SMEM_AUX + slot * AUX_BYTES);
-    const float* T_ADD = tab; const float* T_AF = tab + 1536; const float* T_RAD = tab + 2560; const float* T_SR = tab + 3584;
+    const float* T_ADD = tab; const float* T_AF = tab + 1152; const float* T_RAD = tab + 1664; const float* T_SR = tab + 2432;
     const int gtid = threadIdx.x - 64 - slot * 128;
     {
       float4* dst = reinterpret_cast<float4*>(smem + SMEM_AUX + slot * AUX_BYTES);
-      for (int i = gtid; i < 1024; i += 128) {
-        const float* src = i < 384 ? cst + C_ADD + 4 * i : i < 640 ? cst + C_AF + 4 * (i - 384)
-                         : i < 896 ? cst + C_RAD + 4 * (i - 640) : cst + C_SR + 4 * (i - 896);
+      for (int i = gtid; i < 736; i += 128) {
+        const float* src = i < 288 ? cst + C_ADD + 4 * i : i < 416 ? cst + C_AF + 4 * (i - 288)
+                         : i < 608 ? cst + C_RAD + 4 * (i - 416) : cst + C_SR + 4 * (i - 608);
         dst[i] = __ldg(reinterpret_cast<const float4*>(src));
       }
       named_bar_sync(1 + slot, 128);
@@ -258,21 +271,19 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_dgrad_kernel(DgradParams prm
         const uint32_t mw[8] = {mw0.x, mw0.y, mw0.z, mw0.w, mw1.x, mw1.y, mw1.z, mw1.w};
         for (int cc = 0; cc < ncc; ++cc) {
           float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
           if (which == 2) {
-            const float4* w = reinterpret_cast<const float4*>(T_AF) + cc * 32;
             if (cc < 4) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) { float4 ww = w[j]; v[j] = g[1] * ww.x + g[2] * ww.y + g[3] * ww.z; }
+              for (int q = 0; q < 3; ++q) axpy32(v, g[1 + q], T_AF + q * 128 + cc * 32);
             } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) { float4 ww = w[j]; v[j] = g[5] * ww.x; }
+              axpy32(v, g[5], T_AF + 384 + (cc - 4) * 32);
             }
           } else {
             const int head = which == 1 ? 2 : (cc >> 2);
-            const float4* w = reinterpret_cast<const float4*>(T_ADD) + head * 128 + (cc & 3) * 32;
-            const float g0 = g[9 + 3 * head], g1 = g[10 + 3 * head], g2 = g[11 + 3 * head];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) { float4 ww = w[j]; v[j] = g0 * ww.x + g1 * ww.y + g2 * ww.z; }
+            for (int q = 0; q < 3; ++q) axpy32(v, g[9 + 3 * head + q], T_ADD + head * 384 + q * 128 + (cc & 3) * 32);
           }
           const uint32_t m = mw[cc];
 #pragma unroll
@@ -329,13 +340,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_dgrad_kernel(DgradParams prm
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
           if (t == 1) {
-            const float4* w = reinterpret_cast<const float4*>(T_RAD) + cc * 32;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) { float4 ww = w[j]; v[j] += g[6] * ww.x + g[7] * ww.y + g[8] * ww.z; }
+            for (int q = 0; q < 3; ++q) axpy32(v, g[6 + q], T_RAD + q * 256 + cc * 32);
           } else if (t == 4) {
-            const float2* w = reinterpret_cast<const float2*>(T_SR) + cc * 32;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) { float2 ww = w[j]; v[j] += g[0] * ww.x + g[4] * ww.y; }
+            axpy32(v, g[0], T_SR + cc * 32);
+            axpy32(v, g[4], T_SR + 256 + cc * 32);
           }
           const uint32_t m = mw[cc];
 #pragma unroll
