@@ -36,6 +36,7 @@ _SIGS = {
     "ibln_mlp_bwd": [c_p, c_p, c_p, c_i64, c_p, c_p],
     "ibln_umma_selftest": [c_p, c_p, c_p, c_int, c_int, c_int],
     "ibln_umma_mn_selftest": [c_p, c_p, c_p, c_int],
+    "ibln_store_probe": [c_p, c_i64, c_int, c_int],
 }
 _PLAIN = {  # no device/stream tail
     "ibln_abi_version": ([], c_int),

@@ -20,6 +20,7 @@ namespace ibln {
 namespace mlp {
 
 // ---------------------------------------------------------------- the fused forward kernel
+__device__ int g_dbg = 0;   // diagnostics: bit0 skip tile copies, bit1 skip AF/ADD direct stores, bit2 skip mask stores
 struct FwdParams {
   const uint8_t* packed;     // chunk stream + const section
   PointGen gen;
@@ -95,7 +96,7 @@ __device__ __forceinline__ void process_chunk(const EpiCtx& c, Heads& hd, const 
                         pack_bf16x2(h[8 * q + 4], h[8 * q + 5]), pack_bf16x2(h[8 * q + 6], h[8 * q + 7]));
       const uint32_t o = c.off[(cc & 1) * 4 + q];
       if (kWriteAct) *reinterpret_cast<uint4*>(c.act + kb * KB_BYTES + o) = pk;
-      else *reinterpret_cast<uint4*>(c.rec + (size_t)(sv_blk + kb) * KB_BYTES + o) = pk;   // STASH only (AF / ADD): no smem copy exists
+      else if (!(g_dbg & 2)) *reinterpret_cast<uint4*>(c.rec + (size_t)(sv_blk + kb) * KB_BYTES + o) = pk;   // STASH only (AF / ADD): no smem copy exists
     }
   }
   const float* T = c.heads_s;     // this step's head rows (staged in the idle encoding tile)
@@ -145,7 +146,7 @@ __device__ __forceinline__ void drain(const EpiCtx& c, Heads& hd, int sv_blk, in
     if (cc + 2 < NCHUNK) tmem_ld32(c.t_lane + (cc + 2) * 32, va);
     process_chunk<KIND, STASH>(c, hd, vb, cc + 1, sv_blk, mw[cc + 1]);
   }
-  if (STASH && KIND != K_FEATURE) {      // one full 32-byte sector per row: [mask slot][row][8 words]
+  if (STASH && KIND != K_FEATURE && !(g_dbg & 4)) {      // one full 32-byte sector per row: [mask slot][row][8 words]
     uint4* dst = reinterpret_cast<uint4*>(c.rec + (size_t)SV_MASK * KB_BYTES + sv_mask * 4096 + c.row * 32);
     dst[0] = make_uint4(mw[0], mw[1], mw[2], mw[3]);
     dst[1] = make_uint4(mw[4], mw[5], mw[6], mw[7]);
@@ -206,6 +207,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_fwd_kernel(FwdParams prm) {
     // ===================== MMA issuer =====================
     if (elect_one()) {
       constexpr uint32_t IDESC = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t IDESC256 = make_idesc_bf16(128, 256, 0, 0);
+      static_assert(N_STAGES == 4, "stage pairing assumes a 4-deep ring and even chunk counts per step");
       int stage = 0;
       uint32_t phase = 0;
       uint32_t act_phase[2] = {0, 0};
@@ -227,16 +230,32 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_fwd_kernel(FwdParams prm) {
               const bool from_aux = (st.aux_first && kbi == 0) || (st.aux_last && kbi == nkb - 1);
               const uint32_t a_addr = from_aux ? aux_addr : act_addr + (kbi - st.aux_first) * KB_BYTES;
               const int ksteps = (st.aux_last && kbi == nkb - 1) ? 2 : 4;
-              for (int nh = 0; nh < nh_count; ++nh) {
+              if (!SIGMA_ONLY && nh_count == 2) {
+                // (full path; the sigma-only path keeps per-stage N=128 MMAs, whose finer pipelining measures faster)
+                // both 128-row halves of this K-block sit in adjacent ring stages (stage is even here): one N=256
+                // MMA per K-step reads the A tile once instead of twice (shared-memory operand bandwidth)
                 mbar_wait(&w_full[stage], phase);
+                mbar_wait(&w_full[stage + 1], phase);
                 tc_fence_after();
                 const uint32_t b_addr = smem_u32(smem + SMEM_RING + stage * KB_BYTES);
-                for (int ks = 0; ks < ksteps; ++ks) {
-                  umma_bf16(d_tmem + nh * 128, make_desc_kmajor_sw128(a_addr + ks * 32), make_desc_kmajor_sw128(b_addr + ks * 32),
-                            IDESC, (kbi > 0 || ks > 0) ? 1u : 0u);
-                }
+                for (int ks = 0; ks < ksteps; ++ks)
+                  umma_bf16(d_tmem, make_desc_kmajor_sw128(a_addr + ks * 32), make_desc_kmajor_sw128(b_addr + ks * 32),
+                            IDESC256, (kbi > 0 || ks > 0) ? 1u : 0u);
                 umma_commit(&w_empty[stage]);
-                if (++stage == N_STAGES) { stage = 0; phase ^= 1; }
+                umma_commit(&w_empty[stage + 1]);
+                stage += 2;
+                if (stage == N_STAGES) { stage = 0; phase ^= 1; }
+              } else {
+                for (int nh = 0; nh < nh_count; ++nh) {
+                  mbar_wait(&w_full[stage], phase);
+                  tc_fence_after();
+                  const uint32_t b_addr = smem_u32(smem + SMEM_RING + stage * KB_BYTES);
+                  for (int ks = 0; ks < ksteps; ++ks)
+                    umma_bf16(d_tmem + nh * 128, make_desc_kmajor_sw128(a_addr + ks * 32), make_desc_kmajor_sw128(b_addr + ks * 32),
+                              IDESC, (kbi > 0 || ks > 0) ? 1u : 0u);
+                  umma_commit(&w_empty[stage]);
+                  if (++stage == N_STAGES) { stage = 0; phase ^= 1; }
+                }
               }
             }
             umma_commit(&acc_ready[slot]);
@@ -282,10 +301,15 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_fwd_kernel(FwdParams prm) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&act_ready[slot]);
     };
-    // STASH: a finished shared-memory tile goes to the stash record as ONE bulk (TMA) store issued by one thread
-    // after the group barrier; the tile may only be overwritten after cp.async.bulk.wait_group.read
+    // STASH: after the group barrier a finished shared-memory tile is copied verbatim to the stash record by the
+    // group's 128 threads with fully coalesced 16-byte stores (the LSU path: bulk TMA stores of this size would
+    // queue in front of the weight producer's bulk loads on the SM's TMA unit and starve the MMA pipe)
     auto stash_tile = [&](const uint8_t* tile_smem, int blk, int nblk) {
-      if (gtid == 0) { bulk_s2g(c.rec + (size_t)blk * KB_BYTES, tile_smem, (uint32_t)nblk * KB_BYTES); bulk_commit(); }
+      const uint4* src = reinterpret_cast<const uint4*>(tile_smem);
+      uint4* dst = reinterpret_cast<uint4*>(c.rec + (size_t)blk * KB_BYTES);
+      if (g_dbg & 1) return;
+#pragma unroll 8
+      for (int i = gtid; i < nblk * (KB_BYTES / 16); i += 128) dst[i] = src[i];
     };
     for (long long k = slot; k < my_tiles; k += 2) {
       const long long tile = blockIdx.x + k * gridDim.x;
@@ -296,12 +320,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_fwd_kernel(FwdParams prm) {
       if (STASH) c.rec = prm.saved + (size_t)tile * SV_BYTES;
       load_bias(0);
       write_encoding<10, 8>(aux, row, x);
-      if (STASH) {
-        fence_proxy_async();
-        named_bar_sync(1 + slot, 128);
-        stash_tile(aux, SV_PE, 1);
-      }
+      if (STASH) named_bar_sync(1 + slot, 128);
       publish();
+      if (STASH) stash_tile(aux, SV_PE, 1);      // off the critical path: overlaps the layer-0 GEMM
 
       Heads hd;
       const float2 zero2 = make_float2(0.f, 0.f);
@@ -318,8 +339,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_fwd_kernel(FwdParams prm) {
         mbar_wait(&acc_ready[slot], acc_phase);
         acc_phase ^= 1;
         tc_fence_after();
-        if (STASH && gtid == 0) bulk_wait_read0();    // earlier bulk stores have finished reading act / aux
-        if (!SIGMA_ONLY && s == 10) { if (STASH) named_bar_sync(1 + slot, 128); load_heads(10); }   // view encoding consumed: reuse its tile
+        if (!SIGMA_ONLY && s == 10) { if (STASH) named_bar_sync(1 + slot, 128); load_heads(10); }   // view encoding consumed (and stashed): reuse its tile
         named_bar_sync(1 + slot, 128);       // bias row (+ head table) of this step are in smem
         switch (s) {
           case 7:
@@ -337,16 +357,15 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_fwd_kernel(FwdParams prm) {
           default: drain<K_RELU_ACT, STASH, 8>(c, hd, SV_H(s), s); break;
         }
         if (s + 1 < n_steps) {
-          if (STASH) fence_proxy_async();    // this step's tile writes -> visible to the bulk-store (async) proxy
-          named_bar_sync(1 + slot, 128);     // everyone is done reading this step's bias row / head table
-          if (STASH) {
+          named_bar_sync(1 + slot, 128);     // everyone is done reading this step's bias row / head table; tile complete
+          load_bias(s + 1);
+          if (s + 1 == 7 || (!SIGMA_ONLY && (s + 1 == 8 || s + 1 == 11 || s + 1 == 12))) load_heads(s + 1);
+          publish();
+          if (STASH) {   // copy the finished tile out while the next GEMM reads it (both only read)
             if (s <= 7) stash_tile(c.act, SV_H(s), 4);
             else if (s == 9) { stash_tile(c.act, SV_FEAT, 4); stash_tile(aux, SV_DE, 1); }
             else if (s == 10) stash_tile(c.act, SV_HV, 4);
           }
-          load_bias(s + 1);
-          if (s + 1 == 7 || (!SIGMA_ONLY && (s + 1 == 8 || s + 1 == 11 || s + 1 == 12))) load_heads(s + 1);
-          publish();
         }
       }
       // ---- outputs
@@ -373,11 +392,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_fwd_kernel(FwdParams prm) {
           for (int j = 0; j < 9; ++j) dst[j] = make_float2(r[2 * j], r[2 * j + 1]);
         }
       }
-      if (STASH && gtid == 0) bulk_wait_read0();
       named_bar_sync(1 + slot, 128);         // last step's bias row no longer needed (next tile overwrites it)
       tc_fence_before();   // order this tile's TMEM reads before the next tile's act_ready arrival
     }
-    if (STASH && gtid == 0) bulk_wait0();    // all stash writes complete before the CTA exits
   }
   tc_fence_before();
   __syncthreads();
@@ -453,6 +470,8 @@ umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, f
 
 using namespace ibln;
 using namespace ibln::mlp;
+
+extern "C" int ibln_debug_set(int flags) { return (int)cudaMemcpyToSymbol(ibln::mlp::g_dbg, &flags, sizeof(int)); }
 
 extern "C" int64_t ibln_mlp_packed_bytes(void) { return PACKED_BYTES; }
 

@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_dgrad_kernel(DgradParams prm
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      constexpr uint32_t IDESC = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t IDESC256 = make_idesc_bf16(128, 256, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       uint32_t act_phase[2] = {0, 0};
@@ -176,17 +176,20 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_dgrad_kernel(DgradParams prm
             tc_fence_after();
             const uint32_t act_addr = smem_u32(smem + SMEM_ACT + slot * ACT_BYTES);
             const uint32_t d_tmem = tmem_base + slot * 256;
-            for (int kbi = 0; kbi < st.nkb; ++kbi)
-              for (int nh = 0; nh < 2; ++nh) {
-                mbar_wait(&w_full[stage], phase);
-                tc_fence_after();
-                const uint32_t b_addr = smem_u32(smem + SMEM_RING + stage * KB_BYTES);
-                for (int ks = 0; ks < 4; ++ks)
-                  umma_bf16(d_tmem + nh * 128, make_desc_kmajor_sw128(act_addr + kbi * KB_BYTES + ks * 32),
-                            make_desc_kmajor_sw128(b_addr + ks * 32), IDESC, (st.accumulate || kbi > 0 || ks > 0) ? 1u : 0u);
-                umma_commit(&w_empty[stage]);
-                if (++stage == N_STAGES) { stage = 0; phase ^= 1; }
-              }
+            for (int kbi = 0; kbi < st.nkb; ++kbi) {
+              // the two 128-row halves of a K-block are in adjacent ring stages: one N=256 MMA per K-step
+              mbar_wait(&w_full[stage], phase);
+              mbar_wait(&w_full[stage + 1], phase);
+              tc_fence_after();
+              const uint32_t b_addr = smem_u32(smem + SMEM_RING + stage * KB_BYTES);
+              for (int ks = 0; ks < 4; ++ks)
+                umma_bf16(d_tmem, make_desc_kmajor_sw128(act_addr + kbi * KB_BYTES + ks * 32),
+                          make_desc_kmajor_sw128(b_addr + ks * 32), IDESC256, (st.accumulate || kbi > 0 || ks > 0) ? 1u : 0u);
+              umma_commit(&w_empty[stage]);
+              umma_commit(&w_empty[stage + 1]);
+              stage += 2;
+              if (stage == N_STAGES) { stage = 0; phase ^= 1; }
+            }
             umma_commit(&acc_ready[slot]);
           }
         }
@@ -295,22 +298,23 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_dgrad_kernel(DgradParams prm
                                    pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7])));
         }
       };
-      // finished gradient tile in `act`: one bulk (TMA) store to the dY record, then hand it to the MMA issuer
+      // finished gradient tile in `act`: verbatim coalesced copy to the dY record (LSU path, see mlp_tc.cu), then
+      // hand it to the MMA issuer
       auto publish = [&](int dblk, int nblk, bool arrive) {
         fence_proxy_async();
         named_bar_sync(1 + slot, 128);
-        if (gtid == 0) { bulk_s2g(dy + (size_t)dblk * KB_BYTES, act, (uint32_t)nblk * KB_BYTES); bulk_commit(); }
         if (arrive) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&act_ready[slot]);
         }
+        const uint4* src = reinterpret_cast<const uint4*>(act);      // overlaps the GEMM that reads the same tile
+        uint4* dst = reinterpret_cast<uint4*>(dy + (size_t)dblk * KB_BYTES);
+#pragma unroll 8
+        for (int i = gtid; i < nblk * (KB_BYTES / 16); i += 128) dst[i] = src[i];
       };
-      // before overwriting `act`: the previous bulk store must have finished reading it
-      auto pre_write = [&]() {
-        if (gtid == 0) bulk_wait_read0();
-        named_bar_sync(1 + slot, 128);
-      };
+      // before overwriting `act`: every thread of the group has finished copying the previous tile out of it
+      auto pre_write = [&]() { named_bar_sync(1 + slot, 128); };
       pre_write();
       write_head_tile(0);
       publish(DY_ADDF01, 4, true);
@@ -370,7 +374,6 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_dgrad_kernel(DgradParams prm
       }
       tc_fence_before();
     }
-    if (gtid == 0) bulk_wait0();     // all dY stores complete before the CTA exits
   }
   tc_fence_before();
   __syncthreads();

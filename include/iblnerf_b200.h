@@ -200,6 +200,10 @@ int ibln_umma_selftest(const float* a, const float* b, float* d, int n, int k, i
  * Y [128 points,N] (N in {64,128,192,256}) staged as swizzled operand tiles and read as MN-major. */
 int ibln_umma_mn_selftest(const float* x, const float* y, float* d, int n, int device, void* stream);
 
+/* Diagnostics: write `total_bytes` to `out` from `ctas` CTAs (mode 0/1: bulk TMA stores from shared memory,
+ * 1 / 4 in flight; mode 2: coalesced st.global.v4) -- used to measure the achievable stash write bandwidth. */
+int ibln_store_probe(void* out, int64_t total_bytes, int mode, int ctas, int device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
