@@ -96,7 +96,7 @@ __device__ __forceinline__ void process_chunk(const EpiCtx& c, Heads& hd, const 
                         pack_bf16x2(h[8 * q + 4], h[8 * q + 5]), pack_bf16x2(h[8 * q + 6], h[8 * q + 7]));
       const uint32_t o = c.off[(cc & 1) * 4 + q];
       if (kWriteAct) *reinterpret_cast<uint4*>(c.act + kb * KB_BYTES + o) = pk;
-      else if (!(g_dbg & 2)) *reinterpret_cast<uint4*>(c.rec + (size_t)(sv_blk + kb) * KB_BYTES + o) = pk;   // STASH only (AF / ADD): no smem copy exists
+      else if (!(g_dbg & 2)) __stcs(reinterpret_cast<uint4*>(c.rec + (size_t)(sv_blk + kb) * KB_BYTES + o), pk);   // STASH only (AF / ADD): no smem copy exists
     }
   }
   const float* T = c.heads_s;     // this step's head rows (staged in the idle encoding tile)
@@ -148,8 +148,8 @@ __device__ __forceinline__ void drain(const EpiCtx& c, Heads& hd, int sv_blk, in
   }
   if (STASH && KIND != K_FEATURE && !(g_dbg & 4)) {      // one full 32-byte sector per row: [mask slot][row][8 words]
     uint4* dst = reinterpret_cast<uint4*>(c.rec + (size_t)SV_MASK * KB_BYTES + sv_mask * 4096 + c.row * 32);
-    dst[0] = make_uint4(mw[0], mw[1], mw[2], mw[3]);
-    dst[1] = make_uint4(mw[4], mw[5], mw[6], mw[7]);
+    __stcs(dst, make_uint4(mw[0], mw[1], mw[2], mw[3]));
+    __stcs(dst + 1, make_uint4(mw[4], mw[5], mw[6], mw[7]));
   }
 }
 
@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_fwd_kernel(FwdParams prm) {
       uint4* dst = reinterpret_cast<uint4*>(c.rec + (size_t)blk * KB_BYTES);
       if (g_dbg & 1) return;
 #pragma unroll 8
-      for (int i = gtid; i < nblk * (KB_BYTES / 16); i += 128) dst[i] = src[i];
+      for (int i = gtid; i < nblk * (KB_BYTES / 16); i += 128) __stcs(dst + i, src[i]);   // streaming: keep the weight image in L2
     };
     for (long long k = slot; k < my_tiles; k += 2) {
       const long long tile = blockIdx.x + k * gridDim.x;

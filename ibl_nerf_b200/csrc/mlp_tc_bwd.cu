@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_dgrad_kernel(DgradParams prm
         const uint4* src = reinterpret_cast<const uint4*>(act);      // overlaps the GEMM that reads the same tile
         uint4* dst = reinterpret_cast<uint4*>(dy + (size_t)dblk * KB_BYTES);
 #pragma unroll 8
-        for (int i = gtid; i < nblk * (KB_BYTES / 16); i += 128) dst[i] = src[i];
+        for (int i = gtid; i < nblk * (KB_BYTES / 16); i += 128) __stcs(dst + i, src[i]);   // streaming store
       };
       // before overwriting `act`: every thread of the group has finished copying the previous tile out of it
       auto pre_write = [&]() { named_bar_sync(1 + slot, 128); };
