@@ -471,7 +471,8 @@ umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, f
 using namespace ibln;
 using namespace ibln::mlp;
 
-extern "C" int ibln_debug_set(int flags) { return (int)cudaMemcpyToSymbol(ibln::mlp::g_dbg, &flags, sizeof(int)); }
+namespace ibln { namespace mlp { int g_dbg_host = 0; } }
+extern "C" int ibln_debug_set(int flags) { ibln::mlp::g_dbg_host = flags; return (int)cudaMemcpyToSymbol(ibln::mlp::g_dbg, &flags, sizeof(int)); }
 
 extern "C" int64_t ibln_mlp_packed_bytes(void) { return PACKED_BYTES; }
 

@@ -15,6 +15,7 @@
 
 namespace ibln {
 namespace mlp {
+extern int g_dbg_host;   // diagnostics (mlp_tc.cu): bit4 skip dgrad, bit5 skip wgrad
 
 // ---------------------------------------------------------------- dgrad step program
 constexpr int N_STEPS_BWD = 12;
@@ -532,8 +533,9 @@ extern "C" int ibln_mlp_bwd(const void* packed, const void* saved, const float* 
   dp.flat_grad = flat_grad; dp.P = n_pts; dp.n_tiles = n_tiles;
   IBLN_CUDA(cudaFuncSetAttribute(mlp_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_REQUEST));
   long long grid = n_tiles < (long long)num_sms(device) ? n_tiles : (long long)num_sms(device);
-  mlp_dgrad_kernel<<<(unsigned)grid, N_THREADS, SMEM_REQUEST, stream>>>(dp);
+  if (!(g_dbg_host & 16)) mlp_dgrad_kernel<<<(unsigned)grid, N_THREADS, SMEM_REQUEST, stream>>>(dp);
   IBLN_CUDA(cudaGetLastError());
+  if (g_dbg_host & 32) return 0;
   // ---- wgrad jobs
   IBLN_CUDA(cudaFuncSetAttribute(mlp_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_REQUEST));
   const FlatOff fo = flat_offsets();
