@@ -46,8 +46,9 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// sigmoid with fast exp / reciprocal (rel. error ~3e-7, far inside the 1e-4 parity budget)
-__device__ __forceinline__ float sigmoidf_fast(float x) { return __frcp_rn(1.0f + __expf(-x)); }
+// sigmoid with MUFU exp2 / MUFU reciprocal (rel. error ~4e-7, far inside the 1e-4 parity budget).
+// NB: __frcp_rn is the correctly-rounded (multi-instruction) reciprocal; __fdividef maps to one MUFU.RCP + FMUL.
+__device__ __forceinline__ float sigmoidf_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
 // pow(x + 1e-12, 1/2.2): ibl_nerf_renderer.py:26-27
 __device__ __forceinline__ float srgbf(float x) { return powf(x + 1e-12f, 1.0f / 2.2f); }

@@ -40,41 +40,47 @@ __global__ void stratified_z_kernel(const float* __restrict__ nearp, const float
 }
 
 // ---------------------------------------------------------------- inverse CDF
-// searchsorted(cdf, u, right=True): first index with cdf[idx] > u.
-__device__ __forceinline__ int upper_bound(const float* cdf, int n, float u) {
-  int lo = 0, hi = n;
-  while (lo < hi) {
-    int mid = (lo + hi) >> 1;
-    if (cdf[mid] <= u) lo = mid + 1; else hi = mid;
+// searchsorted(cdf, u, right=True) = number of entries <= u, as a branch-free power-of-two descent
+// (p2 = largest power of two <= n): log2(n)+1 predicated steps, no divergence.
+__device__ __forceinline__ int upper_bound(const float* cdf, int n, int p2, float u) {
+  int pos = 0;
+  for (int step = p2; step > 0; step >>= 1) {
+    const int np = pos + step;
+    if (np <= n && cdf[np - 1] <= u) pos = np;
   }
-  return lo;
+  return pos;
 }
 
-__device__ __forceinline__ float invert_one(const float* cdf, const float* bins, int nbins, float u, int* ind_out) {
-  int ind = upper_bound(cdf, nbins, u);
+// EXACT = true : IEEE division, every op un-contracted -> samples bit-identical to the reference given (cdf, u)
+// EXACT = false: one MUFU reciprocal-multiply (<= 2 ulp); used by the fused sample_pdf / hierarchical paths
+template <bool EXACT>
+__device__ __forceinline__ float invert_one(const float* cdf, const float* bins, int nbins, int p2, float u, int* ind_out) {
+  const int ind = upper_bound(cdf, nbins, p2, u);
   *ind_out = ind;
-  int below = max(ind - 1, 0), above = min(ind, nbins - 1);
-  float c0 = cdf[below], c1 = cdf[above], b0 = bins[below], b1 = bins[above];
+  const int below = max(ind - 1, 0), above = min(ind, nbins - 1);
+  const float c0 = cdf[below], c1 = cdf[above], b0 = bins[below], b1 = bins[above];
   float den = __fsub_rn(c1, c0);
   if (den < 1e-5f) den = 1.0f;
-  float t = __fdiv_rn(__fsub_rn(u, c0), den);
+  const float t = EXACT ? __fdiv_rn(__fsub_rn(u, c0), den) : __fdividef(__fsub_rn(u, c0), den);
   return __fadd_rn(b0, __fmul_rn(t, __fsub_rn(b1, b0)));
 }
+
+__host__ __device__ inline int floor_pow2(int v) { int p = 1; while (p * 2 <= v) p <<= 1; return p; }
 
 // Build cdf[0..nbins) in shared memory from nbins-1 weights (warp-cooperative).
 // pdf = (w+1e-5)/sum; cdf = [0, cumsum(pdf)]  (nerf_renderer_helper.py:93-96)
 __device__ __forceinline__ void warp_build_cdf(const float* __restrict__ w, int nw, float* cdf, int lane) {
   float part = 0.f;
   for (int i = lane; i < nw; i += 32) part += w[i] + 1e-5f;
-  float total = warp_sum(part);
+  const float inv_total = __fdividef(1.0f, warp_sum(part));
   float carry = 0.f;
   if (lane == 0) cdf[0] = 0.f;
   for (int base = 0; base < nw; base += 32) {
-    int i = base + lane;
-    float p = (i < nw) ? __fdiv_rn(w[i] + 1e-5f, total) : 0.f;
+    const int i = base + lane;
+    float p = (i < nw) ? (w[i] + 1e-5f) * inv_total : 0.f;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      float v = __shfl_up_sync(FULL, p, o);
+      const float v = __shfl_up_sync(FULL, p, o);
       if (lane >= o) p += v;
     }
     if (i < nw) cdf[i + 1] = carry + p;
@@ -85,16 +91,20 @@ __device__ __forceinline__ void warp_build_cdf(const float* __restrict__ w, int 
 
 constexpr int SP_WARPS = 4;
 
+template <bool EXACT>
 __global__ void __launch_bounds__(SP_WARPS * 32)
 sample_pdf_kernel(const float* __restrict__ bins, int64_t bins_stride, const float* __restrict__ weights,
                   int64_t w_stride, const float* __restrict__ cdf_in, const float* __restrict__ u, int n, int nbins,
                   int nsamp, int64_t* __restrict__ inds_out, float* __restrict__ samples) {
   extern __shared__ float sm[];
-  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* s_bins = sm + (size_t)warp * 2 * nbins;
   float* s_cdf = s_bins + nbins;
+  const int p2 = floor_pow2(nbins);
   for (int r = blockIdx.x * SP_WARPS + warp; r < n; r += gridDim.x * SP_WARPS) {
     const float* brow = bins + (int64_t)r * bins_stride;
+    const float* urow = u + (int64_t)r * nsamp;
+    float* orow = samples + (int64_t)r * nsamp;
     for (int i = lane; i < nbins; i += 32) s_bins[i] = brow[i];
     if (cdf_in != nullptr) {
       for (int i = lane; i < nbins; i += 32) s_cdf[i] = cdf_in[(int64_t)r * nbins + i];
@@ -102,10 +112,23 @@ sample_pdf_kernel(const float* __restrict__ bins, int64_t bins_stride, const flo
     } else {
       warp_build_cdf(weights + (int64_t)r * w_stride, nbins - 1, s_cdf, lane);
     }
-    for (int j = lane; j < nsamp; j += 32) {
+    int j = lane;
+    for (; j + 96 < nsamp; j += 128) {          // 4 independent searches in flight per lane
+      float uu[4], sv[4];
+      int ind[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) uu[q] = urow[j + 32 * q];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) sv[q] = invert_one<EXACT>(s_cdf, s_bins, nbins, p2, uu[q], &ind[q]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        orow[j + 32 * q] = sv[q];
+        if (inds_out != nullptr) inds_out[(int64_t)r * nsamp + j + 32 * q] = ind[q];
+      }
+    }
+    for (; j < nsamp; j += 32) {
       int ind;
-      float sv = invert_one(s_cdf, s_bins, nbins, u[(int64_t)r * nsamp + j], &ind);
-      samples[(int64_t)r * nsamp + j] = sv;
+      orow[j] = invert_one<EXACT>(s_cdf, s_bins, nbins, p2, urow[j], &ind);
       if (inds_out != nullptr) inds_out[(int64_t)r * nsamp + j] = ind;
     }
     __syncwarp();
@@ -166,9 +189,10 @@ hierarchical_kernel(const float* __restrict__ z, const float* __restrict__ weigh
       if (i < nbins) s_bins[i] = __fmul_rn(0.5f, __fadd_rn(zr[i + 1], zi));
     }
     warp_build_cdf(weights + (int64_t)r * s0 + 1, nbins - 1, s_cdf, lane);
+    const int p2 = floor_pow2(nbins);
     for (int j = lane; j < s1; j += 32) {
       int ind;
-      float sv = invert_one(s_cdf, s_bins, nbins, u[(int64_t)r * s1 + j], &ind);
+      float sv = invert_one<false>(s_cdf, s_bins, nbins, p2, u[(int64_t)r * s1 + j], &ind);
       z_samples[(int64_t)r * s1 + j] = sv;
       s_sort[s0 + j] = sv;
     }
@@ -207,9 +231,14 @@ static int launch_sample_pdf(const float* bins, int64_t bs, const float* w, int6
   DeviceGuard g(device);
   size_t smem = (size_t)SP_WARPS * 2 * nbins * sizeof(float);
   if (smem > 200 * 1024) return IBLN_EINVAL;
-  if (smem > 48 * 1024) IBLN_CUDA(cudaFuncSetAttribute(sample_pdf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = ray_grid(n, device, SP_WARPS, 16);
-  sample_pdf_kernel<<<grid, SP_WARPS * 32, smem, (cudaStream_t)stream>>>(bins, bs, w, ws, cdf, u, n, nbins, nsamp, inds, samples);
+  if (cdf != nullptr) {   // explicit-CDF entry: bit-exact arithmetic
+    if (smem > 48 * 1024) IBLN_CUDA(cudaFuncSetAttribute(sample_pdf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sample_pdf_kernel<true><<<grid, SP_WARPS * 32, smem, (cudaStream_t)stream>>>(bins, bs, w, ws, cdf, u, n, nbins, nsamp, inds, samples);
+  } else {
+    if (smem > 48 * 1024) IBLN_CUDA(cudaFuncSetAttribute(sample_pdf_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sample_pdf_kernel<false><<<grid, SP_WARPS * 32, smem, (cudaStream_t)stream>>>(bins, bs, w, ws, cdf, u, n, nbins, nsamp, inds, samples);
+  }
   IBLN_RETURN_LAST();
 }
 
