@@ -396,8 +396,8 @@ using namespace ibln;
 template <bool SIMPLE>
 static int launch_fwd(const float* raw, const float* z, const float* d, const float* noise, int n, int S, int C, int nc,
                       int sigm, float* weights, float* maps, float* maps_srgb, float* pre, int device, void* stream) {
-  if (n < 0 || S < 1 || C < 9 + 3 * nc || C > MAXCH || nc < 0 || nc > 3 || !raw || !z || !d) return IBLN_EINVAL;
   if (n == 0) return 0;
+  if (n < 0 || S < 1 || C < 9 + 3 * nc || C > MAXCH || nc < 0 || nc > 3 || !raw || !z || !d) return IBLN_EINVAL;
   DeviceGuard g(device);
   const int warps = 8;
   size_t smem = (size_t)warps * (2 * (size_t)ROW * C + 32) * sizeof(float);
@@ -414,12 +414,14 @@ static int launch_fwd(const float* raw, const float* z, const float* d, const fl
 extern "C" int ibln_composite_fwd(const float* raw, const float* z, const float* rays_d, const float* noise, int n,
                                   int S, int C, int nc, int sigm, float* weights, float* maps, float* maps_srgb,
                                   int device, void* stream) {
+  if (n == 0) return 0;
   if (!weights || !maps) return IBLN_EINVAL;
   return launch_fwd<false>(raw, z, rays_d, noise, n, S, C, nc, sigm, weights, maps, maps_srgb, nullptr, device, stream);
 }
 
 extern "C" int ibln_composite_simple_fwd(const float* raw, const float* z, const float* dirs, int n, int S, int C, int nc,
                                          int sigm, float* pre_out, int device, void* stream) {
+  if (n == 0) return 0;
   if (!pre_out) return IBLN_EINVAL;
   return launch_fwd<true>(raw, z, dirs, nullptr, n, S, C, nc, sigm, nullptr, nullptr, nullptr, pre_out, device, stream);
 }
@@ -427,8 +429,8 @@ extern "C" int ibln_composite_simple_fwd(const float* raw, const float* z, const
 extern "C" int ibln_composite_bwd(const float* raw, const float* z, const float* rays_d, const float* noise,
                                   const float* g_weights, const float* g_maps, const float* g_maps_srgb, int n, int S,
                                   int C, int nc, int sigm, float* g_raw, int device, void* stream) {
-  if (n < 0 || S < 1 || C < 9 + 3 * nc || C > MAXCH || nc < 0 || nc > 3 || !raw || !z || !rays_d || !g_raw) return IBLN_EINVAL;
   if (n == 0) return 0;
+  if (n < 0 || S < 1 || C < 9 + 3 * nc || C > MAXCH || nc < 0 || nc > 3 || !raw || !z || !rays_d || !g_raw) return IBLN_EINVAL;
   DeviceGuard g(device);
   int Sp = (S + 31) & ~31;
   int warps = 8;
@@ -447,8 +449,8 @@ extern "C" int ibln_composite_bwd(const float* raw, const float* z, const float*
 
 extern "C" int ibln_depth_fwd(const float* sigma, const float* z, const float* rays_d, int reps, int n, int S,
                               float* depth, float* weights, float* visibility, int device, void* stream) {
-  if (reps < 1 || n < 0 || S < 1 || !sigma || !z || !rays_d || !depth) return IBLN_EINVAL;
   if (n == 0) return 0;
+  if (reps < 1 || n < 0 || S < 1 || !sigma || !z || !rays_d || !depth) return IBLN_EINVAL;
   DeviceGuard g(device);
   depth_fwd_kernel<<<comp_grid((int64_t)reps * n, device, 16), CP_WARPS * 32, 0, (cudaStream_t)stream>>>(
       sigma, z, rays_d, reps, n, S, depth, weights, visibility);

@@ -168,8 +168,8 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, const flo
 using namespace ibln;
 
 extern "C" int ibln_encode(const float* x, int64_t n_pts, int n_freqs, float* out, int64_t ld_out, int device, void* stream) {
-  if (n_pts < 0 || n_freqs < 0 || !x || !out || ld_out < 3 + 6 * n_freqs) return IBLN_EINVAL;
   if (n_pts == 0) return 0;
+  if (n_pts < 0 || n_freqs < 0 || !x || !out || ld_out < 3 + 6 * n_freqs) return IBLN_EINVAL;
   DeviceGuard g(device);
   int64_t tot = n_pts * (3 + 6 * n_freqs);
   encode_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, n_pts, 1, n_freqs, out, ld_out);
@@ -178,8 +178,8 @@ extern "C" int ibln_encode(const float* x, int64_t n_pts, int n_freqs, float* ou
 
 extern "C" int ibln_encode_dirs(const float* dirs, int64_t n_rays, int n_samples, int n_freqs, float* out, int64_t ld_out,
                                 int device, void* stream) {
-  if (n_rays < 0 || n_samples < 1 || n_freqs < 0 || !dirs || !out || ld_out < 3 + 6 * n_freqs) return IBLN_EINVAL;
   if (n_rays == 0) return 0;
+  if (n_rays < 0 || n_samples < 1 || n_freqs < 0 || !dirs || !out || ld_out < 3 + 6 * n_freqs) return IBLN_EINVAL;
   DeviceGuard g(device);
   int64_t tot = n_rays * n_samples * (3 + 6 * n_freqs);
   encode_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dirs, n_rays * n_samples, n_samples, n_freqs, out, ld_out);
@@ -189,8 +189,8 @@ extern "C" int ibln_encode_dirs(const float* dirs, int64_t n_rays, int n_samples
 extern "C" int ibln_sgemm(const float* a, int64_t lda, const float* b, int64_t ldb, int trans_b, const float* bias, float* c,
                           int64_t ldc, int64_t m, int n, int k, int act, int accumulate, const float* relu_mask,
                           int64_t ld_mask, int device, void* stream) {
-  if (m < 0 || n < 1 || k < 1 || !a || !b || !c) return IBLN_EINVAL;
   if (m == 0) return 0;
+  if (m < 0 || n < 1 || k < 1 || !a || !b || !c) return IBLN_EINVAL;
   DeviceGuard g(device);
   dim3 grid((unsigned)((m + TM - 1) / TM), (unsigned)((n + TN - 1) / TN));
   sgemm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, lda, b, ldb, trans_b, bias, c, ldc, m, n, k, act, accumulate,

@@ -493,6 +493,7 @@ extern "C" int64_t ibln_mlp_saved_bytes(int64_t n_pts) { return ((n_pts + TILE_M
 extern "C" int ibln_mlp_fwd(const void* packed, int mode, const float* pts, const float* rays_o, const float* rays_d,
                             const float* z, int64_t n_rays, int n_samples, float eps, int sigma_only, float* out,
                             void* saved, int device, void* stream) {
+  if (n_rays == 0) return 0;
   if (!packed || !out || !rays_d || n_rays < 0 || n_samples < 1 || mode < 0 || mode > 2) return IBLN_EINVAL;
   if (mode == 0 && !pts) return IBLN_EINVAL;
   if (mode != 0 && (!rays_o || !z)) return IBLN_EINVAL;
@@ -500,7 +501,6 @@ extern "C" int ibln_mlp_fwd(const void* packed, int mode, const float* pts, cons
   if (saved && sigma_only) return IBLN_EINVAL;
   if (saved && (reinterpret_cast<uintptr_t>(saved) & 15) != 0) return IBLN_EINVAL;
   if ((reinterpret_cast<uintptr_t>(packed) & 15) != 0) return IBLN_EINVAL;
-  if (n_rays == 0) return 0;
   DeviceGuard g(device);
   FwdParams prm;
   prm.packed = (const uint8_t*)packed;

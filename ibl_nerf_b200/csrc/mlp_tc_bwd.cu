@@ -522,8 +522,8 @@ static int launch_wgrad(WgradParams& p, int device, cudaStream_t stream) {
 
 extern "C" int ibln_mlp_bwd(const void* packed, const void* saved, const float* g_out, int64_t n_pts, float* flat_grad,
                             void* workspace, int device, void* stream_) {
-  if (!packed || !saved || !g_out || !flat_grad || !workspace || n_pts < 0) return IBLN_EINVAL;
   if (n_pts == 0) return 0;
+  if (!packed || !saved || !g_out || !flat_grad || !workspace || n_pts < 0) return IBLN_EINVAL;
   DeviceGuard guard(device);
   cudaStream_t stream = (cudaStream_t)stream_;
   const long long n_tiles = (n_pts + TILE_M - 1) / TILE_M;

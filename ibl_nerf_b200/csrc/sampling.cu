@@ -216,8 +216,8 @@ using namespace ibln;
 
 extern "C" int ibln_stratified_z(const float* nearp, const float* farp, const float* t_rand, int n, int s,
                                  int lindisp, float* z_out, int device, void* stream) {
-  if (n < 0 || s < 1 || !nearp || !farp || !z_out) return IBLN_EINVAL;
   if (n == 0) return 0;
+  if (n < 0 || s < 1 || !nearp || !farp || !z_out) return IBLN_EINVAL;
   DeviceGuard g(device);
   int64_t tot = (int64_t)n * s;
   stratified_z_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(nearp, farp, t_rand, n, s, lindisp, z_out);
@@ -226,8 +226,8 @@ extern "C" int ibln_stratified_z(const float* nearp, const float* farp, const fl
 
 static int launch_sample_pdf(const float* bins, int64_t bs, const float* w, int64_t ws, const float* cdf, const float* u,
                              int n, int nbins, int nsamp, int64_t* inds, float* samples, int device, void* stream) {
-  if (n < 0 || nbins < 2 || nsamp < 1 || !bins || !u || !samples) return IBLN_EINVAL;
   if (n == 0) return 0;
+  if (n < 0 || nbins < 2 || nsamp < 1 || !bins || !u || !samples) return IBLN_EINVAL;
   DeviceGuard g(device);
   size_t smem = (size_t)SP_WARPS * 2 * nbins * sizeof(float);
   if (smem > 200 * 1024) return IBLN_EINVAL;
@@ -244,20 +244,22 @@ static int launch_sample_pdf(const float* bins, int64_t bs, const float* w, int6
 
 extern "C" int ibln_sample_pdf(const float* bins, int64_t bins_stride, const float* weights, int64_t w_stride,
                                const float* u, int n, int nbins, int nsamp, float* samples, int device, void* stream) {
+  if (n == 0) return 0;
   if (!weights) return IBLN_EINVAL;
   return launch_sample_pdf(bins, bins_stride, weights, w_stride, nullptr, u, n, nbins, nsamp, nullptr, samples, device, stream);
 }
 
 extern "C" int ibln_inverse_cdf(const float* cdf, const float* bins, const float* u, int n, int nbins, int nsamp,
                                 int64_t* inds_out, float* samples, int device, void* stream) {
+  if (n == 0) return 0;
   if (!cdf) return IBLN_EINVAL;
   return launch_sample_pdf(bins, nbins, nullptr, 0, cdf, u, n, nbins, nsamp, inds_out, samples, device, stream);
 }
 
 extern "C" int ibln_merge_sort_z(const float* za, const float* zb, int n, int sa, int sb, float* z_out, int device,
                                  void* stream) {
-  if (n < 0 || sa < 0 || sb < 0 || sa + sb < 1 || !z_out) return IBLN_EINVAL;
   if (n == 0) return 0;
+  if (n < 0 || sa < 0 || sb < 0 || sa + sb < 1 || !z_out) return IBLN_EINVAL;
   DeviceGuard g(device);
   int npad = next_pow2(sa + sb);
   if (npad < 2) npad = 2;
@@ -270,8 +272,8 @@ extern "C" int ibln_merge_sort_z(const float* za, const float* zb, int n, int sa
 
 extern "C" int ibln_hierarchical_sample(const float* z, const float* weights, const float* u, int n, int s0, int s1,
                                         float* z_samples, float* z_merged, int device, void* stream) {
-  if (n < 0 || s0 < 4 || s1 < 1 || !z || !weights || !u || !z_samples || !z_merged) return IBLN_EINVAL;
   if (n == 0) return 0;
+  if (n < 0 || s0 < 4 || s1 < 1 || !z || !weights || !u || !z_samples || !z_merged) return IBLN_EINVAL;
   DeviceGuard g(device);
   int npad = next_pow2(s0 + s1);
   size_t smem = (size_t)SP_WARPS * (2 * s0 + npad) * sizeof(float);

@@ -253,8 +253,8 @@ using namespace ibln;
 
 extern "C" int ibln_normal_eps_points(const float* rays_o, const float* rays_d, const float* z, int n, int S, float eps,
                                       float* pts_out, int device, void* stream) {
-  if (n < 0 || S < 1 || !rays_o || !rays_d || !z || !pts_out) return IBLN_EINVAL;
   if (n == 0) return 0;
+  if (n < 0 || S < 1 || !rays_o || !rays_d || !z || !pts_out) return IBLN_EINVAL;
   DeviceGuard g(device);
   int64_t tot = (int64_t)n * S;
   normal_eps_points_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, z, n, S, eps, pts_out);
@@ -263,8 +263,8 @@ extern "C" int ibln_normal_eps_points(const float* rays_o, const float* rays_d, 
 
 extern "C" int ibln_normal_eps_finish(const float* rays_d, const float* depths4, int n, float eps, float* normal,
                                       float* refl, int device, void* stream) {
-  if (n < 0 || !rays_d || !depths4 || !normal) return IBLN_EINVAL;
   if (n == 0) return 0;
+  if (n < 0 || !rays_d || !depths4 || !normal) return IBLN_EINVAL;
   DeviceGuard g(device);
   normal_eps_finish_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rays_d, depths4, n, eps, normal, refl);
   IBLN_RETURN_LAST();
@@ -278,8 +278,8 @@ extern "C" int ibln_shade_fwd(const float* rays_d, const float* normal, const fl
                               const float* farp, const float* prefiltered, int n_pref, const float* lut, int lut_h,
                               int lut_w, int lut_coef, int correct_depth, int n, float* out, float* out_srgb, int device,
                               void* stream) {
-  if (!SHADE_ARGS_OK || !out) return IBLN_EINVAL;
   if (n == 0) return 0;
+  if (!SHADE_ARGS_OK || !out) return IBLN_EINVAL;
   DeviceGuard g(device);
   shade_fwd_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rays_d, normal, albedo, rough, irr, mip_rough, depth,
                                                                      nearp, farp, prefiltered, n_pref, lut, lut_h, lut_w,
@@ -293,8 +293,8 @@ extern "C" int ibln_shade_bwd(const float* rays_d, const float* normal, const fl
                               int lut_w, int lut_coef, int correct_depth, int n, const float* g_out,
                               const float* g_out_srgb, float* g_albedo, float* g_rough, float* g_irr, float* g_mip_rough,
                               int device, void* stream) {
-  if (!SHADE_ARGS_OK || !g_albedo || !g_rough || !g_irr || !g_mip_rough) return IBLN_EINVAL;
   if (n == 0) return 0;
+  if (!SHADE_ARGS_OK || !g_albedo || !g_rough || !g_irr || !g_mip_rough) return IBLN_EINVAL;
   DeviceGuard g(device);
   shade_bwd_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rays_d, normal, albedo, rough, irr, mip_rough, depth,
                                                                      nearp, farp, prefiltered, n_pref, lut, lut_h, lut_w,

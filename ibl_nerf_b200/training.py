@@ -41,7 +41,7 @@ def phase_b_loss(result, targets):
 
 class TrainStep:
     def __init__(self, device, lut, near=0.5, far=8.0, lr=5e-4, seed=0, precision=None, approximate_radiance=True,
-                 chunk=1 << 20):
+                 chunk=1 << 20, micro_batch=8192):
         torch.manual_seed(seed)
         self.coarse = IBLNeRF(**KITCHEN_ARCH).to(device)
         self.fine = IBLNeRF(**KITCHEN_ARCH).to(device)
@@ -53,21 +53,33 @@ class TrainStep:
         self.kw = kitchen_render_kwargs(self.coarse, self.fine, lut, near, far)
         self.approx = approximate_radiance
         self.chunk = chunk
+        self.micro_batch = micro_batch      # rays per forward/backward pass (bounds the activation stash: ~1.7 GB per 1024 rays)
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         if self.world > 1:       # identical replicas
             for p in self.params:
                 dist.broadcast(p.data, 0)
 
     def step(self, rays_o, rays_d, targets):
-        res = render_decomp(0, 0, None, chunk=self.chunk, rays=(rays_o, rays_d), gt_values=targets,
-                            approximate_radiance=self.approx, **self.kw)
-        loss = phase_b_loss(res, targets)
+        """One optimisation step on all given rays.  Rays beyond `micro_batch` are processed as gradient-accumulated
+        micro-batches (each weighted by its share of the rays), which is the same gradient as one big batch because
+        every loss term is a mean over rays."""
+        n = rays_o.shape[0]
         self.opt.zero_grad(set_to_none=True)
-        loss.backward()
+        total = None
+        for lo in range(0, n, self.micro_batch):
+            hi = min(n, lo + self.micro_batch)
+            tg = targets if (lo == 0 and hi == n) else {k: v[lo:hi] for k, v in targets.items()}
+            res = render_decomp(0, 0, None, chunk=self.chunk, rays=(rays_o[lo:hi], rays_d[lo:hi]), gt_values=tg,
+                                approximate_radiance=self.approx, **self.kw)
+            loss = phase_b_loss(res, tg)
+            if hi - lo != n:
+                loss = loss * ((hi - lo) / n)
+            loss.backward()
+            total = loss.detach() if total is None else total + loss.detach()
         if self.world > 1:
             self.allreduce_grads()
         self.opt.step()
-        return loss
+        return total
 
     def allreduce_grads(self):
         """One NCCL all-reduce over the flattened gradients of both networks (2 x 798 994 fp32); the mean over
