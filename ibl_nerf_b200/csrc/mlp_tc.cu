@@ -72,9 +72,9 @@ __device__ __forceinline__ void process_chunk(const EpiCtx& c, Heads& hd, const 
     h[4 * j4] = r0.x; h[4 * j4 + 1] = r0.y; h[4 * j4 + 2] = r1.x; h[4 * j4 + 3] = r1.y;
   }
   if (STASH && KIND != K_FEATURE) {      // relu bit mask from the sign bits of the pre-activation
-    uint32_t m = 0;
+    uint32_t m = 0;     // one funnel shift per column: bit j = sign of h[j]
 #pragma unroll
-    for (int j = 0; j < 32; ++j) m = (m >> 1) | (__float_as_uint(h[j]) & 0x80000000u);
+    for (int j = 31; j >= 0; --j) m = __funnelshift_l(__float_as_uint(h[j]), m, 1);
     mask_word = ~m;
   }
   constexpr bool kWriteAct = KIND == K_RELU_ACT || KIND == K_L7_FULL || KIND == K_FEATURE || KIND == K_VIEW;
@@ -308,6 +308,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_fwd_kernel(FwdParams prm) {
       const uint4* src = reinterpret_cast<const uint4*>(tile_smem);
       uint4* dst = reinterpret_cast<uint4*>(c.rec + (size_t)blk * KB_BYTES);
       if (g_dbg & 1) return;
+      if (g_dbg & 8) {       // experiment: one bulk (TMA) store with an evict-first L2 policy
+        if (gtid == 0) { bulk_s2g_hint(dst, src, (uint32_t)nblk * KB_BYTES, l2_policy_evict_first()); bulk_commit(); }
+        return;
+      }
 #pragma unroll 8
       for (int i = gtid; i < nblk * (KB_BYTES / 16); i += 128) __stcs(dst + i, src[i]);   // streaming: keep the weight image in L2
     };
@@ -320,7 +324,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_fwd_kernel(FwdParams prm) {
       if (STASH) c.rec = prm.saved + (size_t)tile * SV_BYTES;
       load_bias(0);
       write_encoding<10, 8>(aux, row, x);
-      if (STASH) named_bar_sync(1 + slot, 128);
+      if (STASH) { fence_proxy_async(); named_bar_sync(1 + slot, 128); }
       publish();
       if (STASH) stash_tile(aux, SV_PE, 1);      // off the critical path: overlaps the layer-0 GEMM
 
@@ -339,6 +343,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_fwd_kernel(FwdParams prm) {
         mbar_wait(&acc_ready[slot], acc_phase);
         acc_phase ^= 1;
         tc_fence_after();
+        if (STASH && (g_dbg & 8) && gtid == 0) bulk_wait_read0();   // the previous tile image has left shared memory
         if (!SIGMA_ONLY && s == 10) { if (STASH) named_bar_sync(1 + slot, 128); load_heads(10); }   // view encoding consumed (and stashed): reuse its tile
         named_bar_sync(1 + slot, 128);       // bias row (+ head table) of this step are in smem
         switch (s) {
@@ -357,6 +362,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_fwd_kernel(FwdParams prm) {
           default: drain<K_RELU_ACT, STASH, 8>(c, hd, SV_H(s), s); break;
         }
         if (s + 1 < n_steps) {
+          if (STASH) fence_proxy_async();
           named_bar_sync(1 + slot, 128);     // everyone is done reading this step's bias row / head table; tile complete
           load_bias(s + 1);
           if (s + 1 == 7 || (!SIGMA_ONLY && (s + 1 == 8 || s + 1 == 11 || s + 1 == 12))) load_heads(s + 1);
@@ -392,9 +398,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_fwd_kernel(FwdParams prm) {
           for (int j = 0; j < 9; ++j) dst[j] = make_float2(r[2 * j], r[2 * j + 1]);
         }
       }
+      if (STASH && (g_dbg & 8) && gtid == 0) bulk_wait_read0();
       named_bar_sync(1 + slot, 128);         // last step's bias row no longer needed (next tile overwrites it)
       tc_fence_before();   // order this tile's TMEM reads before the next tile's act_ready arrival
     }
+    if (STASH && gtid == 0) bulk_wait0();
   }
   tc_fence_before();
   __syncthreads();

@@ -11,6 +11,7 @@
 //                 operands are the stashed tiles read as MN-major UMMA operands (no transposes);
 //                 fp32 accumulators live in TMEM for the whole K loop (all points of the CTA) and
 //                 are flushed once with red.global.add.f32 into the flat gradient image.
+#include <cstring>
 #include "mlp_tc.cuh"
 
 namespace ibln {
@@ -98,6 +99,7 @@ struct DgradParams {
   float* flat_grad;          // head-bias gradients are accumulated here directly
   long long P;
   long long n_tiles;
+  int dbg;
 };
 
 // v[0..31] += a * row[0..31] as 16 packed fp32x2 FMAs
@@ -266,6 +268,17 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_dgrad_kernel(DgradParams prm
       }
       // ---- phase writers for the CUDA-core produced gradient tiles
       // heads: 0 = coarse radiance 0|1 (256 cols), 1 = coarse radiance 2 (128 cols), 2 = albedo|irradiance features
+      // Copy-out of a finished K-block: every warp streams its OWN 32 rows (4 KB, contiguous in the operand layout)
+      // to the dY record with coalesced 16-byte stores right after writing them.  No cross-warp hazard (so no
+      // group barrier), and the stores are spread over the drain instead of bursting on the SM's L2 request
+      // port while the weight producer needs it.
+      auto copy_rows = [&](int rec_blk, int kb) {
+        __syncwarp();
+        const uint4* src = reinterpret_cast<const uint4*>(act + (size_t)kb * KB_BYTES + quarter * 4096);
+        uint4* dst = reinterpret_cast<uint4*>(dy + (size_t)rec_blk * KB_BYTES + quarter * 4096);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) __stcs(dst + lane + 32 * i, src[lane + 32 * i]);
+      };
       auto write_head_tile = [&](int which) {
         const int ncc = which == 1 ? 4 : 8;
         const int mslot = which == 0 ? 10 : which == 1 ? 11 : 8;
@@ -297,35 +310,25 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_dgrad_kernel(DgradParams prm
             store_tile4(act, cc >> 1, off[(cc & 1) * 4 + q],
                         make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
                                    pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7])));
+          if (cc & 1) copy_rows(dblk + (cc >> 1), cc >> 1);
         }
       };
-      // finished gradient tile in `act`: verbatim coalesced copy to the dY record (LSU path, see mlp_tc.cu), then
-      // hand it to the MMA issuer
-      auto publish = [&](int dblk, int nblk, bool arrive) {
+      // finished gradient tile in `act`: hand it to the MMA issuer (one arrival per warp)
+      auto publish = [&](bool arrive) {
+        if (!arrive) return;
         fence_proxy_async();
-        named_bar_sync(1 + slot, 128);
-        if (arrive) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&act_ready[slot]);
-        }
-        const uint4* src = reinterpret_cast<const uint4*>(act);      // overlaps the GEMM that reads the same tile
-        uint4* dst = reinterpret_cast<uint4*>(dy + (size_t)dblk * KB_BYTES);
-#pragma unroll 8
-        for (int i = gtid; i < nblk * (KB_BYTES / 16); i += 128) __stcs(dst + i, src[i]);   // streaming store
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&act_ready[slot]);
       };
-      // before overwriting `act`: every thread of the group has finished copying the previous tile out of it
-      auto pre_write = [&]() { named_bar_sync(1 + slot, 128); };
-      pre_write();
       write_head_tile(0);
-      publish(DY_ADDF01, 4, true);
+      publish(true);
       for (int t = 0; t < N_STEPS_BWD; ++t) {
         mbar_wait(&acc_ready[slot], acc_phase);
         acc_phase ^= 1;
         tc_fence_after();
-        pre_write();
-        if (t == 0) { write_head_tile(1); publish(DY_ADDF2, 2, true); continue; }
-        if (t == 3) { write_head_tile(2); publish(DY_AF, 4, true); continue; }
+        if (t == 0) { write_head_tile(1); publish(true); continue; }
+        if (t == 3) { write_head_tile(2); publish(true); continue; }
         // drain: t=1 -> dY_view (mask HV, + radiance term); t=2 -> dY_feat (no mask); t=4 -> dY_7 (+ sigma/rough terms);
         // t>=5 -> dY_{11-t} (mask h_{11-t})
         const int mslot = t == 1 ? 9 : t == 2 ? -1 : t == 4 ? 7 : 11 - t;
@@ -359,6 +362,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_dgrad_kernel(DgradParams prm
             store_tile4(act, cc >> 1, off[(cc & 1) * 4 + q],
                         make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
                                    pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7])));
+          if (cc & 1) copy_rows(dblk + (cc >> 1), cc >> 1);
         };
         uint32_t ra[32], rb[32];
         tmem_ld32(t_lane, ra);
@@ -371,7 +375,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_dgrad_kernel(DgradParams prm
           if (cc + 2 < 8) tmem_ld32(t_lane + (cc + 2) * 32, ra);
           chunk(rb, cc + 1);
         }
-        publish(dblk, 4, !last);
+        publish(!last);
       }
       tc_fence_before();
     }
@@ -382,56 +386,98 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_dgrad_kernel(DgradParams prm
 }
 
 // ---------------------------------------------------------------- wgrad kernel
-// D[m][n] += sum_pt A[pt][m] * B[pt][n] over the tiles of this CTA.  A = 2 adjacent 16 KB blocks of a record
-// (128 "m" columns), B = nb adjacent blocks (64*nb "n" columns, the last one possibly only n_last wide), both
-// read as MN-major SWIZZLE_128B operands.  Optional extra N=16 MMA against a constant ones tile gives the
-// column sums of A (bias gradient) in accumulator column 256.
-struct OutSpec { float* ptr; int m_lo, m_hi, n_lo, n_hi, stride_m, stride_n; };
-struct WgradParams {
-  const uint8_t* a_base; long long a_stride; int a_blk;     // record base / bytes per tile / first block of m-half 0
-  const uint8_t* b_base; long long b_stride; int b_blk;
+// D[m][n] += sum_pt A[pt][m] * B[pt][n].  A = 2 adjacent 16 KB blocks of a record (128 "m" columns), B = nb
+// adjacent blocks (64*nb "n" columns), both read as MN-major SWIZZLE_128B operands straight from the stash /
+// dY records.  Optional extra N=64 MMA against a constant ones tile gives the column sums of A (bias
+// gradient) in accumulator column 256.
+//
+// ONE persistent launch per network covers all 21 GEMMs ("jobs").  The (job, tile) space is linearised with a
+// per-job cost (bytes streamed per tile) and cut into equal contiguous ranges, one per CTA PAIR; the two
+// CTAs of a pair take the two 128-row halves of the same tiles at the same time (the second read of the
+// shared B operand hits L2) or, for single-half jobs, split the tile range.  A CTA therefore flushes its
+// TMEM accumulator (red.global.add.f32) only once per (job, range) segment: ~200 flushes per network
+// instead of one per CTA per job, and no launch gaps between the jobs.
+struct WOut { int off; int m_lo, m_hi, n_lo, n_hi, stride_m, stride_n; };
+struct WJob {
+  int a_sv, a_blk;       // A operand: record (1 = forward stash, 0 = dY record) and first block of m-half 0
+  int b_sv, b_blk;
   int m_halves;          // 1 or 2: CTA class c handles blocks a_blk + 2c, a_blk + 2c + 1
   int nb;                // B blocks (1..4)
   int n_total;           // N of the main MMA (multiple of 16, <= 256)
   int with_ones;
-  long long n_tiles;
-  OutSpec out[4];
+  int cost;              // relative streaming cost of one tile for a CTA pair
   int n_out;
+  WOut out[4];
+};
+constexpr int WG_MAX_JOBS = 21;
+struct WgradParams {
+  const uint8_t* sv; const uint8_t* dy; float* flat;
+  long long n_tiles;
+  int n_jobs;
+  WJob job[WG_MAX_JOBS];
 };
 
-constexpr int WG_STAGE_BYTES = 6 * KB_BYTES;     // A (2 blocks) + B (<= 4 blocks)
-constexpr int WG_SMEM_ONES = 2 * WG_STAGE_BYTES;
-constexpr int WG_SMEM_BAR = WG_SMEM_ONES + KB_BYTES;
-constexpr int WG_SMEM_REQUEST = WG_SMEM_BAR + 128 + 1024;
+// Operand ring: a stage holds WG_STAGE_PTS points of every block (the rows of a 16 KB block are contiguous, so a
+// row range is one bulk copy per block).  Small stages keep more bytes in flight per SM (Little's law: the
+// kernel is a pure HBM/L2 stream, ~0.09 FLOP/B short of the tensor roofline) than whole-tile double buffering.
+constexpr int WG_STAGE_PTS = 32;
+constexpr int WG_SUB = TILE_M / WG_STAGE_PTS;              // stages per tile
+constexpr int WG_BLK_BYTES = WG_STAGE_PTS * 128;           // bytes of one block's row range
+constexpr int WG_STAGE_BYTES = 6 * WG_BLK_BYTES;           // A (2 blocks) + B (<= 4 blocks)
+constexpr int WG_NSTAGES = 8;
+constexpr int WG_SMEM_ONES = WG_NSTAGES * WG_STAGE_BYTES;  // [WG_STAGE_PTS rows][64] ones tile
+constexpr int WG_SMEM_BAR = WG_SMEM_ONES + WG_BLK_BYTES;
+constexpr int WG_SMEM_REQUEST = WG_SMEM_BAR + 256 + 1024;
 constexpr int WG_THREADS = 192;                  // warp 0 producer, warp 1 MMA, warps 2-5 epilogue
 
-__global__ void __launch_bounds__(WG_THREADS, 1) mlp_wgrad_kernel(WgradParams prm) {
+// tile range [t0, t1) and m-half of job j for CTA (pair, r); pairs = number of CTA pairs in the grid
+struct WSeg { long long t0, t1; int cls; };
+__device__ __forceinline__ WSeg wgrad_segment(const WgradParams& prm, int j, long long job_start, long long w_total, int pair,
+                                               int pairs, int r) {
+  const long long lo = w_total * pair / pairs, hi = w_total * (pair + 1) / pairs;
+  const long long c = prm.job[j].cost;
+  auto f = [&](long long x) {
+    long long t = (x - job_start) / c;
+    if (x <= job_start) t = 0;
+    return t > prm.n_tiles ? prm.n_tiles : t;
+  };
+  WSeg s;
+  s.t0 = f(lo); s.t1 = f(hi); s.cls = r;
+  if (prm.job[j].m_halves == 1) {
+    const long long mid = s.t0 + (s.t1 - s.t0 + 1) / 2;
+    if (r == 0) s.t1 = mid; else s.t0 = mid;
+    s.cls = 0;
+  }
+  return s;
+}
+
+__global__ void __launch_bounds__(WG_THREADS, 1) mlp_wgrad_kernel(const __grid_constant__ WgradParams prm) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WG_SMEM_BAR);
-  uint64_t* full = bars;        // [2]
-  uint64_t* empty = bars + 2;   // [2]
-  uint64_t* done = bars + 4;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 5);
+  uint64_t* full = bars;                       // [WG_NSTAGES]
+  uint64_t* empty = bars + WG_NSTAGES;         // [WG_NSTAGES]
+  uint64_t* done = bars + 2 * WG_NSTAGES;      // MMA -> epilogue: the segment's accumulator is complete
+  uint64_t* acc_free = bars + 2 * WG_NSTAGES + 1;   // epilogue -> MMA: the accumulator has been drained
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * WG_NSTAGES + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int cls = blockIdx.x % prm.m_halves;                    // m-half handled by this CTA
-  const int idx = blockIdx.x / prm.m_halves, per_cls = gridDim.x / prm.m_halves;
-  const long long my_tiles = (prm.n_tiles > idx) ? (prm.n_tiles - idx + per_cls - 1) / per_cls : 0;
-  const uint32_t b_bytes = (uint32_t)prm.nb * KB_BYTES;
+  const int pair = blockIdx.x >> 1, r = blockIdx.x & 1, pairs = gridDim.x >> 1;
+  long long w_total = 0;
+  for (int j = 0; j < prm.n_jobs; ++j) w_total += prm.n_tiles * prm.job[j].cost;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < WG_NSTAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(done, 1);
+    mbar_init(acc_free, 4);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr, 512);
-  if (prm.with_ones) {      // ones tile: column 0 of every row = 1.0 (bf16), everything else 0
-    for (int e = threadIdx.x; e < 128 * 8; e += blockDim.x) {
-      int r = e >> 3, c16 = e & 7;
-      *reinterpret_cast<uint4*>(smem + WG_SMEM_ONES + swz_offset(r, c16)) = make_uint4(c16 == 0 ? 0x00003F80u : 0u, 0u, 0u, 0u);
-    }
-    fence_proxy_async();
+  // ones tile: column 0 of every row = 1.0 (bf16), everything else 0
+  for (int e = threadIdx.x; e < WG_STAGE_PTS * 8; e += blockDim.x) {
+    int rr = e >> 3, c16 = e & 7;
+    *reinterpret_cast<uint4*>(smem + WG_SMEM_ONES + swz_offset(rr, c16)) = make_uint4(c16 == 0 ? 0x00003F80u : 0u, 0u, 0u, 0u);
   }
+  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -439,68 +485,188 @@ __global__ void __launch_bounds__(WG_THREADS, 1) mlp_wgrad_kernel(WgradParams pr
 
   if (warp == 0) {
     if (elect_one()) {
-      for (long long i = 0; i < my_tiles; ++i) {
-        const long long tile = idx + i * per_cls;
-        const int stage = (int)(i & 1);
-        const uint32_t ph = (uint32_t)((i >> 1) & 1);
-        mbar_wait(&empty[stage], ph ^ 1);
-        mbar_arrive_expect_tx(&full[stage], 2 * KB_BYTES + b_bytes);
-        uint8_t* dst = smem + stage * WG_STAGE_BYTES;
-        bulk_g2s(dst, prm.a_base + (size_t)tile * prm.a_stride + (size_t)(prm.a_blk + 2 * cls) * KB_BYTES, 2 * KB_BYTES, &full[stage]);
-        bulk_g2s(dst + 2 * KB_BYTES, prm.b_base + (size_t)tile * prm.b_stride + (size_t)prm.b_blk * KB_BYTES, b_bytes, &full[stage]);
+      long long i = 0, job_start = 0;           // i: running tile counter of this CTA (ring position)
+      for (int j = 0; j < prm.n_jobs; ++j) {
+        const WJob& jb = prm.job[j];
+        const WSeg sg = wgrad_segment(prm, j, job_start, w_total, pair, pairs, r);
+        job_start += prm.n_tiles * jb.cost;
+        const uint8_t* a_base = (jb.a_sv ? prm.sv : prm.dy) + (size_t)(jb.a_blk + 2 * sg.cls) * KB_BYTES;
+        const uint8_t* b_base = (jb.b_sv ? prm.sv : prm.dy) + (size_t)jb.b_blk * KB_BYTES;
+        const long long a_stride = jb.a_sv ? SV_BYTES : DY_BYTES, b_stride = jb.b_sv ? SV_BYTES : DY_BYTES;
+        const uint32_t st_bytes = (uint32_t)(2 + jb.nb) * WG_BLK_BYTES;
+        for (long long t = sg.t0; t < sg.t1; ++t) {
+          const uint8_t* a_src = a_base + (size_t)t * a_stride;
+          const uint8_t* b_src = b_base + (size_t)t * b_stride;
+          for (int q = 0; q < WG_SUB; ++q, ++i) {
+            const int stage = (int)(i % WG_NSTAGES);
+            const uint32_t ph = (uint32_t)((i / WG_NSTAGES) & 1);
+            mbar_wait(&empty[stage], ph ^ 1);
+            mbar_arrive_expect_tx(&full[stage], st_bytes);
+            uint8_t* dst = smem + stage * WG_STAGE_BYTES;
+            for (int b = 0; b < 2; ++b)
+              bulk_g2s(dst + b * WG_BLK_BYTES, a_src + (size_t)b * KB_BYTES + q * WG_BLK_BYTES, WG_BLK_BYTES, &full[stage]);
+            for (int b = 0; b < jb.nb; ++b)
+              bulk_g2s(dst + (2 + b) * WG_BLK_BYTES, b_src + (size_t)b * KB_BYTES + q * WG_BLK_BYTES, WG_BLK_BYTES, &full[stage]);
+          }
+        }
       }
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      const uint32_t idesc = make_idesc_bf16(128, (uint32_t)prm.n_total, 1, 1);
       const uint32_t idesc1 = make_idesc_bf16(128, 64, 1, 1);   // whole 64-wide swizzle atom; only column 0 is non-zero
       const uint32_t ones_addr = smem_u32(smem + WG_SMEM_ONES);
-      for (long long i = 0; i < my_tiles; ++i) {
-        const int stage = (int)(i & 1);
-        const uint32_t ph = (uint32_t)((i >> 1) & 1);
-        mbar_wait(&full[stage], ph);
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + stage * WG_STAGE_BYTES);
-        const uint32_t b_addr = a_addr + 2 * KB_BYTES;
-        for (int ks = 0; ks < 8; ++ks) {       // 16 points per MMA
-          const uint32_t acc = (i > 0 || ks > 0) ? 1u : 0u;
-          const uint64_t da = make_desc_mnmajor_sw128(a_addr + ks * 2048, KB_BYTES);
-          umma_bf16(tmem_base, da, make_desc_mnmajor_sw128(b_addr + ks * 2048, KB_BYTES), idesc, acc);
-          if (prm.with_ones) umma_bf16(tmem_base + 256, da, make_desc_mnmajor_sw128(ones_addr + ks * 2048, KB_BYTES), idesc1, acc);
+      long long i = 0, job_start = 0;
+      uint32_t nseg = 0;
+      for (int j = 0; j < prm.n_jobs; ++j) {
+        const WJob& jb = prm.job[j];
+        const WSeg sg = wgrad_segment(prm, j, job_start, w_total, pair, pairs, r);
+        job_start += prm.n_tiles * jb.cost;
+        if (sg.t1 <= sg.t0) continue;
+        if (nseg > 0) { mbar_wait(acc_free, (nseg - 1) & 1); tc_fence_after(); }
+        ++nseg;
+        const uint32_t idesc = make_idesc_bf16(128, (uint32_t)jb.n_total, 1, 1);
+        for (long long t = sg.t0; t < sg.t1; ++t) {
+          for (int q = 0; q < WG_SUB; ++q, ++i) {
+            const int stage = (int)(i % WG_NSTAGES);
+            const uint32_t ph = (uint32_t)((i / WG_NSTAGES) & 1);
+            mbar_wait(&full[stage], ph);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(smem + stage * WG_STAGE_BYTES);
+            const uint32_t b_addr = a_addr + 2 * WG_BLK_BYTES;
+            for (int ks = 0; ks < WG_STAGE_PTS / 16; ++ks) {       // 16 points per MMA
+              const uint32_t acc = (t > sg.t0 || q > 0 || ks > 0) ? 1u : 0u;
+              const uint64_t da = make_desc_mnmajor_sw128(a_addr + ks * 2048, WG_BLK_BYTES);
+              umma_bf16(tmem_base, da, make_desc_mnmajor_sw128(b_addr + ks * 2048, WG_BLK_BYTES), idesc, acc);
+              if (jb.with_ones) umma_bf16(tmem_base + 256, da, make_desc_mnmajor_sw128(ones_addr + ks * 2048, WG_BLK_BYTES), idesc1, acc);
+            }
+            umma_commit(&empty[stage]);
+          }
         }
-        umma_commit(&empty[stage]);
+        umma_commit(done);
       }
-      umma_commit(done);
     }
   } else {
-    mbar_wait(done, 0);
-    tc_fence_after();
-    if (my_tiles > 0) {
-      const int quarter = warp & 3;
-      const int m = cls * 128 + quarter * 32 + lane;
-      const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
-      const int ncols = prm.with_ones ? 288 : ((prm.n_total + 31) & ~31);
+    const int quarter = warp & 3;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    long long job_start = 0;
+    uint32_t nseg = 0;
+    for (int j = 0; j < prm.n_jobs; ++j) {
+      const WJob& jb = prm.job[j];
+      const WSeg sg = wgrad_segment(prm, j, job_start, w_total, pair, pairs, r);
+      job_start += prm.n_tiles * jb.cost;
+      if (sg.t1 <= sg.t0) continue;
+      mbar_wait(done, nseg & 1);
+      ++nseg;
+      tc_fence_after();
+      const int m = sg.cls * 128 + quarter * 32 + lane;
+      const int nmain = (jb.n_total + 31) & ~31;
+      const int ncols = jb.with_ones ? 288 : nmain;
       for (int c0 = 0; c0 < ncols; c0 += 32) {
-        if (c0 >= ((prm.n_total + 31) & ~31) && c0 < 256) continue;
+        if (c0 >= nmain && c0 < 256) continue;
         uint32_t raw[32];
         tmem_ld32(t_lane + c0, raw);
         tmem_wait_ld();
-        for (int o = 0; o < prm.n_out; ++o) {
-          const OutSpec sp = prm.out[o];
+        for (int o = 0; o < jb.n_out; ++o) {
+          const WOut sp = jb.out[o];
           if (m < sp.m_lo || m >= sp.m_hi) continue;
+          float* dst = prm.flat + sp.off + (long long)(m - sp.m_lo) * sp.stride_m;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = c0 + j;
-            if (n >= sp.n_lo && n < sp.n_hi)
-              atomicAdd(sp.ptr + (long long)(m - sp.m_lo) * sp.stride_m + (long long)(n - sp.n_lo) * sp.stride_n, __uint_as_float(raw[j]));
+          for (int jj = 0; jj < 32; ++jj) {
+            const int n = c0 + jj;
+            if (n >= sp.n_lo && n < sp.n_hi) atomicAdd(dst + (long long)(n - sp.n_lo) * sp.stride_n, __uint_as_float(raw[jj]));
           }
         }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_free);
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) { __syncwarp(); tmem_dealloc(tmem_base, 512); }
+}
+
+// the 21 GEMMs of one network's weight gradient
+static WgradParams make_wgrad_jobs() {
+  WgradParams P;
+  memset(&P, 0, sizeof(P));
+  const FlatOff fo = flat_offsets();
+  auto job = [&](int a_sv, int a_blk, int m_halves, int b_sv, int b_blk, int nb, int n_total, int with_ones) -> WJob& {
+    WJob& j = P.job[P.n_jobs++];
+    j.a_sv = a_sv; j.a_blk = a_blk; j.m_halves = m_halves; j.b_sv = b_sv; j.b_blk = b_blk; j.nb = nb; j.n_total = n_total;
+    j.with_ones = with_ones; j.n_out = 0;
+    j.cost = (2 + nb) * (m_halves == 2 ? 2 : 1);
+    return j;
+  };
+  auto add_out = [&](WJob& j, int off, int m_lo, int m_hi, int n_lo, int n_hi, int stride_m, int stride_n) {
+    WOut& o = j.out[j.n_out++];
+    o.off = off; o.m_lo = m_lo; o.m_hi = m_hi; o.n_lo = n_lo; o.n_hi = n_hi; o.stride_m = stride_m; o.stride_n = stride_n;
+  };
+  constexpr int DYR = 0, SVR = 1;
+  // trunk layers: dW_l = dY_l^T X_l (+ bias through the ones column)
+  for (int l = 0; l < 8; ++l) {
+    const int ld = l == 0 ? 63 : (l == 5 ? 319 : 256);
+    if (l == 0 || l == 5) {   // positional-encoding part (63 valid of 64 columns)
+      WJob& p = job(DYR, DY_H(l), 2, SVR, SV_PE, 1, 64, l == 0);
+      add_out(p, fo.w[l], 0, 256, 0, 63, ld, 1);
+      if (l == 0) add_out(p, fo.b[l], 0, 256, 256, 257, 1, 0);
+    }
+    if (l > 0) {
+      WJob& p = job(DYR, DY_H(l), 2, SVR, SV_H(l - 1), 4, 256, 1);
+      add_out(p, fo.w[l] + (l == 5 ? 63 : 0), 0, 256, 0, 256, ld, 1);
+      add_out(p, fo.b[l], 0, 256, 256, 257, 1, 0);
+    }
+  }
+  {   // feature_linear: dY_feat x h7
+    WJob& p = job(DYR, DY_FEAT, 2, SVR, SV_H(7), 4, 256, 1);
+    add_out(p, fo.w[9], 0, 256, 0, 256, 256, 1);
+    add_out(p, fo.b[9], 0, 256, 256, 257, 1, 0);
+  }
+  {   // albedo / irradiance feature linears: dY_af x h7 (rows 0..127 albedo_f, 128..255 irradiance_f)
+    WJob& p = job(DYR, DY_AF, 2, SVR, SV_H(7), 4, 256, 1);
+    add_out(p, fo.w[11], 0, 128, 0, 256, 256, 1);
+    add_out(p, fo.w[14], 128, 256, 0, 256, 256, 1);
+    add_out(p, fo.b[11], 0, 128, 256, 257, 1, 0);
+    add_out(p, fo.b[14], 128, 256, 256, 257, 1, 0);
+  }
+  {   // views_linears.0: dY_view x [feature | view encoding]
+    WJob& p = job(DYR, DY_VIEW, 2, SVR, SV_FEAT, 4, 256, 1);
+    add_out(p, fo.w[8], 0, 256, 0, 256, 283, 1);
+    add_out(p, fo.b[8], 0, 256, 256, 257, 1, 0);
+    WJob& q = job(DYR, DY_VIEW, 2, SVR, SV_DE, 1, 64, 0);   // columns 27.. of the tile are unused
+    add_out(q, fo.w[8] + 256, 0, 256, 0, 27, 283, 1);
+  }
+  {   // coarse-radiance feature linears: dY_addf x hv
+    WJob& p = job(DYR, DY_ADDF01, 2, SVR, SV_HV, 4, 256, 1);
+    add_out(p, fo.w[17], 0, 128, 0, 256, 256, 1);
+    add_out(p, fo.w[18], 128, 256, 0, 256, 256, 1);
+    add_out(p, fo.b[17], 0, 128, 256, 257, 1, 0);
+    add_out(p, fo.b[18], 128, 256, 256, 257, 1, 0);
+    WJob& q = job(DYR, DY_ADDF2, 1, SVR, SV_HV, 4, 256, 1);
+    add_out(q, fo.w[19], 0, 128, 0, 256, 256, 1);
+    add_out(q, fo.b[19], 0, 128, 256, 257, 1, 0);
+  }
+  // small heads: D[feature col][g channel] = X^T G
+  {   // sigma / roughness from h7
+    WJob& p = job(SVR, SV_H(7), 2, DYR, DY_G, 1, 64, 0);
+    add_out(p, fo.w[10], 0, 256, 0, 1, 1, 0);
+    add_out(p, fo.w[13], 0, 256, 4, 5, 1, 0);
+  }
+  {   // albedo (cols 0..127 x channels 1..3) / irradiance (cols 128..255 x channel 5) from AF
+    WJob& p = job(SVR, SV_AF, 2, DYR, DY_G, 1, 64, 0);
+    add_out(p, fo.w[12], 0, 128, 1, 4, 1, 128);
+    add_out(p, fo.w[15], 128, 256, 5, 6, 1, 0);
+  }
+  {   // radiance from hv
+    WJob& p = job(SVR, SV_HV, 2, DYR, DY_G, 1, 64, 0);
+    add_out(p, fo.w[16], 0, 256, 6, 9, 1, 256);
+  }
+  for (int k = 0; k < 3; ++k) {   // coarse radiance heads from ADDF block pair k
+    WJob& p = job(SVR, SV_ADDF + 2 * k, 1, DYR, DY_G, 1, 64, 0);
+    add_out(p, fo.w[20 + k], 0, 128, 9 + 3 * k, 12 + 3 * k, 1, 128);
+  }
+  return P;
 }
 
 }  // namespace mlp
@@ -510,15 +676,6 @@ using namespace ibln;
 using namespace ibln::mlp;
 
 extern "C" int64_t ibln_mlp_bwd_workspace_bytes(int64_t n_pts) { return ((n_pts + TILE_M - 1) / TILE_M) * DY_BYTES; }
-
-static int launch_wgrad(WgradParams& p, int device, cudaStream_t stream) {
-  int sms = num_sms(device);
-  int grid = (sms / p.m_halves) * p.m_halves;
-  long long need = p.n_tiles * p.m_halves;
-  if (need < grid) grid = (int)need;
-  mlp_wgrad_kernel<<<grid, WG_THREADS, WG_SMEM_REQUEST, stream>>>(p);
-  return (int)cudaGetLastError();
-}
 
 extern "C" int ibln_mlp_bwd(const void* packed, const void* saved, const float* g_out, int64_t n_pts, float* flat_grad,
                             void* workspace, int device, void* stream_) {
@@ -530,105 +687,23 @@ extern "C" int ibln_mlp_bwd(const void* packed, const void* saved, const float* 
   // ---- dgrad chain
   DgradParams dp;
   dp.packed = (const uint8_t*)packed; dp.saved = (const uint8_t*)saved; dp.g_out = g_out; dp.dy = (uint8_t*)workspace;
-  dp.flat_grad = flat_grad; dp.P = n_pts; dp.n_tiles = n_tiles;
+  dp.flat_grad = flat_grad; dp.P = n_pts; dp.n_tiles = n_tiles; dp.dbg = g_dbg_host;
   IBLN_CUDA(cudaFuncSetAttribute(mlp_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_REQUEST));
-  long long grid = n_tiles < (long long)num_sms(device) ? n_tiles : (long long)num_sms(device);
+  const int sms = num_sms(device);
+  long long grid = n_tiles < (long long)sms ? n_tiles : (long long)sms;
   if (!(g_dbg_host & 16)) mlp_dgrad_kernel<<<(unsigned)grid, N_THREADS, SMEM_REQUEST, stream>>>(dp);
   IBLN_CUDA(cudaGetLastError());
   if (g_dbg_host & 32) return 0;
-  // ---- wgrad jobs
+  // ---- all weight-gradient GEMMs in one persistent launch
+  static const WgradParams job_table = make_wgrad_jobs();
+  WgradParams wp = job_table;
+  wp.sv = (const uint8_t*)saved; wp.dy = (const uint8_t*)workspace; wp.flat = flat_grad; wp.n_tiles = n_tiles;
   IBLN_CUDA(cudaFuncSetAttribute(mlp_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_REQUEST));
-  const FlatOff fo = flat_offsets();
-  const uint8_t* SV = (const uint8_t*)saved;
-  const uint8_t* DY = (const uint8_t*)workspace;
-  auto job = [&](const uint8_t* a_base, long long a_stride, int a_blk, int m_halves, const uint8_t* b_base, long long b_stride,
-                 int b_blk, int nb, int n_total, int with_ones) {
-    WgradParams p;
-    p.a_base = a_base; p.a_stride = a_stride; p.a_blk = a_blk; p.b_base = b_base; p.b_stride = b_stride; p.b_blk = b_blk;
-    p.m_halves = m_halves; p.nb = nb; p.n_total = n_total; p.with_ones = with_ones; p.n_tiles = n_tiles; p.n_out = 0;
-    return p;
-  };
-  auto add_out = [&](WgradParams& p, float* ptr, int m_lo, int m_hi, int n_lo, int n_hi, int stride_m, int stride_n) {
-    OutSpec& o = p.out[p.n_out++];
-    o.ptr = ptr; o.m_lo = m_lo; o.m_hi = m_hi; o.n_lo = n_lo; o.n_hi = n_hi; o.stride_m = stride_m; o.stride_n = stride_n;
-  };
-  float* G = flat_grad;
-  int rc;
-  // trunk layers: dW_l = dY_l^T X_l (+ bias through the ones column)
-  for (int l = 0; l < 8; ++l) {
-    const int ld = l == 0 ? 63 : (l == 5 ? 319 : 256);
-    if (l == 0 || l == 5) {   // positional-encoding part (63 valid of 64 columns)
-      WgradParams p = job(DY, DY_BYTES, DY_H(l), 2, SV, SV_BYTES, SV_PE, 1, 64, l == 0);
-      add_out(p, G + fo.w[l], 0, 256, 0, 63, ld, 1);
-      if (l == 0) add_out(p, G + fo.b[l], 0, 256, 256, 257, 1, 0);
-      if ((rc = launch_wgrad(p, device, stream)) != 0) return rc;
-    }
-    if (l > 0) {
-      WgradParams p = job(DY, DY_BYTES, DY_H(l), 2, SV, SV_BYTES, SV_H(l - 1), 4, 256, 1);
-      add_out(p, G + fo.w[l] + (l == 5 ? 63 : 0), 0, 256, 0, 256, ld, 1);
-      add_out(p, G + fo.b[l], 0, 256, 256, 257, 1, 0);
-      if ((rc = launch_wgrad(p, device, stream)) != 0) return rc;
-    }
-  }
-  {   // feature_linear: dY_feat x h7
-    WgradParams p = job(DY, DY_BYTES, DY_FEAT, 2, SV, SV_BYTES, SV_H(7), 4, 256, 1);
-    add_out(p, G + fo.w[9], 0, 256, 0, 256, 256, 1);
-    add_out(p, G + fo.b[9], 0, 256, 256, 257, 1, 0);
-    if ((rc = launch_wgrad(p, device, stream)) != 0) return rc;
-  }
-  {   // albedo / irradiance feature linears: dY_af x h7 (rows 0..127 albedo_f, 128..255 irradiance_f)
-    WgradParams p = job(DY, DY_BYTES, DY_AF, 2, SV, SV_BYTES, SV_H(7), 4, 256, 1);
-    add_out(p, G + fo.w[11], 0, 128, 0, 256, 256, 1);
-    add_out(p, G + fo.w[14], 128, 256, 0, 256, 256, 1);
-    add_out(p, G + fo.b[11], 0, 128, 256, 257, 1, 0);
-    add_out(p, G + fo.b[14], 128, 256, 256, 257, 1, 0);
-    if ((rc = launch_wgrad(p, device, stream)) != 0) return rc;
-  }
-  {   // views_linears.0: dY_view x [feature | view encoding]
-    WgradParams p = job(DY, DY_BYTES, DY_VIEW, 2, SV, SV_BYTES, SV_FEAT, 4, 256, 1);
-    add_out(p, G + fo.w[8], 0, 256, 0, 256, 283, 1);
-    add_out(p, G + fo.b[8], 0, 256, 256, 257, 1, 0);
-    if ((rc = launch_wgrad(p, device, stream)) != 0) return rc;
-    WgradParams q = job(DY, DY_BYTES, DY_VIEW, 2, SV, SV_BYTES, SV_DE, 1, 64, 0);   // columns 27.. of the tile are unused
-    add_out(q, G + fo.w[8] + 256, 0, 256, 0, 27, 283, 1);
-    if ((rc = launch_wgrad(q, device, stream)) != 0) return rc;
-  }
-  {   // coarse-radiance feature linears: dY_addf x hv
-    WgradParams p = job(DY, DY_BYTES, DY_ADDF01, 2, SV, SV_BYTES, SV_HV, 4, 256, 1);
-    add_out(p, G + fo.w[17], 0, 128, 0, 256, 256, 1);
-    add_out(p, G + fo.w[18], 128, 256, 0, 256, 256, 1);
-    add_out(p, G + fo.b[17], 0, 128, 256, 257, 1, 0);
-    add_out(p, G + fo.b[18], 128, 256, 256, 257, 1, 0);
-    if ((rc = launch_wgrad(p, device, stream)) != 0) return rc;
-    WgradParams q = job(DY, DY_BYTES, DY_ADDF2, 1, SV, SV_BYTES, SV_HV, 4, 256, 1);
-    add_out(q, G + fo.w[19], 0, 128, 0, 256, 256, 1);
-    add_out(q, G + fo.b[19], 0, 128, 256, 257, 1, 0);
-    if ((rc = launch_wgrad(q, device, stream)) != 0) return rc;
-  }
-  // small heads: D[feature col][g channel] = X^T G
-  {   // sigma / roughness from h7
-    WgradParams p = job(SV, SV_BYTES, SV_H(7), 2, DY, DY_BYTES, DY_G, 1, 64, 0);
-    add_out(p, G + fo.w[10], 0, 256, 0, 1, 1, 0);
-    add_out(p, G + fo.w[13], 0, 256, 4, 5, 1, 0);
-    if ((rc = launch_wgrad(p, device, stream)) != 0) return rc;
-  }
-  {   // albedo (cols 0..127 x channels 1..3) / irradiance (cols 128..255 x channel 5) from AF
-    WgradParams p = job(SV, SV_BYTES, SV_AF, 2, DY, DY_BYTES, DY_G, 1, 64, 0);
-    add_out(p, G + fo.w[12], 0, 128, 1, 4, 1, 128);
-    add_out(p, G + fo.w[15], 128, 256, 5, 6, 1, 0);
-    if ((rc = launch_wgrad(p, device, stream)) != 0) return rc;
-  }
-  {   // radiance from hv
-    WgradParams p = job(SV, SV_BYTES, SV_HV, 2, DY, DY_BYTES, DY_G, 1, 64, 0);
-    add_out(p, G + fo.w[16], 0, 256, 6, 9, 1, 256);
-    if ((rc = launch_wgrad(p, device, stream)) != 0) return rc;
-  }
-  for (int k = 0; k < 3; ++k) {   // coarse radiance heads from ADDF block pair k
-    WgradParams p = job(SV, SV_BYTES, SV_ADDF + 2 * k, 1, DY, DY_BYTES, DY_G, 1, 64, 0);
-    add_out(p, G + fo.w[20 + k], 0, 128, 9 + 3 * k, 12 + 3 * k, 1, 128);
-    if ((rc = launch_wgrad(p, device, stream)) != 0) return rc;
-  }
-  return 0;
+  long long pairs = sms / 2;
+  if (pairs > n_tiles * 4) pairs = n_tiles * 4;      // tiny inputs: do not launch CTAs that would only idle
+  if (pairs < 1) pairs = 1;
+  mlp_wgrad_kernel<<<(unsigned)(2 * pairs), WG_THREADS, WG_SMEM_REQUEST, stream>>>(wp);
+  IBLN_RETURN_LAST();
 }
 
 // MN-major operand self-test: D[128,N] = X^T Y with X [128 pts][128], Y [128 pts][N] staged as operand tiles.

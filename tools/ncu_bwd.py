@@ -1,4 +1,5 @@
-import sys, os, ctypes
+"""ncu target: one forward-with-stash + one backward (dgrad + wgrad) of the fine pass (786 432 points)."""
+import sys, os
 R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, R); sys.path.insert(0, os.path.join(R, "tests"))
 import torch, fixtures as fx
@@ -9,23 +10,17 @@ dev = torch.device("cuda:0")
 torch.manual_seed(0)
 net = ib.IBLNeRF(**fx.KITCHEN_ARCH).to(dev)
 h = _lib.lib()
-h.ibln_debug_set.argtypes = [ctypes.c_int]
 n, s = 4096, 192
 o = torch.rand(n, 3, device=dev); d = torch.randn(n, 3, device=dev)
 z = torch.sort(torch.rand(n, s, device=dev) * 7 + 0.5, -1)[0]
 P = n * s
 out = torch.empty(P, 18, device=dev)
 stash = torch.empty(h.ibln_mlp_saved_bytes(P), dtype=torch.uint8, device=dev)
+ws = torch.empty(h.ibln_mlp_bwd_workspace_bytes(P), dtype=torch.uint8, device=dev)
+flat = torch.zeros(798994, device=dev)
+g = torch.randn(P, 18, device=dev)
 packed = net.packed_weights()
-def run(st):
-    call("ibln_mlp_fwd", dev, ptr(packed), 1, None, ptr(o), ptr(d), ptr(z), n, s, 0.0, 0, ptr(out), ptr(st) if st is not None else None)
-for flags in (0, 8, 1, 7, -1):
-    if flags >= 0: h.ibln_debug_set(flags)
-    st = stash if flags >= 0 else None
-    for _ in range(2): run(st)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(5): run(st)
-    e1.record(); torch.cuda.synchronize()
-    print("flags", flags, "ms %.3f" % (e0.elapsed_time(e1) / 5))
+for _ in range(2):
+    call("ibln_mlp_fwd", dev, ptr(packed), 1, None, ptr(o), ptr(d), ptr(z), n, s, 0.0, 0, ptr(out), ptr(stash))
+    call("ibln_mlp_bwd", dev, ptr(packed), ptr(stash), ptr(g), P, ptr(flat), ptr(ws))
+torch.cuda.synchronize()
