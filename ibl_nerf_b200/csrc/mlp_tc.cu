@@ -479,7 +479,8 @@ umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, f
 using namespace ibln;
 using namespace ibln::mlp;
 
-namespace ibln { namespace mlp { int g_dbg_host = 0; } }
+namespace ibln { namespace mlp { int g_dbg_host = 0; void* g_timeline = nullptr; } }
+extern "C" int ibln_debug_timeline(void* device_buf) { ibln::mlp::g_timeline = device_buf; return 0; }
 extern "C" int ibln_debug_set(int flags) { ibln::mlp::g_dbg_host = flags; return (int)cudaMemcpyToSymbol(ibln::mlp::g_dbg, &flags, sizeof(int)); }
 
 extern "C" int64_t ibln_mlp_packed_bytes(void) { return PACKED_BYTES; }

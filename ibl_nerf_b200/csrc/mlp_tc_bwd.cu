@@ -16,7 +16,8 @@
 
 namespace ibln {
 namespace mlp {
-extern int g_dbg_host;   // diagnostics (mlp_tc.cu): bit4 skip dgrad, bit5 skip wgrad
+extern int g_dbg_host;
+extern void* g_timeline;   // diagnostics: device buffer set by ibln_debug_timeline (mlp_tc.cu)   // diagnostics (mlp_tc.cu): bit4 skip dgrad, bit5 skip wgrad
 
 // ---------------------------------------------------------------- dgrad step program
 constexpr int N_STEPS_BWD = 12;
@@ -100,7 +101,12 @@ struct DgradParams {
   long long P;
   long long n_tiles;
   int dbg;
+  unsigned long long* tl;    // optional timeline buffer (diagnostics): block 0 appends (tag << 48 | clock64)
 };
+
+__device__ __forceinline__ void tl_mark(unsigned long long* tl, int base, int& n, int tag) {
+  if (tl != nullptr && blockIdx.x == 0 && n < 1000) tl[base + n++] = ((unsigned long long)tag << 48) | ((unsigned long long)clock64() & 0xFFFFFFFFFFFFull);
+}
 
 // v[0..31] += a * row[0..31] as 16 packed fp32x2 FMAs
 __device__ __forceinline__ void axpy32(float (&v)[32], float a, const float* row) {
@@ -119,7 +125,13 @@ __device__ __forceinline__ void store_tile4(uint8_t* tile, int kb, uint32_t swz,
   *reinterpret_cast<uint4*>(tile + (size_t)kb * KB_BYTES + swz) = pk;
 }
 
-__global__ void __launch_bounds__(N_THREADS, 1) mlp_dgrad_kernel(DgradParams prm) {
+// 18 warps: producer, MMA issuer, and 8 epilogue warps per tile slot.  Two warps share each TMEM lane quarter
+// (a warp may only touch lanes 32*(warp%4)..) and split the 256 accumulator columns in halves; the epilogue
+// is latency-bound (TMEM load -> select -> pack -> st.shared chains), so 4 warps per scheduler instead of 2
+// nearly halve it.
+constexpr int DG_EPI_THREADS = 256;              // per slot
+constexpr int DG_THREADS = 64 + 2 * DG_EPI_THREADS;
+__global__ void __launch_bounds__(DG_THREADS, 1) mlp_dgrad_kernel(DgradParams prm) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_BAR);
@@ -133,7 +145,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_dgrad_kernel(DgradParams prm
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < N_STAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&act_ready[i], 4); mbar_init(&acc_ready[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&act_ready[i], DG_EPI_THREADS / 32); mbar_init(&acc_ready[i], 1); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr, 512);
@@ -166,6 +178,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_dgrad_kernel(DgradParams prm
     if (elect_one()) {
       constexpr uint32_t IDESC256 = make_idesc_bf16(128, 256, 0, 0);
       int stage = 0;
+      int tl_n = 0;
       uint32_t phase = 0;
       uint32_t act_phase[2] = {0, 0};
       long long rounds = (my_tiles + 1) / 2;
@@ -177,6 +190,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_dgrad_kernel(DgradParams prm
             mbar_wait(&act_ready[slot], act_phase[slot]);
             act_phase[slot] ^= 1;
             tc_fence_after();
+            tl_mark(prm.tl, 2048, tl_n, 100 + t * 2 + slot);
             const uint32_t act_addr = smem_u32(smem + SMEM_ACT + slot * ACT_BYTES);
             const uint32_t d_tmem = tmem_base + slot * 256;
             for (int kbi = 0; kbi < st.nkb; ++kbi) {
@@ -194,31 +208,36 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_dgrad_kernel(DgradParams prm
               if (stage == N_STAGES) { stage = 0; phase ^= 1; }
             }
             umma_commit(&acc_ready[slot]);
+            tl_mark(prm.tl, 2048, tl_n, 200 + t * 2 + slot);
           }
         }
     }
   } else {
-    const int slot = (warp - 2) >> 2;
-    const int quarter = warp & 3;
+    const int slot = (warp - 2) >> 3;
+    const int quarter = warp & 3;                   // TMEM lane quarter this warp may access
+    const int half = ((warp - 2) >> 2) & 1;         // column half (chunks 4*half .. 4*half+3) of the 256-wide tiles
     const int row = quarter * 32 + lane;
     uint8_t* act = smem + SMEM_ACT + slot * ACT_BYTES;
     const float* cst = reinterpret_cast<const float*>(prm.packed + PACKED_CONST_OFF);
     const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + slot * 256;
     const FlatOff fo = flat_offsets();
     uint32_t acc_phase = 0;
+    int tl_n = 0;
+    unsigned long long* tl = (quarter == 0 && half == 0 && lane == 0) ? prm.tl : nullptr;
+    const int tl_base = slot * 1024;
     // small-head weight tables -> the slot's (otherwise unused) encoding tile, once per kernel:
     // channel-major rows: [coarse radiance k: 3x128 each, 1152][albedo 3x128 | irradiance 128: 512][radiance 3x256: 768][sigma, rough: 512]
     const float* tab = reinterpret_cast<const float*>(smem + SMEM_AUX + slot * AUX_BYTES);
     const float* T_ADD = tab; const float* T_AF = tab + 1152; const float* T_RAD = tab + 1664; const float* T_SR = tab + 2432;
-    const int gtid = threadIdx.x - 64 - slot * 128;
+    const int gtid = threadIdx.x - 64 - slot * DG_EPI_THREADS;
     {
       float4* dst = reinterpret_cast<float4*>(smem + SMEM_AUX + slot * AUX_BYTES);
-      for (int i = gtid; i < 736; i += 128) {
+      for (int i = gtid; i < 736; i += DG_EPI_THREADS) {
         const float* src = i < 288 ? cst + C_ADD + 4 * i : i < 416 ? cst + C_AF + 4 * (i - 288)
                          : i < 608 ? cst + C_RAD + 4 * (i - 416) : cst + C_SR + 4 * (i - 608);
         dst[i] = __ldg(reinterpret_cast<const float4*>(src));
       }
-      named_bar_sync(1 + slot, 128);
+      named_bar_sync(1 + slot, DG_EPI_THREADS);
     }
     uint32_t off[8];
 #pragma unroll
@@ -237,7 +256,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_dgrad_kernel(DgradParams prm
         g[2 * j] = v.x; g[2 * j + 1] = v.y;
       }
       // ---- head-bias gradients: column sums of g over the warp's 32 rows
-      {
+      if (half == 0) {
         float s[18];
 #pragma unroll
         for (int j = 0; j < 18; ++j) s[j] = warp_sum(g[j]);
@@ -256,7 +275,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_dgrad_kernel(DgradParams prm
         }
       }
       // ---- G tile: g_raw as bf16 [128][64] (columns 18.. zero) for the small-head wgrads
-      {
+      if (half == 0) {
         float e[64];
 #pragma unroll
         for (int j = 0; j < 64; ++j) e[j] = j < 18 ? g[j] : 0.f;
@@ -283,10 +302,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_dgrad_kernel(DgradParams prm
         const int ncc = which == 1 ? 4 : 8;
         const int mslot = which == 0 ? 10 : which == 1 ? 11 : 8;
         const int dblk = which == 0 ? DY_ADDF01 : which == 1 ? DY_ADDF2 : DY_AF;
-        uint4 mw0 = __ldg(reinterpret_cast<const uint4*>(masks + mslot * 1024));
-        uint4 mw1 = __ldg(reinterpret_cast<const uint4*>(masks + mslot * 1024) + 1);
-        const uint32_t mw[8] = {mw0.x, mw0.y, mw0.z, mw0.w, mw1.x, mw1.y, mw1.z, mw1.w};
-        for (int cc = 0; cc < ncc; ++cc) {
+        const int cc0 = half * (ncc >> 1), w0 = cc0 & ~3;     // this warp's chunks and the 4-word mask group holding them
+        const uint4 mwv = __ldg(reinterpret_cast<const uint4*>(masks + mslot * 1024 + w0));
+        const uint32_t mw[4] = {mwv.x, mwv.y, mwv.z, mwv.w};
+        for (int cc = cc0; cc < cc0 + (ncc >> 1); ++cc) {
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = 0.f;
@@ -302,7 +321,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_dgrad_kernel(DgradParams prm
 #pragma unroll
             for (int q = 0; q < 3; ++q) axpy32(v, g[9 + 3 * head + q], T_ADD + head * 384 + q * 128 + (cc & 3) * 32);
           }
-          const uint32_t m = mw[cc];
+          const uint32_t m = mw[cc - w0];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = ((m >> j) & 1u) ? v[j] : 0.f;
 #pragma unroll
@@ -321,26 +340,28 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_dgrad_kernel(DgradParams prm
         __syncwarp();
         if (lane == 0) mbar_arrive(&act_ready[slot]);
       };
+      tl_mark(tl, tl_base, tl_n, 1);
       write_head_tile(0);
       publish(true);
+      tl_mark(tl, tl_base, tl_n, 2);
       for (int t = 0; t < N_STEPS_BWD; ++t) {
         mbar_wait(&acc_ready[slot], acc_phase);
         acc_phase ^= 1;
         tc_fence_after();
-        if (t == 0) { write_head_tile(1); publish(true); continue; }
-        if (t == 3) { write_head_tile(2); publish(true); continue; }
+        tl_mark(tl, tl_base, tl_n, 10 + 2 * t);
+        if (t == 0) { write_head_tile(1); publish(true); tl_mark(tl, tl_base, tl_n, 11 + 2 * t); continue; }
+        if (t == 3) { write_head_tile(2); publish(true); tl_mark(tl, tl_base, tl_n, 11 + 2 * t); continue; }
         // drain: t=1 -> dY_view (mask HV, + radiance term); t=2 -> dY_feat (no mask); t=4 -> dY_7 (+ sigma/rough terms);
         // t>=5 -> dY_{11-t} (mask h_{11-t})
         const int mslot = t == 1 ? 9 : t == 2 ? -1 : t == 4 ? 7 : 11 - t;
         const int dblk = t == 1 ? DY_VIEW : t == 2 ? DY_FEAT : t == 4 ? DY_H(7) : DY_H(11 - t);
-        uint32_t mw[8];
+        uint32_t mw[4];
         if (mslot >= 0) {
-          uint4 mw0 = __ldg(reinterpret_cast<const uint4*>(masks + mslot * 1024));
-          uint4 mw1 = __ldg(reinterpret_cast<const uint4*>(masks + mslot * 1024) + 1);
-          mw[0] = mw0.x; mw[1] = mw0.y; mw[2] = mw0.z; mw[3] = mw0.w; mw[4] = mw1.x; mw[5] = mw1.y; mw[6] = mw1.z; mw[7] = mw1.w;
+          const uint4 mwv = __ldg(reinterpret_cast<const uint4*>(masks + mslot * 1024 + half * 4));
+          mw[0] = mwv.x; mw[1] = mwv.y; mw[2] = mwv.z; mw[3] = mwv.w;
         } else {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) mw[i] = 0xffffffffu;
+          for (int i = 0; i < 4; ++i) mw[i] = 0xffffffffu;
         }
         const bool last = (t == N_STEPS_BWD - 1);
         auto chunk = [&](const uint32_t (&raw)[32], int cc) {
@@ -354,7 +375,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_dgrad_kernel(DgradParams prm
             axpy32(v, g[0], T_SR + cc * 32);
             axpy32(v, g[4], T_SR + 256 + cc * 32);
           }
-          const uint32_t m = mw[cc];
+          const uint32_t m = mw[cc & 3];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = ((m >> j) & 1u) ? v[j] : 0.f;
 #pragma unroll
@@ -365,17 +386,19 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_dgrad_kernel(DgradParams prm
           if (cc & 1) copy_rows(dblk + (cc >> 1), cc >> 1);
         };
         uint32_t ra[32], rb[32];
-        tmem_ld32(t_lane, ra);
+        const int c0 = half * 4;
+        tmem_ld32(t_lane + c0 * 32, ra);
 #pragma unroll
-        for (int cc = 0; cc < 8; cc += 2) {
+        for (int i = 0; i < 4; i += 2) {
           tmem_wait_ld();
-          tmem_ld32(t_lane + (cc + 1) * 32, rb);
-          chunk(ra, cc);
+          tmem_ld32(t_lane + (c0 + i + 1) * 32, rb);
+          chunk(ra, c0 + i);
           tmem_wait_ld();
-          if (cc + 2 < 8) tmem_ld32(t_lane + (cc + 2) * 32, ra);
-          chunk(rb, cc + 1);
+          if (i + 2 < 4) tmem_ld32(t_lane + (c0 + i + 2) * 32, ra);
+          chunk(rb, c0 + i + 1);
         }
         publish(!last);
+        tl_mark(tl, tl_base, tl_n, 11 + 2 * t);
       }
       tc_fence_before();
     }
@@ -687,11 +710,11 @@ extern "C" int ibln_mlp_bwd(const void* packed, const void* saved, const float* 
   // ---- dgrad chain
   DgradParams dp;
   dp.packed = (const uint8_t*)packed; dp.saved = (const uint8_t*)saved; dp.g_out = g_out; dp.dy = (uint8_t*)workspace;
-  dp.flat_grad = flat_grad; dp.P = n_pts; dp.n_tiles = n_tiles; dp.dbg = g_dbg_host;
+  dp.flat_grad = flat_grad; dp.P = n_pts; dp.n_tiles = n_tiles; dp.dbg = g_dbg_host; dp.tl = (unsigned long long*)g_timeline;
   IBLN_CUDA(cudaFuncSetAttribute(mlp_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_REQUEST));
   const int sms = num_sms(device);
   long long grid = n_tiles < (long long)sms ? n_tiles : (long long)sms;
-  if (!(g_dbg_host & 16)) mlp_dgrad_kernel<<<(unsigned)grid, N_THREADS, SMEM_REQUEST, stream>>>(dp);
+  if (!(g_dbg_host & 16)) mlp_dgrad_kernel<<<(unsigned)grid, DG_THREADS, SMEM_REQUEST, stream>>>(dp);
   IBLN_CUDA(cudaGetLastError());
   if (g_dbg_host & 32) return 0;
   // ---- all weight-gradient GEMMs in one persistent launch
