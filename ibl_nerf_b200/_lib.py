@@ -36,6 +36,7 @@ _SIGS = {
     "ibln_mlp_bwd": [c_p, c_p, c_p, c_i64, c_p, c_p],
     "ibln_umma_selftest": [c_p, c_p, c_p, c_int, c_int, c_int],
     "ibln_umma_mn_selftest": [c_p, c_p, c_p, c_int],
+    "ibln_umma_pair_selftest": [c_p, c_p, c_p, c_int],
     "ibln_store_probe": [c_p, c_i64, c_int, c_int],
 }
 _PLAIN = {  # no device/stream tail
@@ -49,7 +50,7 @@ _PLAIN = {  # no device/stream tail
 
 _lib = None
 # kernels launched per entry point (for bench.py's gpu_launches); default 1
-KERNELS_PER_CALL = {"ibln_sgemm_wgrad": 2, "ibln_mlp_pack_weights": 3, "ibln_mlp_bwd": 24}
+KERNELS_PER_CALL = {"ibln_sgemm_wgrad": 2, "ibln_mlp_pack_weights": 3, "ibln_mlp_bwd": 2}
 # bench.py sets this to {} to collect per-entry launch counts, CUDA-event pairs and algorithmic FLOPs
 PROFILE = None
 

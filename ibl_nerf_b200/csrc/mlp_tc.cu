@@ -19,14 +19,41 @@
 namespace ibln {
 namespace mlp {
 
+int g_dbg_host = 0;
+void* g_timeline = nullptr;   // diagnostics: device buffer set by ibln_debug_timeline
+
+int make_chunk_stream_map(CUtensorMap* map, const void* base, int n_chunks) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = []() -> EncodeFn {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<EncodeFn>(fn);
+  }();
+  if (encode == nullptr) return IBLN_EINVAL;
+  const cuuint64_t dims[2] = {64, (cuuint64_t)n_chunks * 128};
+  const cuuint64_t strides[1] = {128};
+  const cuuint32_t box[2] = {64, 64};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : IBLN_EINVAL;
+}
+
 // ---------------------------------------------------------------- the fused forward kernel
 __device__ int g_dbg = 0;   // diagnostics: bit0 skip tile copies, bit1 skip AF/ADD direct stores, bit2 skip mask stores
 struct FwdParams {
+  CUtensorMap wmap;          // forward chunk stream as a 2-D tensor (rows of 64 bf16)
   const uint8_t* packed;     // chunk stream + const section
   PointGen gen;
   float* out;                // [P] or [P,18]
   uint8_t* saved;            // activation stash (SV_BYTES per tile) or nullptr
   long long n_tiles;
+  unsigned long long* tl;    // optional timeline buffer (diagnostics)
 };
 
 __device__ __forceinline__ int n_chunks_of(const Step& st) { return (st.aux_first + st.kb_act + st.aux_last) * (st.n / 128); }
@@ -72,9 +99,14 @@ __device__ __forceinline__ void process_chunk(const EpiCtx& c, Heads& hd, const 
     h[4 * j4] = r0.x; h[4 * j4 + 1] = r0.y; h[4 * j4 + 2] = r1.x; h[4 * j4 + 3] = r1.y;
   }
   if (STASH && KIND != K_FEATURE) {      // relu bit mask from the sign bits of the pre-activation
-    uint32_t m = 0;     // one funnel shift per column: bit j = sign of h[j]
+    // one funnel shift per column (bit j = sign of h[j]) as four independent 8-long chains: a single 32-long
+    // dependent chain costs ~160 cycles of latency per chunk with only two epilogue warps per scheduler
+    uint32_t pm[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-    for (int j = 31; j >= 0; --j) m = __funnelshift_l(__float_as_uint(h[j]), m, 1);
+    for (int i = 7; i >= 0; --i)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) pm[q] = __funnelshift_l(__float_as_uint(h[8 * q + i]), pm[q], 1);
+    const uint32_t m = (pm[0] & 0xffu) | ((pm[1] & 0xffu) << 8) | ((pm[2] & 0xffu) << 16) | (pm[3] << 24);
     mask_word = ~m;
   }
   constexpr bool kWriteAct = KIND == K_RELU_ACT || KIND == K_L7_FULL || KIND == K_FEATURE || KIND == K_VIEW;
@@ -96,7 +128,7 @@ __device__ __forceinline__ void process_chunk(const EpiCtx& c, Heads& hd, const 
                         pack_bf16x2(h[8 * q + 4], h[8 * q + 5]), pack_bf16x2(h[8 * q + 6], h[8 * q + 7]));
       const uint32_t o = c.off[(cc & 1) * 4 + q];
       if (kWriteAct) *reinterpret_cast<uint4*>(c.act + kb * KB_BYTES + o) = pk;
-      else if (!(g_dbg & 2)) __stcs(reinterpret_cast<uint4*>(c.rec + (size_t)(sv_blk + kb) * KB_BYTES + o), pk);   // STASH only (AF / ADD): no smem copy exists
+      else if (c.rec != nullptr && !(g_dbg & 2)) __stcs(reinterpret_cast<uint4*>(c.rec + (size_t)(sv_blk + kb) * KB_BYTES + o), pk);   // STASH only (AF / ADD): no smem copy exists
     }
   }
   const float* T = c.heads_s;     // this step's head rows (staged in the idle encoding tile)
@@ -146,57 +178,70 @@ __device__ __forceinline__ void drain(const EpiCtx& c, Heads& hd, int sv_blk, in
     if (cc + 2 < NCHUNK) tmem_ld32(c.t_lane + (cc + 2) * 32, va);
     process_chunk<KIND, STASH>(c, hd, vb, cc + 1, sv_blk, mw[cc + 1]);
   }
-  if (STASH && KIND != K_FEATURE && !(g_dbg & 4)) {      // one full 32-byte sector per row: [mask slot][row][8 words]
+  if (STASH && KIND != K_FEATURE && c.rec != nullptr && !(g_dbg & 4)) {      // one full 32-byte sector per row: [mask slot][row][8 words]
     uint4* dst = reinterpret_cast<uint4*>(c.rec + (size_t)SV_MASK * KB_BYTES + sv_mask * 4096 + c.row * 32);
     __stcs(dst, make_uint4(mw[0], mw[1], mw[2], mw[3]));
     __stcs(dst + 1, make_uint4(mw[4], mw[5], mw[6], mw[7]));
   }
 }
 
+// CTA pair (cluster of 2 = the two SMs of a TPC): every GEMM step is ONE M=256 tcgen05.mma.cta_group::2 chain over
+// the two CTAs' 128-point tiles.  Each CTA streams only ITS half of the weight rows (N/2) into its ring, so the
+// per-SM L2->shared weight traffic and the shared-memory B-operand reads are halved -- with all 148 SMs
+// re-streaming the full 1.5 MB image per 128 points the chip-wide L2 bandwidth capped the MMA rate at ~2/3.
+// Rank 0 issues the MMAs; tcgen05.commit multicasts stage-free / accumulator-ready to both CTAs; rank 1's
+// otherwise idle warp 1 relays "my half of the stage has landed" to the leader; the epilogue warps of both CTAs
+// arrive on the leader's act_ready barrier.
 template <bool SIGMA_ONLY, bool STASH>
-__global__ void __launch_bounds__(N_THREADS, 1) mlp_fwd_kernel(FwdParams prm) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) mlp_fwd_kernel(const __grid_constant__ FwdParams prm) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_BAR);
-  uint64_t* w_full = bars;                 // [N_STAGES]
-  uint64_t* w_empty = bars + N_STAGES;     // [N_STAGES]
-  uint64_t* act_ready = bars + 2 * N_STAGES;      // [2] epilogue -> MMA
-  uint64_t* acc_ready = bars + 2 * N_STAGES + 2;  // [2] MMA -> epilogue
+  uint64_t* w_full = bars;                 // [N_STAGES] (leader) both CTAs' halves of the stage have landed
+  uint64_t* w_empty = bars + N_STAGES;     // [N_STAGES] stage consumed (multicast commit)
+  uint64_t* act_ready = bars + 2 * N_STAGES;      // [2] (leader) epilogues of both CTAs -> MMA
+  uint64_t* acc_ready = bars + 2 * N_STAGES + 2;  // [2] MMA -> epilogue (multicast commit)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * N_STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
   constexpr int n_steps = SIGMA_ONLY ? N_STEPS_SIGMA : N_STEPS_FULL;
-  // tiles of this CTA: t = blockIdx.x + k * gridDim.x, k-th tile goes to slot k & 1
-  const long long my_tiles = (prm.n_tiles > (long long)blockIdx.x) ? (prm.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  // tiles of this CTA: t = blockIdx.x + k * gridDim.x, k-th tile goes to slot k & 1.  The pair runs in lock step
+  // for pair_tiles rounds (= the leader's count); a tile the second CTA does not have is a phantom (no loads/stores).
+  const long long lead = (long long)(blockIdx.x & ~1u);
+  const long long pair_tiles = (prm.n_tiles > lead) ? (prm.n_tiles - lead + gridDim.x - 1) / gridDim.x : 0;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < N_STAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&act_ready[i], 4); mbar_init(&acc_ready[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&act_ready[i], 8); mbar_init(&acc_ready[i], 1); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_ptr, 512);
+  if (warp == 1) tmem_alloc_pair(tmem_ptr, 512);
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  const long long rounds = (pair_tiles + 1) / 2;
 
   if (warp == 0) {
-    // ===================== weight producer =====================
+    // ===================== weight producer (both CTAs: own half of every K-block) =====================
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      long long rounds = (my_tiles + 1) / 2;
       for (long long r = 0; r < rounds; ++r) {
         for (int s = 0; s < n_steps; ++s) {
           const Step st = step_at(s);
-          const int nch = n_chunks_of(st);
+          const int nkb = st.aux_first + st.kb_act + st.aux_last;
+          const int halves = st.n == 256 ? 2 : 1;      // my N/2 weight rows of a K-block = 128 or 64 rows of 128 B
           for (int slot = 0; slot < 2; ++slot) {
-            if (2 * r + slot >= my_tiles) continue;
-            for (int c = 0; c < nch; ++c) {
+            if (2 * r + slot >= pair_tiles) continue;
+            for (int kbi = 0; kbi < nkb; ++kbi) {
+              const int row0 = st.n == 256 ? (st.chunk_base + 2 * kbi + (int)rank) * 128 : (st.chunk_base + kbi) * 128 + (int)rank * 64;
               mbar_wait(&w_empty[stage], phase ^ 1);
-              mbar_arrive_expect_tx(&w_full[stage], KB_BYTES);
-              bulk_g2s(smem + SMEM_RING + stage * KB_BYTES, prm.packed + (size_t)(st.chunk_base + c) * KB_BYTES, KB_BYTES,
-                       &w_full[stage]);
+              if (rank == 0) mbar_arrive_expect_tx(&w_full[stage], 2u * halves * (KB_BYTES / 2));   // both CTAs' bytes
+              for (int h = 0; h < halves; ++h)
+                tma_load_2d_pair(smem + SMEM_RING + stage * KB_BYTES + h * (KB_BYTES / 2), &prm.wmap, 0, row0 + 64 * h, &w_full[stage]);
               if (++stage == N_STAGES) { stage = 0; phase ^= 1; }
             }
           }
@@ -204,61 +249,45 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_fwd_kernel(FwdParams prm) {
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
     if (elect_one()) {
-      constexpr uint32_t IDESC = make_idesc_bf16(128, 128, 0, 0);
-      constexpr uint32_t IDESC256 = make_idesc_bf16(128, 256, 0, 0);
-      static_assert(N_STAGES == 4, "stage pairing assumes a 4-deep ring and even chunk counts per step");
       int stage = 0;
       uint32_t phase = 0;
-      uint32_t act_phase[2] = {0, 0};
-      long long rounds = (my_tiles + 1) / 2;
-      for (long long r = 0; r < rounds; ++r) {
-        for (int s = 0; s < n_steps; ++s) {
-          const Step st = step_at(s);
-          const int nh_count = st.n / 128;
-          const int nkb = st.aux_first + st.kb_act + st.aux_last;
-          for (int slot = 0; slot < 2; ++slot) {
-            if (2 * r + slot >= my_tiles) continue;
-            mbar_wait(&act_ready[slot], act_phase[slot]);
-            act_phase[slot] ^= 1;
-            tc_fence_after();
-            const uint32_t act_addr = smem_u32(smem + SMEM_ACT + slot * ACT_BYTES);
-            const uint32_t aux_addr = smem_u32(smem + SMEM_AUX + slot * AUX_BYTES);
-            const uint32_t d_tmem = tmem_base + slot * 256;
-            for (int kbi = 0; kbi < nkb; ++kbi) {
-              const bool from_aux = (st.aux_first && kbi == 0) || (st.aux_last && kbi == nkb - 1);
-              const uint32_t a_addr = from_aux ? aux_addr : act_addr + (kbi - st.aux_first) * KB_BYTES;
-              const int ksteps = (st.aux_last && kbi == nkb - 1) ? 2 : 4;
-              if (!SIGMA_ONLY && nh_count == 2) {
-                // (full path; the sigma-only path keeps per-stage N=128 MMAs, whose finer pipelining measures faster)
-                // both 128-row halves of this K-block sit in adjacent ring stages (stage is even here): one N=256
-                // MMA per K-step reads the A tile once instead of twice (shared-memory operand bandwidth)
+      if (rank == 0) {
+        // ===================== MMA issuer (leader) =====================
+        constexpr uint32_t IDESC256 = make_idesc_bf16(256, 256, 0, 0);
+        constexpr uint32_t IDESC128 = make_idesc_bf16(256, 128, 0, 0);
+        uint32_t act_phase[2] = {0, 0};
+        int tl_n = 0;
+        for (long long r = 0; r < rounds; ++r) {
+          for (int s = 0; s < n_steps; ++s) {
+            const Step st = step_at(s);
+            const int nkb = st.aux_first + st.kb_act + st.aux_last;
+            const uint32_t idesc = st.n == 256 ? IDESC256 : IDESC128;
+            for (int slot = 0; slot < 2; ++slot) {
+              if (2 * r + slot >= pair_tiles) continue;
+              mbar_wait(&act_ready[slot], act_phase[slot]);
+              act_phase[slot] ^= 1;
+              tc_fence_after();
+              tl_mark(prm.tl, 2048, tl_n, 100 + 2 * s + slot);
+              const uint32_t act_addr = smem_u32(smem + SMEM_ACT + slot * ACT_BYTES);
+              const uint32_t aux_addr = smem_u32(smem + SMEM_AUX + slot * AUX_BYTES);
+              const uint32_t d_tmem = tmem_base + slot * 256;
+              for (int kbi = 0; kbi < nkb; ++kbi) {
+                const bool from_aux = (st.aux_first && kbi == 0) || (st.aux_last && kbi == nkb - 1);
+                const uint32_t a_addr = from_aux ? aux_addr : act_addr + (kbi - st.aux_first) * KB_BYTES;
+                const int ksteps = (st.aux_last && kbi == nkb - 1) ? 2 : 4;
                 mbar_wait(&w_full[stage], phase);
-                mbar_wait(&w_full[stage + 1], phase);
                 tc_fence_after();
                 const uint32_t b_addr = smem_u32(smem + SMEM_RING + stage * KB_BYTES);
                 for (int ks = 0; ks < ksteps; ++ks)
-                  umma_bf16(d_tmem, make_desc_kmajor_sw128(a_addr + ks * 32), make_desc_kmajor_sw128(b_addr + ks * 32),
-                            IDESC256, (kbi > 0 || ks > 0) ? 1u : 0u);
-                umma_commit(&w_empty[stage]);
-                umma_commit(&w_empty[stage + 1]);
-                stage += 2;
-                if (stage == N_STAGES) { stage = 0; phase ^= 1; }
-              } else {
-                for (int nh = 0; nh < nh_count; ++nh) {
-                  mbar_wait(&w_full[stage], phase);
-                  tc_fence_after();
-                  const uint32_t b_addr = smem_u32(smem + SMEM_RING + stage * KB_BYTES);
-                  for (int ks = 0; ks < ksteps; ++ks)
-                    umma_bf16(d_tmem + nh * 128, make_desc_kmajor_sw128(a_addr + ks * 32), make_desc_kmajor_sw128(b_addr + ks * 32),
-                              IDESC, (kbi > 0 || ks > 0) ? 1u : 0u);
-                  umma_commit(&w_empty[stage]);
-                  if (++stage == N_STAGES) { stage = 0; phase ^= 1; }
-                }
+                  umma_bf16_pair(d_tmem, make_desc_kmajor_sw128(a_addr + ks * 32), make_desc_kmajor_sw128(b_addr + ks * 32),
+                                 idesc, (kbi > 0 || ks > 0) ? 1u : 0u);
+                umma_commit_pair(&w_empty[stage]);
+                if (++stage == N_STAGES) { stage = 0; phase ^= 1; }
               }
+              umma_commit_pair(&acc_ready[slot]);
+              tl_mark(prm.tl, 2048, tl_n, 200 + 2 * s + slot);
             }
-            umma_commit(&acc_ready[slot]);
           }
         }
       }
@@ -282,46 +311,52 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_fwd_kernel(FwdParams prm) {
 #pragma unroll
     for (int q = 0; q < 8; ++q) c.off[q] = swz_offset(row, q);
     uint32_t acc_phase = 0;
+    int tl_n = 0;
+    unsigned long long* tl = (quarter == 0 && lane == 0) ? prm.tl : nullptr;
+    const int tl_base = slot * 1024;
     // bias row of step `s` -> smem (each thread 2 floats); consumed after the group barrier of that step
-    auto load_bias = [&](int s) {
-      reinterpret_cast<float2*>(bias_s)[gtid] = __ldg(reinterpret_cast<const float2*>(c.cst + C_BIAS + s * 256) + gtid);
-    };
+    // The bias row / head table of step s+1 are FETCHED (global -> registers) before step s is drained and only
+    // STORED to shared memory after the group barrier that ends the drain: the L2 latency of these loads is off
+    // the publish critical path.
+    auto bias_src = [&](int s) { return reinterpret_cast<const float2*>(c.cst + C_BIAS + s * 256) + gtid; };
+    auto load_bias = [&](int s) { reinterpret_cast<float2*>(bias_s)[gtid] = __ldg(bias_src(s)); };
     // small-head weight table of a head step -> the slot's encoding tile, which is idle during every head epilogue
     // (positional encoding is dead after L5, the view encoding after the view GEMM)
-    auto load_heads = [&](int s) {
+    auto heads_src = [&](int s) {
       const int off = s == 7 ? C_SR : s == 8 ? C_AF : s == 10 ? C_RAD : s == 11 ? C_ADD : C_ADD + 768;
-      const int n4 = SIGMA_ONLY ? 64 : (s == 7 ? 128 : s == 8 ? 128 : s == 12 ? 96 : 192);
-      const float4* src = reinterpret_cast<const float4*>(c.cst + off);
+      return reinterpret_cast<const float4*>(c.cst + off);
+    };
+    auto heads_n4 = [&](int s) { return SIGMA_ONLY ? 64 : (s == 7 ? 128 : s == 8 ? 128 : s == 12 ? 96 : 192); };
+    auto has_heads = [&](int s) { return s == 7 || (!SIGMA_ONLY && (s == 8 || s == 11 || s == 12)); };
+    auto load_heads = [&](int s) {
+      const float4* src = heads_src(s);
       float4* dst = reinterpret_cast<float4*>(aux);
-      for (int i = gtid; i < n4; i += 128) dst[i] = __ldg(src + i);
+      for (int i = gtid; i < heads_n4(s); i += 128) dst[i] = __ldg(src + i);
     };
     auto publish = [&]() {
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&act_ready[slot]);
+      if (lane == 0) mbar_arrive_cluster(&act_ready[slot], 0);     // the leader's barrier counts both CTAs' warps
     };
-    // STASH: after the group barrier a finished shared-memory tile is copied verbatim to the stash record by the
-    // group's 128 threads with fully coalesced 16-byte stores (the LSU path: bulk TMA stores of this size would
-    // queue in front of the weight producer's bulk loads on the SM's TMA unit and starve the MMA pipe)
+    // STASH: after the group barrier a finished shared-memory tile is copied verbatim to the stash record by ONE
+    // bulk (TMA) store with an evict-first L2 policy (the 1.5 MB weight image must stay L2-resident); the
+    // epilogue warps are the critical path of the CTA-pair pipeline and spend no issue slots on the copy.  The
+    // issuing thread waits for the store's shared-memory reads before the tile is overwritten (next drain).
     auto stash_tile = [&](const uint8_t* tile_smem, int blk, int nblk) {
       const uint4* src = reinterpret_cast<const uint4*>(tile_smem);
       uint4* dst = reinterpret_cast<uint4*>(c.rec + (size_t)blk * KB_BYTES);
-      if (g_dbg & 1) return;
-      if (g_dbg & 8) {       // experiment: one bulk (TMA) store with an evict-first L2 policy
-        if (gtid == 0) { bulk_s2g_hint(dst, src, (uint32_t)nblk * KB_BYTES, l2_policy_evict_first()); bulk_commit(); }
-        return;
-      }
-#pragma unroll 8
-      for (int i = gtid; i < nblk * (KB_BYTES / 16); i += 128) __stcs(dst + i, src[i]);   // streaming: keep the weight image in L2
+      if (c.rec == nullptr || (g_dbg & 1)) return;
+      if (gtid == 0) { bulk_s2g_hint(dst, src, (uint32_t)nblk * KB_BYTES, l2_policy_evict_first()); bulk_commit(); }
     };
-    for (long long k = slot; k < my_tiles; k += 2) {
+    for (long long k = slot; k < pair_tiles; k += 2) {
       const long long tile = blockIdx.x + k * gridDim.x;
+      const bool real = tile < prm.n_tiles;            // phantom tile: keep the pair in lock step, touch no memory
       const long long p = tile * TILE_M + row;
-      const bool valid = p < prm.gen.P;
+      const bool valid = real && p < prm.gen.P;
       float x[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 0.f};
       if (valid) gen_point(prm.gen, p, x, dir);
-      if (STASH) c.rec = prm.saved + (size_t)tile * SV_BYTES;
+      if (STASH) c.rec = real ? prm.saved + (size_t)tile * SV_BYTES : nullptr;
       load_bias(0);
       write_encoding<10, 8>(aux, row, x);
       if (STASH) { fence_proxy_async(); named_bar_sync(1 + slot, 128); }
@@ -343,8 +378,21 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_fwd_kernel(FwdParams prm) {
         mbar_wait(&acc_ready[slot], acc_phase);
         acc_phase ^= 1;
         tc_fence_after();
-        if (STASH && (g_dbg & 8) && gtid == 0) bulk_wait_read0();   // the previous tile image has left shared memory
+        tl_mark(tl, tl_base, tl_n, 10 + 2 * s);
+        if (STASH && gtid == 0) bulk_wait_read0();   // the previous tile image has left shared memory
         if (!SIGMA_ONLY && s == 10) { if (STASH) named_bar_sync(1 + slot, 128); load_heads(10); }   // view encoding consumed (and stashed): reuse its tile
+        // prefetch the next step's constants into registers (consumed after the drain)
+        float2 nb = make_float2(0.f, 0.f);
+        float4 nh0 = make_float4(0.f, 0.f, 0.f, 0.f), nh1 = nh0;
+        if (s + 1 < n_steps) {
+          nb = __ldg(bias_src(s + 1));
+          if (has_heads(s + 1)) {
+            const float4* src = heads_src(s + 1);
+            const int n4 = heads_n4(s + 1);
+            if (gtid < n4) nh0 = __ldg(src + gtid);
+            if (gtid + 128 < n4) nh1 = __ldg(src + gtid + 128);
+          }
+        }
         named_bar_sync(1 + slot, 128);       // bias row (+ head table) of this step are in smem
         switch (s) {
           case 7:
@@ -364,9 +412,14 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_fwd_kernel(FwdParams prm) {
         if (s + 1 < n_steps) {
           if (STASH) fence_proxy_async();
           named_bar_sync(1 + slot, 128);     // everyone is done reading this step's bias row / head table; tile complete
-          load_bias(s + 1);
-          if (s + 1 == 7 || (!SIGMA_ONLY && (s + 1 == 8 || s + 1 == 11 || s + 1 == 12))) load_heads(s + 1);
+          reinterpret_cast<float2*>(bias_s)[gtid] = nb;
+          if (has_heads(s + 1)) {
+            const int n4 = heads_n4(s + 1);
+            if (gtid < n4) reinterpret_cast<float4*>(aux)[gtid] = nh0;
+            if (gtid + 128 < n4) reinterpret_cast<float4*>(aux)[gtid + 128] = nh1;
+          }
           publish();
+          tl_mark(tl, tl_base, tl_n, 11 + 2 * s);
           if (STASH) {   // copy the finished tile out while the next GEMM reads it (both only read)
             if (s <= 7) stash_tile(c.act, SV_H(s), 4);
             else if (s == 9) { stash_tile(c.act, SV_FEAT, 4); stash_tile(aux, SV_DE, 1); }
@@ -398,7 +451,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_fwd_kernel(FwdParams prm) {
           for (int j = 0; j < 9; ++j) dst[j] = make_float2(r[2 * j], r[2 * j + 1]);
         }
       }
-      if (STASH && (g_dbg & 8) && gtid == 0) bulk_wait_read0();
+      if (STASH && gtid == 0) bulk_wait_read0();
       named_bar_sync(1 + slot, 128);         // last step's bias row no longer needed (next tile overwrites it)
       tc_fence_before();   // order this tile's TMEM reads before the next tile's act_ready arrival
     }
@@ -406,7 +459,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) mlp_fwd_kernel(FwdParams prm) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) { __syncwarp(); tmem_dealloc(tmem_base, 512); }
+  cluster_sync_all();      // the peer may still be reading my shared memory / arriving on my barriers
+  if (warp == 1) { __syncwarp(); tmem_dealloc_pair(tmem_base, 512); }
 }
 
 // ---------------------------------------------------------------- tcgen05 self-test
@@ -473,13 +527,73 @@ umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, f
   if (warp == 0) { __syncwarp(); tmem_dealloc(tmem_base, 256); }
 }
 
+// ---------------------------------------------------------------- cta_group::2 self-test
+// D[256,256] = A[256,K] * B[256,K]^T on a CTA pair: CTA r stages rows 128r.. of A and of B, the leader issues
+// the M=256 MMAs, each CTA drains its 128 rows of D.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+umma_pair_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D, int K) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int nkb = K / 64;
+  const uint32_t rank = cluster_ctarank();
+  uint8_t* sA = smem;                                 // nkb x [128][64]
+  uint8_t* sB = smem + (size_t)nkb * KB_BYTES;        // nkb x [128][64]
+  uint64_t* bar_done = reinterpret_cast<uint64_t*>(sB + (size_t)nkb * KB_BYTES);
+  uint64_t* bar_peer = bar_done + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar_done + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) { mbar_init(bar_done, 1); mbar_init(bar_peer, 1); fence_barrier_init(); }
+  __syncwarp();
+  if (warp == 0) tmem_alloc_pair(tmem_ptr, 256);
+  for (int e = threadIdx.x; e < 128 * (K / 8); e += blockDim.x) {
+    int row = e / (K / 8), cg = e % (K / 8);
+    int kb = cg / 8, c16 = cg % 8;
+    const float* sa = A + (size_t)(rank * 128 + row) * K + cg * 8;
+    const float* sb = B + (size_t)(rank * 128 + row) * K + cg * 8;
+    *reinterpret_cast<uint4*>(sA + (size_t)kb * KB_BYTES + swz_offset(row, c16)) =
+        make_uint4(pack_bf16x2(sa[0], sa[1]), pack_bf16x2(sa[2], sa[3]), pack_bf16x2(sa[4], sa[5]), pack_bf16x2(sa[6], sa[7]));
+    *reinterpret_cast<uint4*>(sB + (size_t)kb * KB_BYTES + swz_offset(row, c16)) =
+        make_uint4(pack_bf16x2(sb[0], sb[1]), pack_bf16x2(sb[2], sb[3]), pack_bf16x2(sb[4], sb[5]), pack_bf16x2(sb[6], sb[7]));
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();            // barriers initialised and TMEM allocated in both CTAs
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  if (rank == 1 && threadIdx.x == 0) mbar_arrive_cluster(bar_peer, 0);     // my operand halves are staged
+  if (rank == 0 && warp == 1 && elect_one()) {
+    mbar_wait(bar_peer, 0);
+    tc_fence_after();
+    const uint32_t idesc = make_idesc_bf16(256, 256, 0, 0);
+    for (int kb = 0; kb < nkb; ++kb)
+      for (int ks = 0; ks < 4; ++ks)
+        umma_bf16_pair(tmem_base, make_desc_kmajor_sw128(smem_u32(sA + (size_t)kb * KB_BYTES) + ks * 32),
+                       make_desc_kmajor_sw128(smem_u32(sB + (size_t)kb * KB_BYTES) + ks * 32), idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+    umma_commit_pair(bar_done);
+  }
+  mbar_wait(bar_done, 0);
+  tc_fence_after();
+  const int row = (warp & 3) * 32 + lane;
+  for (int cc = 0; cc < 8; ++cc) {
+    uint32_t v[32];
+    tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + cc * 32, v);
+    tmem_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) D[(size_t)(rank * 128 + row) * 256 + cc * 32 + j] = __uint_as_float(v[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 0) { __syncwarp(); tmem_dealloc_pair(tmem_base, 256); }
+}
+
 }  // namespace mlp
 }  // namespace ibln
 
 using namespace ibln;
 using namespace ibln::mlp;
 
-namespace ibln { namespace mlp { int g_dbg_host = 0; void* g_timeline = nullptr; } }
 extern "C" int ibln_debug_timeline(void* device_buf) { ibln::mlp::g_timeline = device_buf; return 0; }
 extern "C" int ibln_debug_set(int flags) { ibln::mlp::g_dbg_host = flags; return (int)cudaMemcpyToSymbol(ibln::mlp::g_dbg, &flags, sizeof(int)); }
 
@@ -519,7 +633,10 @@ extern "C" int ibln_mlp_fwd(const void* packed, int mode, const float* pts, cons
   prm.out = out;
   prm.saved = (uint8_t*)saved;
   prm.n_tiles = (prm.gen.P + TILE_M - 1) / TILE_M;
-  long long grid = prm.n_tiles < (long long)num_sms(device) ? prm.n_tiles : (long long)num_sms(device);
+  prm.tl = (unsigned long long*)g_timeline;
+  { int rc = make_chunk_stream_map(&prm.wmap, packed, N_CHUNKS); if (rc != 0) return rc; }
+  long long grid = (long long)(num_sms(device) & ~1);            // CTA pairs
+  if (((prm.n_tiles + 1) & ~1LL) < grid) grid = (prm.n_tiles + 1) & ~1LL;
   auto launch = [&](auto kern) -> int {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_REQUEST);
     if (e != cudaSuccess) return (int)e;
@@ -529,6 +646,15 @@ extern "C" int ibln_mlp_fwd(const void* packed, int mode, const float* pts, cons
   if (sigma_only) return launch(mlp_fwd_kernel<true, false>);
   if (saved) return launch(mlp_fwd_kernel<false, true>);
   return launch(mlp_fwd_kernel<false, false>);
+}
+
+extern "C" int ibln_umma_pair_selftest(const float* a, const float* b, float* d, int k, int device, void* stream) {
+  if (!a || !b || !d || k < 64 || k % 64 != 0 || k > 256) return IBLN_EINVAL;
+  DeviceGuard g(device);
+  int smem = 2 * (k / 64) * KB_BYTES + 64 + 1024;
+  IBLN_CUDA(cudaFuncSetAttribute(umma_pair_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  umma_pair_selftest_kernel<<<2, 128, smem, (cudaStream_t)stream>>>(a, b, d, k);
+  IBLN_RETURN_LAST();
 }
 
 extern "C" int ibln_umma_selftest(const float* a, const float* b, float* d, int n, int k, int variant, int device, void* stream) {

@@ -176,6 +176,16 @@ static __global__ void pack_consts_kernel(PackArgs a, float* __restrict__ cst) {
 // defined in mlp_tc_bwd.cu: packs the transposed (dgrad) weight chunk stream at packed + PACKED_BWD_OFF
 int launch_pack_bwd(const PackArgs& a, uint8_t* packed, cudaStream_t stream);
 
+// diagnostics: blocks 0/1 append (tag << 48 | clock64) to a timeline buffer (ibln_debug_timeline)
+__device__ __forceinline__ void tl_mark(unsigned long long* tl, int base, int& n, int tag) {
+  if (tl != nullptr && blockIdx.x < 2 && n < 1000)
+    tl[blockIdx.x * 4096 + base + n++] = ((unsigned long long)tag << 48) | ((unsigned long long)clock64() & 0xFFFFFFFFFFFFull);
+}
+
+// Tensor map over a packed chunk stream: rows of 64 bf16 (128 B), box = 64 rows (8 KB, no swizzle: the image is
+// pre-swizzled).  Host side; returns 0 or an error code.
+int make_chunk_stream_map(CUtensorMap* map, const void* base, int n_chunks);
+
 // ---------------------------------------------------------------- point generation + encodings
 struct PointGen {
   const float* pts; const float* o; const float* d; const float* z;

@@ -93,6 +93,7 @@ constexpr int FLAT_TOTAL = 798994;
 
 // ---------------------------------------------------------------- dgrad kernel
 struct DgradParams {
+  CUtensorMap wmap;          // transposed (dgrad) chunk stream as a 2-D tensor
   const uint8_t* packed;
   const uint8_t* saved;      // forward stash (masks)
   const float* g_out;        // [P,18]
@@ -103,10 +104,6 @@ struct DgradParams {
   int dbg;
   unsigned long long* tl;    // optional timeline buffer (diagnostics): block 0 appends (tag << 48 | clock64)
 };
-
-__device__ __forceinline__ void tl_mark(unsigned long long* tl, int base, int& n, int tag) {
-  if (tl != nullptr && blockIdx.x == 0 && n < 1000) tl[base + n++] = ((unsigned long long)tag << 48) | ((unsigned long long)clock64() & 0xFFFFFFFFFFFFull);
-}
 
 // v[0..31] += a * row[0..31] as 16 packed fp32x2 FMAs
 __device__ __forceinline__ void axpy32(float (&v)[32], float a, const float* row) {
@@ -125,13 +122,9 @@ __device__ __forceinline__ void store_tile4(uint8_t* tile, int kb, uint32_t swz,
   *reinterpret_cast<uint4*>(tile + (size_t)kb * KB_BYTES + swz) = pk;
 }
 
-// 18 warps: producer, MMA issuer, and 8 epilogue warps per tile slot.  Two warps share each TMEM lane quarter
-// (a warp may only touch lanes 32*(warp%4)..) and split the 256 accumulator columns in halves; the epilogue
-// is latency-bound (TMEM load -> select -> pack -> st.shared chains), so 4 warps per scheduler instead of 2
-// nearly halve it.
-constexpr int DG_EPI_THREADS = 256;              // per slot
-constexpr int DG_THREADS = 64 + 2 * DG_EPI_THREADS;
-__global__ void __launch_bounds__(DG_THREADS, 1) mlp_dgrad_kernel(DgradParams prm) {
+// CTA pair like the forward kernel (see mlp_tc.cu): M=256 cta_group::2 MMAs over the two CTAs' tiles, each CTA
+// streams half of the transposed weight rows, the leader issues, commits are multicast.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) mlp_dgrad_kernel(const __grid_constant__ DgradParams prm) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_BAR);
@@ -141,52 +134,55 @@ __global__ void __launch_bounds__(DG_THREADS, 1) mlp_dgrad_kernel(DgradParams pr
   uint64_t* acc_ready = bars + 2 * N_STAGES + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * N_STAGES + 4);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long my_tiles = (prm.n_tiles > (long long)blockIdx.x) ? (prm.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const uint32_t rank = cluster_ctarank();
+  const long long lead = (long long)(blockIdx.x & ~1u);
+  const long long pair_tiles = (prm.n_tiles > lead) ? (prm.n_tiles - lead + gridDim.x - 1) / gridDim.x : 0;
+  const long long rounds = (pair_tiles + 1) / 2;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < N_STAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&act_ready[i], DG_EPI_THREADS / 32); mbar_init(&acc_ready[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&act_ready[i], 8); mbar_init(&acc_ready[i], 1); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_ptr, 512);
+  if (warp == 1) tmem_alloc_pair(tmem_ptr, 512);
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  const uint8_t* chunks = prm.packed + PACKED_BWD_OFF;
 
   if (warp == 0) {
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      long long rounds = (my_tiles + 1) / 2;
       for (long long r = 0; r < rounds; ++r)
         for (int t = 0; t < N_STEPS_BWD; ++t) {
           const BStep st = bstep_at(t);
           for (int slot = 0; slot < 2; ++slot) {
-            if (2 * r + slot >= my_tiles) continue;
-            for (int c = 0; c < st.nkb * 2; ++c) {
+            if (2 * r + slot >= pair_tiles) continue;
+            for (int kbi = 0; kbi < st.nkb; ++kbi) {
+              const int row0 = (st.chunk_base + 2 * kbi + (int)rank) * 128;     // my 128 of the 256 output rows
               mbar_wait(&w_empty[stage], phase ^ 1);
-              mbar_arrive_expect_tx(&w_full[stage], KB_BYTES);
-              bulk_g2s(smem + SMEM_RING + stage * KB_BYTES, chunks + (size_t)(st.chunk_base + c) * KB_BYTES, KB_BYTES, &w_full[stage]);
+              if (rank == 0) mbar_arrive_expect_tx(&w_full[stage], 2u * KB_BYTES);   // both CTAs' halves
+              for (int h = 0; h < 2; ++h)
+                tma_load_2d_pair(smem + SMEM_RING + stage * KB_BYTES + h * (KB_BYTES / 2), &prm.wmap, 0, row0 + 64 * h, &w_full[stage]);
               if (++stage == N_STAGES) { stage = 0; phase ^= 1; }
             }
           }
         }
     }
   } else if (warp == 1) {
-    if (elect_one()) {
-      constexpr uint32_t IDESC256 = make_idesc_bf16(128, 256, 0, 0);
+    if (rank == 0 && elect_one()) {
+      constexpr uint32_t IDESC256 = make_idesc_bf16(256, 256, 0, 0);
       int stage = 0;
       int tl_n = 0;
       uint32_t phase = 0;
       uint32_t act_phase[2] = {0, 0};
-      long long rounds = (my_tiles + 1) / 2;
       for (long long r = 0; r < rounds; ++r)
         for (int t = 0; t < N_STEPS_BWD; ++t) {
           const BStep st = bstep_at(t);
           for (int slot = 0; slot < 2; ++slot) {
-            if (2 * r + slot >= my_tiles) continue;
+            if (2 * r + slot >= pair_tiles) continue;
             mbar_wait(&act_ready[slot], act_phase[slot]);
             act_phase[slot] ^= 1;
             tc_fence_after();
@@ -194,60 +190,56 @@ __global__ void __launch_bounds__(DG_THREADS, 1) mlp_dgrad_kernel(DgradParams pr
             const uint32_t act_addr = smem_u32(smem + SMEM_ACT + slot * ACT_BYTES);
             const uint32_t d_tmem = tmem_base + slot * 256;
             for (int kbi = 0; kbi < st.nkb; ++kbi) {
-              // the two 128-row halves of a K-block are in adjacent ring stages: one N=256 MMA per K-step
               mbar_wait(&w_full[stage], phase);
-              mbar_wait(&w_full[stage + 1], phase);
               tc_fence_after();
               const uint32_t b_addr = smem_u32(smem + SMEM_RING + stage * KB_BYTES);
               for (int ks = 0; ks < 4; ++ks)
-                umma_bf16(d_tmem, make_desc_kmajor_sw128(act_addr + kbi * KB_BYTES + ks * 32),
-                          make_desc_kmajor_sw128(b_addr + ks * 32), IDESC256, (st.accumulate || kbi > 0 || ks > 0) ? 1u : 0u);
-              umma_commit(&w_empty[stage]);
-              umma_commit(&w_empty[stage + 1]);
-              stage += 2;
-              if (stage == N_STAGES) { stage = 0; phase ^= 1; }
+                umma_bf16_pair(d_tmem, make_desc_kmajor_sw128(act_addr + kbi * KB_BYTES + ks * 32),
+                               make_desc_kmajor_sw128(b_addr + ks * 32), IDESC256, (st.accumulate || kbi > 0 || ks > 0) ? 1u : 0u);
+              umma_commit_pair(&w_empty[stage]);
+              if (++stage == N_STAGES) { stage = 0; phase ^= 1; }
             }
-            umma_commit(&acc_ready[slot]);
+            umma_commit_pair(&acc_ready[slot]);
             tl_mark(prm.tl, 2048, tl_n, 200 + t * 2 + slot);
           }
         }
     }
   } else {
-    const int slot = (warp - 2) >> 3;
-    const int quarter = warp & 3;                   // TMEM lane quarter this warp may access
-    const int half = ((warp - 2) >> 2) & 1;         // column half (chunks 4*half .. 4*half+3) of the 256-wide tiles
+    const int slot = (warp - 2) >> 2;
+    const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     uint8_t* act = smem + SMEM_ACT + slot * ACT_BYTES;
     const float* cst = reinterpret_cast<const float*>(prm.packed + PACKED_CONST_OFF);
     const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + slot * 256;
     const FlatOff fo = flat_offsets();
     uint32_t acc_phase = 0;
-    int tl_n = 0;
-    unsigned long long* tl = (quarter == 0 && half == 0 && lane == 0) ? prm.tl : nullptr;
-    const int tl_base = slot * 1024;
     // small-head weight tables -> the slot's (otherwise unused) encoding tile, once per kernel:
     // channel-major rows: [coarse radiance k: 3x128 each, 1152][albedo 3x128 | irradiance 128: 512][radiance 3x256: 768][sigma, rough: 512]
     const float* tab = reinterpret_cast<const float*>(smem + SMEM_AUX + slot * AUX_BYTES);
     const float* T_ADD = tab; const float* T_AF = tab + 1152; const float* T_RAD = tab + 1664; const float* T_SR = tab + 2432;
-    const int gtid = threadIdx.x - 64 - slot * DG_EPI_THREADS;
+    const int gtid = threadIdx.x - 64 - slot * 128;
     {
       float4* dst = reinterpret_cast<float4*>(smem + SMEM_AUX + slot * AUX_BYTES);
-      for (int i = gtid; i < 736; i += DG_EPI_THREADS) {
+      for (int i = gtid; i < 736; i += 128) {
         const float* src = i < 288 ? cst + C_ADD + 4 * i : i < 416 ? cst + C_AF + 4 * (i - 288)
                          : i < 608 ? cst + C_RAD + 4 * (i - 416) : cst + C_SR + 4 * (i - 608);
         dst[i] = __ldg(reinterpret_cast<const float4*>(src));
       }
-      named_bar_sync(1 + slot, DG_EPI_THREADS);
+      named_bar_sync(1 + slot, 128);
     }
     uint32_t off[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) off[q] = swz_offset(row, q);
-    for (long long k = slot; k < my_tiles; k += 2) {
+    int tl_n = 0;
+    unsigned long long* tl = (quarter == 0 && lane == 0) ? prm.tl : nullptr;
+    const int tl_base = slot * 1024;
+    for (long long k = slot; k < pair_tiles; k += 2) {
       const long long tile = blockIdx.x + k * gridDim.x;
+      const bool real = tile < prm.n_tiles;      // phantom tile (second CTA of the last pair round): no memory traffic
       const long long p = tile * TILE_M + row;
-      const bool valid = p < prm.P;
-      uint8_t* dy = prm.dy + (size_t)tile * DY_BYTES;
-      const uint8_t* rec = prm.saved + (size_t)tile * SV_BYTES;
+      const bool valid = real && p < prm.P;
+      uint8_t* dy = prm.dy + (size_t)(real ? tile : 0) * DY_BYTES;
+      const uint8_t* rec = prm.saved + (size_t)(real ? tile : 0) * SV_BYTES;
       const uint32_t* masks = reinterpret_cast<const uint32_t*>(rec + (size_t)SV_MASK * KB_BYTES) + row * 8;   // + m * 1024 words
       float g[18];
 #pragma unroll
@@ -256,7 +248,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) mlp_dgrad_kernel(DgradParams pr
         g[2 * j] = v.x; g[2 * j + 1] = v.y;
       }
       // ---- head-bias gradients: column sums of g over the warp's 32 rows
-      if (half == 0) {
+      if (real) {
         float s[18];
 #pragma unroll
         for (int j = 0; j < 18; ++j) s[j] = warp_sum(g[j]);
@@ -275,7 +267,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) mlp_dgrad_kernel(DgradParams pr
         }
       }
       // ---- G tile: g_raw as bf16 [128][64] (columns 18.. zero) for the small-head wgrads
-      if (half == 0) {
+      if (real) {
         float e[64];
 #pragma unroll
         for (int j = 0; j < 64; ++j) e[j] = j < 18 ? g[j] : 0.f;
@@ -287,25 +279,13 @@ __global__ void __launch_bounds__(DG_THREADS, 1) mlp_dgrad_kernel(DgradParams pr
       }
       // ---- phase writers for the CUDA-core produced gradient tiles
       // heads: 0 = coarse radiance 0|1 (256 cols), 1 = coarse radiance 2 (128 cols), 2 = albedo|irradiance features
-      // Copy-out of a finished K-block: every warp streams its OWN 32 rows (4 KB, contiguous in the operand layout)
-      // to the dY record with coalesced 16-byte stores right after writing them.  No cross-warp hazard (so no
-      // group barrier), and the stores are spread over the drain instead of bursting on the SM's L2 request
-      // port while the weight producer needs it.
-      auto copy_rows = [&](int rec_blk, int kb) {
-        __syncwarp();
-        const uint4* src = reinterpret_cast<const uint4*>(act + (size_t)kb * KB_BYTES + quarter * 4096);
-        uint4* dst = reinterpret_cast<uint4*>(dy + (size_t)rec_blk * KB_BYTES + quarter * 4096);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) __stcs(dst + lane + 32 * i, src[lane + 32 * i]);
-      };
       auto write_head_tile = [&](int which) {
         const int ncc = which == 1 ? 4 : 8;
         const int mslot = which == 0 ? 10 : which == 1 ? 11 : 8;
-        const int dblk = which == 0 ? DY_ADDF01 : which == 1 ? DY_ADDF2 : DY_AF;
-        const int cc0 = half * (ncc >> 1), w0 = cc0 & ~3;     // this warp's chunks and the 4-word mask group holding them
-        const uint4 mwv = __ldg(reinterpret_cast<const uint4*>(masks + mslot * 1024 + w0));
-        const uint32_t mw[4] = {mwv.x, mwv.y, mwv.z, mwv.w};
-        for (int cc = cc0; cc < cc0 + (ncc >> 1); ++cc) {
+        uint4 mw0 = __ldg(reinterpret_cast<const uint4*>(masks + mslot * 1024));
+        uint4 mw1 = __ldg(reinterpret_cast<const uint4*>(masks + mslot * 1024) + 1);
+        const uint32_t mw[8] = {mw0.x, mw0.y, mw0.z, mw0.w, mw1.x, mw1.y, mw1.z, mw1.w};
+        for (int cc = 0; cc < ncc; ++cc) {
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = 0.f;
@@ -321,7 +301,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) mlp_dgrad_kernel(DgradParams pr
 #pragma unroll
             for (int q = 0; q < 3; ++q) axpy32(v, g[9 + 3 * head + q], T_ADD + head * 384 + q * 128 + (cc & 3) * 32);
           }
-          const uint32_t m = mw[cc - w0];
+          const uint32_t m = mw[cc];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = ((m >> j) & 1u) ? v[j] : 0.f;
 #pragma unroll
@@ -329,39 +309,53 @@ __global__ void __launch_bounds__(DG_THREADS, 1) mlp_dgrad_kernel(DgradParams pr
             store_tile4(act, cc >> 1, off[(cc & 1) * 4 + q],
                         make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
                                    pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7])));
-          if (cc & 1) copy_rows(dblk + (cc >> 1), cc >> 1);
         }
       };
-      // finished gradient tile in `act`: hand it to the MMA issuer (one arrival per warp)
-      auto publish = [&](bool arrive) {
-        if (!arrive) return;
+      // finished gradient tile in `act`: hand it to the MMA issuer (one arrival per warp on the LEADER's barrier) and
+      // copy it verbatim to the dY record with one bulk (TMA) store (evict-first: the weight image stays in L2)
+      auto publish = [&](int dblk, int nblk, bool arrive) {
         fence_proxy_async();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&act_ready[slot]);
+        named_bar_sync(1 + slot, 128);
+        if (arrive) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(&act_ready[slot], 0);
+        }
+        if (real && gtid == 0) {
+          bulk_s2g_hint(dy + (size_t)dblk * KB_BYTES, act, (uint32_t)nblk * KB_BYTES, l2_policy_evict_first());
+          bulk_commit();
+        }
       };
+      // before overwriting `act`: the bulk store of the previous tile has finished reading it
+      auto pre_write = [&]() {
+        if (gtid == 0) bulk_wait_read0();
+        named_bar_sync(1 + slot, 128);
+      };
+      pre_write();
       tl_mark(tl, tl_base, tl_n, 1);
       write_head_tile(0);
-      publish(true);
+      publish(DY_ADDF01, 4, true);
       tl_mark(tl, tl_base, tl_n, 2);
       for (int t = 0; t < N_STEPS_BWD; ++t) {
         mbar_wait(&acc_ready[slot], acc_phase);
         acc_phase ^= 1;
         tc_fence_after();
         tl_mark(tl, tl_base, tl_n, 10 + 2 * t);
-        if (t == 0) { write_head_tile(1); publish(true); tl_mark(tl, tl_base, tl_n, 11 + 2 * t); continue; }
-        if (t == 3) { write_head_tile(2); publish(true); tl_mark(tl, tl_base, tl_n, 11 + 2 * t); continue; }
+        pre_write();
+        if (t == 0) { write_head_tile(1); publish(DY_ADDF2, 2, true); tl_mark(tl, tl_base, tl_n, 11 + 2 * t); continue; }
+        if (t == 3) { write_head_tile(2); publish(DY_AF, 4, true); tl_mark(tl, tl_base, tl_n, 11 + 2 * t); continue; }
         // drain: t=1 -> dY_view (mask HV, + radiance term); t=2 -> dY_feat (no mask); t=4 -> dY_7 (+ sigma/rough terms);
         // t>=5 -> dY_{11-t} (mask h_{11-t})
         const int mslot = t == 1 ? 9 : t == 2 ? -1 : t == 4 ? 7 : 11 - t;
         const int dblk = t == 1 ? DY_VIEW : t == 2 ? DY_FEAT : t == 4 ? DY_H(7) : DY_H(11 - t);
-        uint32_t mw[4];
+        uint32_t mw[8];
         if (mslot >= 0) {
-          const uint4 mwv = __ldg(reinterpret_cast<const uint4*>(masks + mslot * 1024 + half * 4));
-          mw[0] = mwv.x; mw[1] = mwv.y; mw[2] = mwv.z; mw[3] = mwv.w;
+          uint4 mw0 = __ldg(reinterpret_cast<const uint4*>(masks + mslot * 1024));
+          uint4 mw1 = __ldg(reinterpret_cast<const uint4*>(masks + mslot * 1024) + 1);
+          mw[0] = mw0.x; mw[1] = mw0.y; mw[2] = mw0.z; mw[3] = mw0.w; mw[4] = mw1.x; mw[5] = mw1.y; mw[6] = mw1.z; mw[7] = mw1.w;
         } else {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) mw[i] = 0xffffffffu;
+          for (int i = 0; i < 8; ++i) mw[i] = 0xffffffffu;
         }
         const bool last = (t == N_STEPS_BWD - 1);
         auto chunk = [&](const uint32_t (&raw)[32], int cc) {
@@ -375,7 +369,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) mlp_dgrad_kernel(DgradParams pr
             axpy32(v, g[0], T_SR + cc * 32);
             axpy32(v, g[4], T_SR + 256 + cc * 32);
           }
-          const uint32_t m = mw[cc & 3];
+          const uint32_t m = mw[cc];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = ((m >> j) & 1u) ? v[j] : 0.f;
 #pragma unroll
@@ -383,29 +377,29 @@ __global__ void __launch_bounds__(DG_THREADS, 1) mlp_dgrad_kernel(DgradParams pr
             store_tile4(act, cc >> 1, off[(cc & 1) * 4 + q],
                         make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
                                    pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7])));
-          if (cc & 1) copy_rows(dblk + (cc >> 1), cc >> 1);
         };
         uint32_t ra[32], rb[32];
-        const int c0 = half * 4;
-        tmem_ld32(t_lane + c0 * 32, ra);
+        tmem_ld32(t_lane, ra);
 #pragma unroll
-        for (int i = 0; i < 4; i += 2) {
+        for (int cc = 0; cc < 8; cc += 2) {
           tmem_wait_ld();
-          tmem_ld32(t_lane + (c0 + i + 1) * 32, rb);
-          chunk(ra, c0 + i);
+          tmem_ld32(t_lane + (cc + 1) * 32, rb);
+          chunk(ra, cc);
           tmem_wait_ld();
-          if (i + 2 < 4) tmem_ld32(t_lane + (c0 + i + 2) * 32, ra);
-          chunk(rb, c0 + i + 1);
+          if (cc + 2 < 8) tmem_ld32(t_lane + (cc + 2) * 32, ra);
+          chunk(rb, cc + 1);
         }
-        publish(!last);
+        publish(dblk, 4, !last);
         tl_mark(tl, tl_base, tl_n, 11 + 2 * t);
       }
       tc_fence_before();
     }
+    if (gtid == 0) bulk_wait0();
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) { __syncwarp(); tmem_dealloc(tmem_base, 512); }
+  cluster_sync_all();
+  if (warp == 1) { __syncwarp(); tmem_dealloc_pair(tmem_base, 512); }
 }
 
 // ---------------------------------------------------------------- wgrad kernel
@@ -713,8 +707,10 @@ extern "C" int ibln_mlp_bwd(const void* packed, const void* saved, const float* 
   dp.flat_grad = flat_grad; dp.P = n_pts; dp.n_tiles = n_tiles; dp.dbg = g_dbg_host; dp.tl = (unsigned long long*)g_timeline;
   IBLN_CUDA(cudaFuncSetAttribute(mlp_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_REQUEST));
   const int sms = num_sms(device);
-  long long grid = n_tiles < (long long)sms ? n_tiles : (long long)sms;
-  if (!(g_dbg_host & 16)) mlp_dgrad_kernel<<<(unsigned)grid, DG_THREADS, SMEM_REQUEST, stream>>>(dp);
+  long long grid = (long long)(sms & ~1);                      // CTA pairs
+  if (((n_tiles + 1) & ~1LL) < grid) grid = (n_tiles + 1) & ~1LL;
+  { int rc = make_chunk_stream_map(&dp.wmap, (const uint8_t*)packed + PACKED_BWD_OFF, N_CHUNKS_BWD); if (rc != 0) return rc; }
+  if (!(g_dbg_host & 16)) mlp_dgrad_kernel<<<(unsigned)grid, N_THREADS, SMEM_REQUEST, stream>>>(dp);
   IBLN_CUDA(cudaGetLastError());
   if (g_dbg_host & 32) return 0;
   // ---- all weight-gradient GEMMs in one persistent launch

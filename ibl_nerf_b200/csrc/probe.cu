@@ -47,3 +47,46 @@ extern "C" int ibln_store_probe(void* out, int64_t total_bytes, int mode, int ct
   store_probe_kernel<<<ctas, 256, 65536, (cudaStream_t)stream>>>((uint8_t*)out, per, mode);
   IBLN_RETURN_LAST();
 }
+
+// TMEM read-bandwidth probe: `warps` warps (warp w -> lane quarter w % 4) each issue `iters` tcgen05.ld
+// 32x32b.x32 (4 KB per warp-instruction); out[0] = elapsed clocks of warp 0, out[1] = checksum.
+namespace ibln {
+__global__ void __launch_bounds__(512, 1) tmem_probe_kernel(long long* __restrict__ out, int iters, int depth) {
+  __shared__ uint32_t tmem_ptr;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) tmem_alloc(&tmem_ptr, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t base = tmem_ptr + ((uint32_t)((warp & 3) * 32) << 16);
+  uint32_t acc = 0;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int i = 0; i < iters; ++i) {
+    uint32_t v[32], w[32];
+    tmem_ld32(base + ((i * 2) & 15) * 32, v);
+    if (depth > 1) tmem_ld32(base + ((i * 2 + 1) & 15) * 32, w);
+    tmem_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc ^= v[j];
+    if (depth > 1) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc ^= w[j];
+    }
+  }
+  const long long t1 = clock64();
+  if (threadIdx.x == 0) { out[0] = t1 - t0; }
+  if (acc == 0x12345678u) out[1] = acc;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { __syncwarp(); tmem_dealloc(tmem_ptr, 512); }
+}
+}  // namespace ibln
+
+extern "C" int ibln_tmem_probe(long long* out, int warps, int iters, int depth, int device, void* stream) {
+  using namespace ibln;
+  if (!out || warps < 1 || warps > 16) return IBLN_EINVAL;
+  DeviceGuard g(device);
+  tmem_probe_kernel<<<1, warps * 32, 0, (cudaStream_t)stream>>>(out, iters, depth);
+  IBLN_RETURN_LAST();
+}

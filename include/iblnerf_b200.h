@@ -199,6 +199,8 @@ int ibln_umma_selftest(const float* a, const float* b, float* d, int n, int k, i
 /* Self-test of the MN-major operand path used by the wgrad kernel: D[128,N] = X^T Y with X [128 points,128],
  * Y [128 points,N] (N in {64,128,192,256}) staged as swizzled operand tiles and read as MN-major. */
 int ibln_umma_mn_selftest(const float* x, const float* y, float* d, int n, int device, void* stream);
+/* cta_group::2 operand/commit self-test: D[256,256] = A[256,K] * B[256,K]^T on one CTA pair (K in {64..256}). */
+int ibln_umma_pair_selftest(const float* a, const float* b, float* d, int k, int device, void* stream);
 
 /* Diagnostics: write `total_bytes` to `out` from `ctas` CTAs (mode 0/1: bulk TMA stores from shared memory,
  * 1 / 4 in flight; mode 2: coalesced st.global.v4) -- used to measure the achievable stash write bandwidth. */

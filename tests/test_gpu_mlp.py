@@ -67,6 +67,18 @@ def test_umma_selftest(n, k):
     close(d, want, rtol=1e-3, atol=1e-3, name="umma")
 
 
+@pytest.mark.parametrize("k", [64, 256])
+def test_umma_pair_selftest(k):
+    """cta_group::2: one M=256 N=256 MMA chain across a CTA pair (cluster of 2), each CTA owning half of A, B and D."""
+    gen = torch.Generator().manual_seed(7 + k)
+    a = torch.randn(256, k, generator=gen).to(DEV)
+    b = torch.randn(256, k, generator=gen).to(DEV)
+    d = torch.zeros(256, 256, device=DEV)
+    call("ibln_umma_pair_selftest", a.device, ptr(a), ptr(b), ptr(d), k)
+    want = a.bfloat16().float() @ b.bfloat16().float().t()
+    close(d, want, rtol=1e-3, atol=1e-3, name="umma pair")
+
+
 def bf16_oracle(net, pts, viewdirs):
     """Oracle MLP with the kernel's rounding points: bf16 weights + bf16 hidden activations, fp32 accumulate,
     fp32 small heads on un-rounded features."""
