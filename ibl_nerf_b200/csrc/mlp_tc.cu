@@ -45,7 +45,6 @@ int make_chunk_stream_map(CUtensorMap* map, const void* base, int n_chunks) {
 }
 
 // ---------------------------------------------------------------- the fused forward kernel
-__device__ int g_dbg = 0;   // diagnostics: bit0 skip tile copies, bit1 skip AF/ADD direct stores, bit2 skip mask stores
 struct FwdParams {
   CUtensorMap wmap;          // forward chunk stream as a 2-D tensor (rows of 64 bf16)
   const uint8_t* packed;     // chunk stream + const section
@@ -128,7 +127,7 @@ __device__ __forceinline__ void process_chunk(const EpiCtx& c, Heads& hd, const 
                         pack_bf16x2(h[8 * q + 4], h[8 * q + 5]), pack_bf16x2(h[8 * q + 6], h[8 * q + 7]));
       const uint32_t o = c.off[(cc & 1) * 4 + q];
       if (kWriteAct) *reinterpret_cast<uint4*>(c.act + kb * KB_BYTES + o) = pk;
-      else if (c.rec != nullptr && !(g_dbg & 2)) __stcs(reinterpret_cast<uint4*>(c.rec + (size_t)(sv_blk + kb) * KB_BYTES + o), pk);   // STASH only (AF / ADD): no smem copy exists
+      else if (c.rec != nullptr) __stcs(reinterpret_cast<uint4*>(c.rec + (size_t)(sv_blk + kb) * KB_BYTES + o), pk);   // STASH only (AF / ADD): no smem copy exists
     }
   }
   const float* T = c.heads_s;     // this step's head rows (staged in the idle encoding tile)
@@ -178,7 +177,7 @@ __device__ __forceinline__ void drain(const EpiCtx& c, Heads& hd, int sv_blk, in
     if (cc + 2 < NCHUNK) tmem_ld32(c.t_lane + (cc + 2) * 32, va);
     process_chunk<KIND, STASH>(c, hd, vb, cc + 1, sv_blk, mw[cc + 1]);
   }
-  if (STASH && KIND != K_FEATURE && c.rec != nullptr && !(g_dbg & 4)) {      // one full 32-byte sector per row: [mask slot][row][8 words]
+  if (STASH && KIND != K_FEATURE && c.rec != nullptr) {      // one full 32-byte sector per row: [mask slot][row][8 words]
     uint4* dst = reinterpret_cast<uint4*>(c.rec + (size_t)SV_MASK * KB_BYTES + sv_mask * 4096 + c.row * 32);
     __stcs(dst, make_uint4(mw[0], mw[1], mw[2], mw[3]));
     __stcs(dst + 1, make_uint4(mw[4], mw[5], mw[6], mw[7]));
@@ -346,7 +345,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) mlp_fw
     auto stash_tile = [&](const uint8_t* tile_smem, int blk, int nblk) {
       const uint4* src = reinterpret_cast<const uint4*>(tile_smem);
       uint4* dst = reinterpret_cast<uint4*>(c.rec + (size_t)blk * KB_BYTES);
-      if (c.rec == nullptr || (g_dbg & 1)) return;
+      if (c.rec == nullptr) return;
       if (gtid == 0) { bulk_s2g_hint(dst, src, (uint32_t)nblk * KB_BYTES, l2_policy_evict_first()); bulk_commit(); }
     };
     for (long long k = slot; k < pair_tiles; k += 2) {
@@ -595,7 +594,8 @@ using namespace ibln;
 using namespace ibln::mlp;
 
 extern "C" int ibln_debug_timeline(void* device_buf) { ibln::mlp::g_timeline = device_buf; return 0; }
-extern "C" int ibln_debug_set(int flags) { ibln::mlp::g_dbg_host = flags; return (int)cudaMemcpyToSymbol(ibln::mlp::g_dbg, &flags, sizeof(int)); }
+// diagnostics (host side only: bit4 skip the dgrad launch, bit5 skip the wgrad launch)
+extern "C" int ibln_debug_set(int flags) { ibln::mlp::g_dbg_host = flags; return 0; }
 
 extern "C" int64_t ibln_mlp_packed_bytes(void) { return PACKED_BYTES; }
 

@@ -1,0 +1,122 @@
+// Training-step tail kernels: the phase-gated image losses of src/train.py and the Adam update of
+// both networks, each as ONE launch over flat buffers instead of ~60 small ATen launches + ~100 per-tensor updates.
+#include "common.cuh"
+
+namespace ibln {
+
+// loss += scale * sum over the used terms of mean((pred - target)^2)           (img2mse, nerf_renderer_helper.py:8)
+// terms: radiance_map (maps cols 9..11) vs rgb, radiance_map_k (cols 12+3k..) vs rgb_k, color_map (shade cols
+// 10..12) vs rgb  -- train.py:322-432 with the shipped betas.  Also writes d loss / d maps, d loss / d shade.
+constexpr int LOSS_THREADS = 256;
+__global__ void __launch_bounds__(LOSS_THREADS)
+phase_b_loss_kernel(const float* __restrict__ maps, const float* __restrict__ shade, const float* __restrict__ rgb,
+                    const float* __restrict__ rgb1, const float* __restrict__ rgb2, const float* __restrict__ rgb3, int n,
+                    float scale, float* __restrict__ loss, float* __restrict__ g_maps, float* __restrict__ g_shade) {
+  const int r = blockIdx.x * LOSS_THREADS + threadIdx.x;
+  float acc = 0.f;
+  if (r < n) {
+    const float inv = scale / (3.0f * (float)n);
+    const float* m = maps + (size_t)r * 24;
+    float* gm = g_maps + (size_t)r * 24;
+    const float* tg[4] = {rgb, rgb1, rgb2, rgb3};
+#pragma unroll
+    for (int j = 0; j < 9; ++j) gm[j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float d = 0.f;
+        if (tg[k] != nullptr) d = m[9 + 3 * k + c] - tg[k][(size_t)r * 3 + c];
+        acc += d * d;
+        gm[9 + 3 * k + c] = 2.0f * inv * d;
+      }
+    }
+#pragma unroll
+    for (int j = 21; j < 24; ++j) gm[j] = 0.f;
+    if (shade != nullptr) {
+      const float* s = shade + (size_t)r * 16;
+      float* gs = g_shade + (size_t)r * 16;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) gs[j] = 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float d = s[10 + c] - rgb[(size_t)r * 3 + c];
+        acc += d * d;
+        gs[10 + c] = 2.0f * inv * d;
+      }
+    }
+    acc *= inv;
+  }
+  __shared__ float part[LOSS_THREADS / 32];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < LOSS_THREADS / 32 ? part[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) atomicAdd(loss, v);
+  }
+}
+
+// torch.optim.Adam (amsgrad=False, weight_decay=0, maximize=False) on flat buffers, train.py:479-498:
+//   m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  p -= (lr / bc1) * m / (sqrt(v) / sqrt(bc2) + eps)
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
+            float step_size, float b1, float b2, float eps, float inv_sqrt_bc2, float grad_scale) {
+  const int64_t i4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i4 >= n) return;
+  if (i4 + 4 <= n) {
+    float4 pp = *reinterpret_cast<float4*>(p + i4), gg = *reinterpret_cast<const float4*>(g + i4);
+    float4 mm = *reinterpret_cast<float4*>(m + i4), vv = *reinterpret_cast<float4*>(v + i4);
+    float* P = &pp.x; float* G = &gg.x; float* M = &mm.x; float* V = &vv.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gr = G[k] * grad_scale;
+      M[k] = __fmaf_rn(b1, M[k], (1.0f - b1) * gr);           // lerp form of torch: m + (g - m)(1 - b1)
+      V[k] = __fmaf_rn(b2, V[k], (1.0f - b2) * gr * gr);
+      const float denom = sqrtf(V[k]) * inv_sqrt_bc2 + eps;
+      P[k] -= step_size * (M[k] / denom);
+    }
+    *reinterpret_cast<float4*>(p + i4) = pp;
+    *reinterpret_cast<float4*>(m + i4) = mm;
+    *reinterpret_cast<float4*>(v + i4) = vv;
+  } else {
+    for (int64_t i = i4; i < n; ++i) {
+      const float gr = g[i] * grad_scale;
+      const float mi = __fmaf_rn(b1, m[i], (1.0f - b1) * gr);
+      const float vi = __fmaf_rn(b2, v[i], (1.0f - b2) * gr * gr);
+      m[i] = mi; v[i] = vi;
+      p[i] -= step_size * (mi / (sqrtf(vi) * inv_sqrt_bc2 + eps));
+    }
+  }
+}
+
+}  // namespace ibln
+
+using namespace ibln;
+
+extern "C" int ibln_phase_b_loss(const float* maps_srgb, const float* shade_srgb, const float* rgb, const float* rgb_1,
+                                 const float* rgb_2, const float* rgb_3, int n, float scale, float* loss, float* g_maps,
+                                 float* g_shade, int device, void* stream) {
+  if (n == 0) return 0;
+  if (n < 0 || !maps_srgb || !rgb || !loss || !g_maps || (shade_srgb && !g_shade)) return IBLN_EINVAL;
+  DeviceGuard g(device);
+  phase_b_loss_kernel<<<(n + LOSS_THREADS - 1) / LOSS_THREADS, LOSS_THREADS, 0, (cudaStream_t)stream>>>(
+      maps_srgb, shade_srgb, rgb, rgb_1, rgb_2, rgb_3, n, scale, loss, g_maps, g_shade);
+  IBLN_RETURN_LAST();
+}
+
+extern "C" int ibln_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                              float beta1, float beta2, float eps, int step, float grad_scale, int device, void* stream) {
+  if (n == 0) return 0;
+  if (n < 0 || !param || !grad || !exp_avg || !exp_avg_sq || step < 1) return IBLN_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(exp_avg) |
+       reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15) return IBLN_EINVAL;
+  DeviceGuard g(device);
+  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+  const float step_size = (float)((double)lr / bc1), inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+  const int64_t threads = (n + 3) / 4;
+  adam_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, step_size,
+                                                                                  beta1, beta2, eps, inv_sqrt_bc2, grad_scale);
+  IBLN_RETURN_LAST();
+}

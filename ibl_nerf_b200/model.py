@@ -36,6 +36,7 @@ class _MLPTc(torch.autograd.Function):
         call("ibln_mlp_fwd", dev, ptr(packed), mode, ptr(pts), ptr(o), ptr(d), ptr(z), n, s, 0.0, 0, ptr(out), ptr(saved),
              flops=P * FLOP_FULL)
         ctx.packed, ctx.stash, ctx.P = packed, saved, P
+        ctx.sink = getattr(net, "_grad_sink", None)
         ctx.shapes = [p.shape for p in params]
         ctx.need = [p.requires_grad for p in params]
         return out
@@ -45,11 +46,15 @@ class _MLPTc(torch.autograd.Function):
         dev = g_out.device
         h = _lib.lib()
         g_out = f32c(g_out)
-        flat = torch.zeros(FLAT_PARAMS, dtype=torch.float32, device=dev)
+        # flat gradient image (state-dict order).  With a gradient sink (training.FlatParameters) the kernel
+        # accumulates straight into the optimizer's flat buffer and autograd sees no per-tensor gradients.
+        flat = ctx.sink if ctx.sink is not None else torch.zeros(FLAT_PARAMS, dtype=torch.float32, device=dev)
         ws = torch.empty(h.ibln_mlp_bwd_workspace_bytes(ctx.P), dtype=torch.uint8, device=dev)
         call("ibln_mlp_bwd", dev, ptr(ctx.packed), ptr(ctx.stash), ptr(g_out), ctx.P, ptr(flat), ptr(ws),
              flops=2.0 * ctx.P * FLOP_FULL)
         ctx.stash = None
+        if ctx.sink is not None:
+            return (None,) * (8 + len(ctx.shapes))
         grads, off = [], 0
         for shp, need in zip(ctx.shapes, ctx.need):
             k = 1
@@ -125,6 +130,10 @@ class IBLNeRF(nn.Module):
             call("ibln_mlp_pack_weights", dev, arr, ptr(self._packed))
             self._packed_key = key
         return self._packed
+
+    def invalidate_packed(self):
+        """Force a re-pack on the next query (parameters were updated in place outside torch, e.g. ibln_adam_step)."""
+        self._packed_key = None
 
     # ------------------------------------------------------------------ reference API
     def forward(self, x):

@@ -191,6 +191,25 @@ int64_t ibln_mlp_bwd_workspace_bytes(int64_t n_pts);
 int ibln_mlp_bwd(const void* packed, const void* saved, const float* g_out, int64_t n_pts,
                  float* flat_grad, void* workspace, int device, void* stream);
 
+/* ---- training-step tail ------------------------------------------------------ */
+
+/* Phase-B image losses of src/train.py:322-432 (shipped betas = 1) on the packed gamma-corrected outputs of
+ * ibln_composite_fwd / ibln_shade_fwd, forward and backward in one launch:
+ *   *loss += scale * [ mse(radiance_map, rgb) + sum_k mse(radiance_map_k, rgb_k) + mse(color_map, rgb) ]
+ * with mse = mean over N*3 elements (img2mse, nerf_renderer_helper.py:8).  maps_srgb [N,24] (radiance cols 9..11,
+ * coarse radiance k cols 12+3k..), shade_srgb [N,16] nullable (color cols 10..12; null = radiance-only phase),
+ * rgb_k [N,3] nullable (term skipped).  g_maps [N,24], g_shade [N,16] receive d loss / d input (all columns
+ * written).  *loss must be zeroed by the caller. */
+int ibln_phase_b_loss(const float* maps_srgb, const float* shade_srgb, const float* rgb, const float* rgb_1,
+                      const float* rgb_2, const float* rgb_3, int n, float scale, float* loss, float* g_maps,
+                      float* g_shade, int device, void* stream);
+
+/* torch.optim.Adam step (amsgrad off, no weight decay; src/train.py:479-498) over one flat fp32 buffer:
+ * step = 1-based iteration count (bias correction), grad_scale multiplies the gradient first (e.g. 1/world).
+ * All four buffers 16-byte aligned, n elements. */
+int ibln_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                   float beta1, float beta2, float eps, int step, float grad_scale, int device, void* stream);
+
 /* Self-test of the tcgen05 building block: D[128,N] = A[128,K] * B[N,K]^T with bf16 inputs staged
  * through the same swizzled shared-memory layout the MLP kernels use. a,b fp32 (rounded to bf16
  * inside), d fp32.  variant selects descriptor hypotheses (0 = production). */

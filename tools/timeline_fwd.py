@@ -12,14 +12,19 @@ net = ib.IBLNeRF(**fx.KITCHEN_ARCH).to(dev)
 h = _lib.lib()
 h.ibln_debug_timeline.argtypes = [ctypes.c_void_p]
 sigma = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+use_stash = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+flags = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+h.ibln_debug_set.argtypes = [ctypes.c_int]
+h.ibln_debug_set(flags)
 n, s = 4096, 192
 o = torch.rand(n, 3, device=dev); d = torch.randn(n, 3, device=dev)
 z = torch.sort(torch.rand(n, s, device=dev) * 7 + 0.5, -1)[0]
 P = n * s
 out = torch.empty(P, 18, device=dev)
 packed = net.packed_weights()
+stash = torch.empty(h.ibln_mlp_saved_bytes(P), dtype=torch.uint8, device=dev) if use_stash else None
 def run():
-    call("ibln_mlp_fwd", dev, ptr(packed), 1, None, ptr(o), ptr(d), ptr(z), n, s, 0.0, sigma, ptr(out), None)
+    call("ibln_mlp_fwd", dev, ptr(packed), 1, None, ptr(o), ptr(d), ptr(z), n, s, 0.0, sigma, ptr(out), ptr(stash))
 run(); torch.cuda.synchronize()
 tl = torch.zeros(8192, dtype=torch.int64, device=dev)
 h.ibln_debug_timeline(ctypes.c_void_p(tl.data_ptr()))
@@ -39,5 +44,4 @@ def show(name, ev, lo, hi):
         prev = c
 per = 2 * nst - 1
 show("rank0 epilogue slot 0 (10+2s acc ready, 11+2s published)", e0, 2 * per, 3 * per + 2)
-show("rank1 epilogue slot 0", e1, 2 * per, 3 * per + 2)
 show("leader MMA (100+2s+slot act ready; 200+2s+slot issued)", mm, 4 * 2 * nst, 4 * 2 * nst + 4 * nst)
