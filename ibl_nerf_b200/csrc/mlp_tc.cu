@@ -348,29 +348,66 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) mlp_fw
       if (c.rec == nullptr) return;
       if (gtid == 0) { bulk_s2g_hint(dst, src, (uint32_t)nblk * KB_BYTES, l2_policy_evict_first()); bulk_commit(); }
     };
-    for (long long k = slot; k < pair_tiles; k += 2) {
-      const long long tile = blockIdx.x + k * gridDim.x;
-      const bool real = tile < prm.n_tiles;            // phantom tile: keep the pair in lock step, touch no memory
+    // ---- tile pipeline.  The point data and the layer-0 bias row of the NEXT tile are fetched a whole tile ahead,
+    // the small-head biases are folded into the accumulators' initial values, and at a tile boundary the next
+    // tile's encoding is published BEFORE the finished tile's outputs are stored: the boundary costs one barrier
+    // plus the encoding arithmetic instead of three exposed L2 round trips.
+    struct Pt { float x[3], dir[3]; bool real, valid; };
+    auto fetch_point = [&](long long kk) {
+      Pt q;
+      const long long tile = blockIdx.x + kk * gridDim.x;
+      q.real = kk < pair_tiles && tile < prm.n_tiles;       // phantom tile: keep the pair in lock step, touch no memory
       const long long p = tile * TILE_M + row;
-      const bool valid = real && p < prm.gen.P;
-      float x[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 0.f};
-      if (valid) gen_point(prm.gen, p, x, dir);
-      if (STASH) c.rec = real ? prm.saved + (size_t)tile * SV_BYTES : nullptr;
-      load_bias(0);
-      write_encoding<10, 8>(aux, row, x);
+      q.valid = q.real && p < prm.gen.P;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { q.x[i] = 0.f; q.dir[i] = 0.f; }
+      if (q.valid) gen_point(prm.gen, p, q.x, q.dir);
+      return q;
+    };
+    auto begin_tile = [&](const Pt& q, long long kk, float2 bias0) {
+      if (STASH) c.rec = q.real ? prm.saved + (size_t)(blockIdx.x + kk * gridDim.x) * SV_BYTES : nullptr;
+      reinterpret_cast<float2*>(bias_s)[gtid] = bias0;
+      write_encoding<10, 8>(aux, row, q.x);
       if (STASH) { fence_proxy_async(); named_bar_sync(1 + slot, 128); }
       publish();
       if (STASH) stash_tile(aux, SV_PE, 1);      // off the critical path: overlaps the layer-0 GEMM
+    };
+    Pt cur = fetch_point(slot);
+    if (slot < pair_tiles) begin_tile(cur, slot, __ldg(bias_src(0)));
+    for (long long k = slot; k < pair_tiles; k += 2) {
+      const long long p = (blockIdx.x + k * gridDim.x) * TILE_M + row;
+      const bool valid = cur.valid;
+      float dir[3] = {cur.dir[0], cur.dir[1], cur.dir[2]};
+      const Pt nxt = fetch_point(k + 2);           // in flight during the whole tile
+      const float2 bias0 = __ldg(bias_src(0));
 
-      Heads hd;
-      const float2 zero2 = make_float2(0.f, 0.f);
-      hd.sigma = hd.rough = hd.irr = zero2;
+      Heads hd;                                    // accumulators start at the head biases (column 0 of each pair)
+      {
+        const float4 b_sr = __ldg(reinterpret_cast<const float4*>(c.cst + C_SR + 512));
+        hd.sigma = make_float2(b_sr.x, 0.f);
+        hd.rough = make_float2(b_sr.y, 0.f);
+        if (!SIGMA_ONLY) {
+          const float4 b_af = __ldg(reinterpret_cast<const float4*>(c.cst + C_AF + 512));
+          const float4 b_rad = __ldg(reinterpret_cast<const float4*>(c.cst + C_RAD + 768));
+          hd.alb[0] = make_float2(b_af.x, 0.f); hd.alb[1] = make_float2(b_af.y, 0.f); hd.alb[2] = make_float2(b_af.z, 0.f);
+          hd.irr = make_float2(b_af.w, 0.f);
+          hd.rad[0][0] = make_float2(b_rad.x, 0.f); hd.rad[0][1] = make_float2(b_rad.y, 0.f); hd.rad[0][2] = make_float2(b_rad.z, 0.f);
 #pragma unroll
-      for (int a = 0; a < 3; ++a) hd.alb[a] = zero2;
+          for (int a = 0; a < 3; ++a) {
+            const float4 b_add = __ldg(reinterpret_cast<const float4*>(c.cst + C_ADD + 1152 + 4 * a));
+            hd.rad[1 + a][0] = make_float2(b_add.x, 0.f); hd.rad[1 + a][1] = make_float2(b_add.y, 0.f); hd.rad[1 + a][2] = make_float2(b_add.z, 0.f);
+          }
+        } else {
+          const float2 zero2 = make_float2(0.f, 0.f);
+          hd.irr = zero2;
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
+          for (int a = 0; a < 3; ++a) hd.alb[a] = zero2;
 #pragma unroll
-        for (int q = 0; q < 3; ++q) hd.rad[a][q] = zero2;
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int q = 0; q < 3; ++q) hd.rad[a][q] = zero2;
+        }
+      }
 
 #pragma unroll 1
       for (int s = 0; s < n_steps; ++s) {
@@ -426,33 +463,34 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) mlp_fw
           }
         }
       }
-      // ---- outputs
+      // ---- tile boundary: free the slot's shared tables, start the next tile, then store this tile's outputs
+      if (STASH && gtid == 0) bulk_wait_read0();
+      named_bar_sync(1 + slot, 128);         // everyone is done with the last step's bias row / head table
+      tc_fence_before();                     // order this tile's TMEM reads before the next tile's act_ready arrival
+      if (k + 2 < pair_tiles) begin_tile(nxt, k + 2, bias0);
       if (valid) {
         auto sum2 = [](float2 v) { return v.x + v.y; };
-        const float sigma = sum2(hd.sigma) + __ldg(c.cst + C_SR + 512);
         if (SIGMA_ONLY) {
-          prm.out[p] = sigma;
+          prm.out[p] = sum2(hd.sigma);
         } else {
           float r[18];
-          r[0] = sigma;
+          r[0] = sum2(hd.sigma);
 #pragma unroll
-          for (int q = 0; q < 3; ++q) r[1 + q] = sum2(hd.alb[q]) + __ldg(c.cst + C_AF + 512 + q);
-          r[4] = sum2(hd.rough) + __ldg(c.cst + C_SR + 513);
-          r[5] = sum2(hd.irr) + __ldg(c.cst + C_AF + 515);
+          for (int q = 0; q < 3; ++q) r[1 + q] = sum2(hd.alb[q]);
+          r[4] = sum2(hd.rough);
+          r[5] = sum2(hd.irr);
 #pragma unroll
-          for (int q = 0; q < 3; ++q) r[6 + q] = sum2(hd.rad[0][q]) + __ldg(c.cst + C_RAD + 768 + q);
+          for (int q = 0; q < 3; ++q) r[6 + q] = sum2(hd.rad[0][q]);
 #pragma unroll
           for (int a = 0; a < 3; ++a)
 #pragma unroll
-            for (int q = 0; q < 3; ++q) r[9 + 3 * a + q] = sum2(hd.rad[1 + a][q]) + __ldg(c.cst + C_ADD + 1152 + 4 * a + q);
+            for (int q = 0; q < 3; ++q) r[9 + 3 * a + q] = sum2(hd.rad[1 + a][q]);
           float2* dst = reinterpret_cast<float2*>(prm.out + p * 18);
 #pragma unroll
           for (int j = 0; j < 9; ++j) dst[j] = make_float2(r[2 * j], r[2 * j + 1]);
         }
       }
-      if (STASH && gtid == 0) bulk_wait_read0();
-      named_bar_sync(1 + slot, 128);         // last step's bias row no longer needed (next tile overwrites it)
-      tc_fence_before();   // order this tile's TMEM reads before the next tile's act_ready arrival
+      cur = nxt;
     }
     if (STASH && gtid == 0) bulk_wait0();
   }
