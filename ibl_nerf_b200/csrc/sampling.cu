@@ -40,32 +40,88 @@ __global__ void stratified_z_kernel(const float* __restrict__ nearp, const float
 }
 
 // ---------------------------------------------------------------- inverse CDF
-// searchsorted(cdf, u, right=True) = number of entries <= u, as a branch-free power-of-two descent
-// (p2 = largest power of two <= n): log2(n)+1 predicated steps, no divergence.
-__device__ __forceinline__ int upper_bound(const float* cdf, int n, int p2, float u) {
-  int pos = 0;
-  for (int step = p2; step > 0; step >>= 1) {
-    const int np = pos + step;
-    if (np <= n && cdf[np - 1] <= u) pos = np;
+// searchsorted(cdf, u, right=True) = number of entries <= u.  A per-ray binary search costs log2(n)+1 dependent
+// shared-memory probes with random (bank-conflicting) addresses per sample and made the kernel LSU-bound at a
+// quarter of the HBM roofline.  Instead every ray gets a 256-cell GUIDE TABLE over the value range [0,1]:
+//   G[m] = #{k : floor(256 cdf[k]) <= m}
+// (a shared-memory histogram of the nbins entries + one warp prefix scan).  For a sample u in cell m every entry
+// counted in G[m-1] is <= u and every entry beyond G[m] is > u, so the answer lies in [G[m-1], G[m]] -- for the
+// ~3/4 of the cells that hold no entry it IS G[m], with no probe at all; otherwise a short exact binary search
+// over the entries of that one cell.  One 16-byte record {cdf[i-1], cdf[i], bins[i-1], bins[i]} then feeds the
+// interpolation.  Indices are bit-identical to torch.searchsorted (the cell tests are exact in fp32).
+constexpr int GUIDE_CELLS = 256;
+
+struct RaySmem {            // per-warp carve-up (floats)
+  float* cdf;               // [nbins]
+  float4* rec;              // [nbins + 1]
+  uint32_t* guide;          // [GUIDE_CELLS / 2] packed u16 inclusive counts
+  float* bins;              // [nbins] staging copy (register-prefetching kernel only)
+};
+__host__ __device__ inline int ray_smem_floats(int nbins) { return 2 * ((nbins + 3) & ~3) + 4 * (nbins + 1) + GUIDE_CELLS / 2; }
+__device__ __forceinline__ RaySmem carve(float* base, int nbins) {
+  RaySmem r;
+  r.rec = reinterpret_cast<float4*>(base);
+  r.cdf = base + 4 * (nbins + 1);
+  r.guide = reinterpret_cast<uint32_t*>(r.cdf + ((nbins + 3) & ~3));
+  r.bins = reinterpret_cast<float*>(r.guide + GUIDE_CELLS / 2);
+  return r;
+}
+
+__device__ __forceinline__ int guide_cell(float v) {
+  const int c = (int)__fmul_rn(v, (float)GUIDE_CELLS);       // exact power-of-two scaling, truncation
+  return min(GUIDE_CELLS - 1, max(0, c));
+}
+
+// cdf[0..nbins) is in shared memory (written by this warp, visible after __syncwarp): build guide + records
+__device__ __forceinline__ void warp_build_guide(const RaySmem& sm, const float* __restrict__ bins, int nbins, int lane) {
+#pragma unroll
+  for (int j = 0; j < GUIDE_CELLS / 64; ++j) sm.guide[lane + 32 * j] = 0u;
+  __syncwarp();
+  for (int i = lane; i <= nbins; i += 32) {
+    const int below = max(i - 1, 0), above = min(i, nbins - 1);
+    sm.rec[i] = make_float4(sm.cdf[below], sm.cdf[above], bins[below], bins[above]);
+    if (i < nbins) {
+      const int c = guide_cell(sm.cdf[i]);
+      atomicAdd(&sm.guide[c >> 1], 1u << (16 * (c & 1)));
+    }
   }
-  return pos;
+  __syncwarp();
+  // inclusive prefix over 256 packed u16 cells: lane owns words 4*lane .. 4*lane+3 (counts <= 65535)
+  uint32_t w[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { w[j] = sm.guide[4 * lane + j]; w[j] += w[j] << 16; }
+#pragma unroll
+  for (int j = 1; j < 4; ++j) w[j] += (w[j - 1] >> 16) * 0x10001u;
+  uint32_t tot = w[3] >> 16, inc = tot;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t v = __shfl_up_sync(FULL, inc, o);
+    if (lane >= o) inc += v;
+  }
+  const uint32_t base = (inc - tot) * 0x10001u;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) sm.guide[4 * lane + j] = w[j] + base;
+  __syncwarp();
 }
 
 // EXACT = true : IEEE division, every op un-contracted -> samples bit-identical to the reference given (cdf, u)
 // EXACT = false: one MUFU reciprocal-multiply (<= 2 ulp); used by the fused sample_pdf / hierarchical paths
 template <bool EXACT>
-__device__ __forceinline__ float invert_one(const float* cdf, const float* bins, int nbins, int p2, float u, int* ind_out) {
-  const int ind = upper_bound(cdf, nbins, p2, u);
-  *ind_out = ind;
-  const int below = max(ind - 1, 0), above = min(ind, nbins - 1);
-  const float c0 = cdf[below], c1 = cdf[above], b0 = bins[below], b1 = bins[above];
-  float den = __fsub_rn(c1, c0);
+__device__ __forceinline__ float invert_one(const RaySmem& sm, float u, int* ind_out) {
+  const uint16_t* g16 = reinterpret_cast<const uint16_t*>(sm.guide);
+  const int m = guide_cell(u);
+  int lo = m ? (int)g16[m - 1] : 0, hi = (int)g16[m];
+  while (lo < hi) {                       // only for samples whose cell holds cdf entries
+    const int mid = (lo + hi) >> 1;
+    if (sm.cdf[mid] <= u) lo = mid + 1; else hi = mid;
+  }
+  *ind_out = lo;
+  const float4 r = sm.rec[lo];
+  float den = __fsub_rn(r.y, r.x);
   if (den < 1e-5f) den = 1.0f;
-  const float t = EXACT ? __fdiv_rn(__fsub_rn(u, c0), den) : __fdividef(__fsub_rn(u, c0), den);
-  return __fadd_rn(b0, __fmul_rn(t, __fsub_rn(b1, b0)));
+  const float t = EXACT ? __fdiv_rn(__fsub_rn(u, r.x), den) : __fdividef(__fsub_rn(u, r.x), den);
+  return __fadd_rn(r.z, __fmul_rn(t, __fsub_rn(r.w, r.z)));
 }
-
-__host__ __device__ inline int floor_pow2(int v) { int p = 1; while (p * 2 <= v) p <<= 1; return p; }
 
 // Build cdf[0..nbins) in shared memory from nbins-1 weights (warp-cooperative).
 // pdf = (w+1e-5)/sum; cdf = [0, cumsum(pdf)]  (nerf_renderer_helper.py:93-96)
@@ -96,30 +152,28 @@ __global__ void __launch_bounds__(SP_WARPS * 32)
 sample_pdf_kernel(const float* __restrict__ bins, int64_t bins_stride, const float* __restrict__ weights,
                   int64_t w_stride, const float* __restrict__ cdf_in, const float* __restrict__ u, int n, int nbins,
                   int nsamp, int64_t* __restrict__ inds_out, float* __restrict__ samples) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* s_bins = sm + (size_t)warp * 2 * nbins;
-  float* s_cdf = s_bins + nbins;
-  const int p2 = floor_pow2(nbins);
+  const RaySmem rs = carve(sm + (size_t)warp * ray_smem_floats(nbins), nbins);
   for (int r = blockIdx.x * SP_WARPS + warp; r < n; r += gridDim.x * SP_WARPS) {
     const float* brow = bins + (int64_t)r * bins_stride;
     const float* urow = u + (int64_t)r * nsamp;
     float* orow = samples + (int64_t)r * nsamp;
-    for (int i = lane; i < nbins; i += 32) s_bins[i] = brow[i];
     if (cdf_in != nullptr) {
-      for (int i = lane; i < nbins; i += 32) s_cdf[i] = cdf_in[(int64_t)r * nbins + i];
+      for (int i = lane; i < nbins; i += 32) rs.cdf[i] = cdf_in[(int64_t)r * nbins + i];
       __syncwarp();
     } else {
-      warp_build_cdf(weights + (int64_t)r * w_stride, nbins - 1, s_cdf, lane);
+      warp_build_cdf(weights + (int64_t)r * w_stride, nbins - 1, rs.cdf, lane);
     }
+    warp_build_guide(rs, brow, nbins, lane);
     int j = lane;
-    for (; j + 96 < nsamp; j += 128) {          // 4 independent searches in flight per lane
+    for (; j + 96 < nsamp; j += 128) {          // 4 independent lookups in flight per lane
       float uu[4], sv[4];
       int ind[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) uu[q] = urow[j + 32 * q];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) sv[q] = invert_one<EXACT>(s_cdf, s_bins, nbins, p2, uu[q], &ind[q]);
+      for (int q = 0; q < 4; ++q) sv[q] = invert_one<EXACT>(rs, uu[q], &ind[q]);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         orow[j + 32 * q] = sv[q];
@@ -128,10 +182,95 @@ sample_pdf_kernel(const float* __restrict__ bins, int64_t bins_stride, const flo
     }
     for (; j < nsamp; j += 32) {
       int ind;
-      orow[j] = invert_one<EXACT>(s_cdf, s_bins, nbins, p2, urow[j], &ind);
+      orow[j] = invert_one<EXACT>(rs, urow[j], &ind);
       if (inds_out != nullptr) inds_out[(int64_t)r * nsamp + j] = ind;
     }
     __syncwarp();
+  }
+}
+
+// The shipped shape (nbins <= 64, nsamp <= 128: 63 bins / 128 samples): every input of a ray fits in 8 registers
+// per lane, so the NEXT ray's weights / bins / uniforms are fetched while the current ray is processed -- the
+// generic kernel exposes three dependent global-load round trips per ray (ncu: 53 % long-scoreboard stalls).
+struct RayRegs { float w0, w1, b0, b1, u[4]; };
+// NB / NS: compile-time nbins / nsamp (0 = run-time); the shipped 63 / 128 instantiation folds every bounds test.
+template <bool EXACT, int NB, int NS>
+__global__ void __launch_bounds__(SP_WARPS * 32)
+sample_pdf_small_kernel(const float* __restrict__ bins, int64_t bins_stride, const float* __restrict__ weights,
+                        int64_t w_stride, const float* __restrict__ cdf_in, const float* __restrict__ u, int n, int nbins_rt,
+                        int nsamp_rt, int64_t* __restrict__ inds_out, float* __restrict__ samples) {
+  extern __shared__ __align__(16) float sm[];
+  const int nbins = NB ? NB : nbins_rt, nsamp = NS ? NS : nsamp_rt;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const RaySmem rs = carve(sm + (size_t)warp * ray_smem_floats(nbins), nbins);
+  const int stride = gridDim.x * SP_WARPS;
+  const int nw = nbins - 1;
+  auto fetch = [&](int r) {
+    RayRegs q;
+    q.w0 = q.w1 = q.b0 = q.b1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) q.u[k] = 0.f;
+    if (r < n) {
+      const float* brow = bins + (int64_t)r * bins_stride;
+      const float* urow = u + (int64_t)r * nsamp;
+      if (cdf_in != nullptr) {          // explicit CDF: w0/w1 carry cdf[lane], cdf[lane + 32]
+        const float* crow = cdf_in + (int64_t)r * nbins;
+        if (lane < nbins) q.w0 = crow[lane];
+        if (lane + 32 < nbins) q.w1 = crow[lane + 32];
+      } else {
+        const float* wrow = weights + (int64_t)r * w_stride;
+        if (lane < nw) q.w0 = wrow[lane];
+        if (lane + 32 < nw) q.w1 = wrow[lane + 32];
+      }
+      if (lane < nbins) q.b0 = brow[lane];
+      if (lane + 32 < nbins) q.b1 = brow[lane + 32];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (lane + 32 * k < nsamp) q.u[k] = urow[lane + 32 * k];
+    }
+    return q;
+  };
+  int r = blockIdx.x * SP_WARPS + warp;
+  RayRegs cur = fetch(r);
+  for (; r < n; r += stride) {
+    const RayRegs nxt = fetch(r + stride);
+    if (cdf_in != nullptr) {
+      if (lane < nbins) rs.cdf[lane] = cur.w0;
+      if (lane + 32 < nbins) rs.cdf[lane + 32] = cur.w1;
+    } else {              // same arithmetic / summation order as warp_build_cdf
+      float part = 0.f;
+      if (lane < nw) part += cur.w0 + 1e-5f;
+      if (lane + 32 < nw) part += cur.w1 + 1e-5f;
+      const float inv_total = __fdividef(1.0f, warp_sum(part));
+      float p0 = (lane < nw) ? (cur.w0 + 1e-5f) * inv_total : 0.f;
+      float p1 = (lane + 32 < nw) ? (cur.w1 + 1e-5f) * inv_total : 0.f;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float v0 = __shfl_up_sync(FULL, p0, o), v1 = __shfl_up_sync(FULL, p1, o);
+        if (lane >= o) { p0 += v0; p1 += v1; }
+      }
+      const float carry = __shfl_sync(FULL, p0, 31);
+      if (lane == 0) rs.cdf[0] = 0.f;
+      if (lane < nw) rs.cdf[lane + 1] = 0.f + p0;
+      if (lane + 32 < nw) rs.cdf[lane + 33] = carry + p1;
+    }
+    if (lane < nbins) rs.bins[lane] = cur.b0;
+    if (lane + 32 < nbins) rs.bins[lane + 32] = cur.b1;
+    __syncwarp();
+    warp_build_guide(rs, rs.bins, nbins, lane);
+    float* orow = samples + (int64_t)r * nsamp;
+    float sv[4];
+    int ind[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sv[k] = invert_one<EXACT>(rs, cur.u[k], &ind[k]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (lane + 32 * k < nsamp) {
+        orow[lane + 32 * k] = sv[k];
+        if (inds_out != nullptr) inds_out[(int64_t)r * nsamp + lane + 32 * k] = ind[k];
+      }
+    __syncwarp();
+    cur = nxt;
   }
 }
 
@@ -171,15 +310,17 @@ merge_sort_kernel(const float* __restrict__ za, const float* __restrict__ zb, in
 }
 
 // z mids -> cdf(weights[1:-1]) -> samples -> sort(cat(z, samples)); ibl_nerf_renderer.py:702-707
+__host__ __device__ inline int hier_smem_floats(int s0, int npad) { return ray_smem_floats(s0 - 1) + ((s0 + 3) & ~3) + npad; }
 __global__ void __launch_bounds__(SP_WARPS * 32)
 hierarchical_kernel(const float* __restrict__ z, const float* __restrict__ weights, const float* __restrict__ u, int n,
                     int s0, int s1, int npad, float* __restrict__ z_samples, float* __restrict__ z_merged) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int nbins = s0 - 1;
-  float* s_bins = sm + (size_t)warp * (2 * s0 + npad);
-  float* s_cdf = s_bins + s0;
-  float* s_sort = s_cdf + s0;
+  float* base = sm + (size_t)warp * hier_smem_floats(s0, npad);
+  const RaySmem rs = carve(base, nbins);
+  float* s_bins = base + ray_smem_floats(nbins);
+  float* s_sort = s_bins + ((s0 + 3) & ~3);
   int tot = s0 + s1;
   for (int r = blockIdx.x * SP_WARPS + warp; r < n; r += gridDim.x * SP_WARPS) {
     const float* zr = z + (int64_t)r * s0;
@@ -188,11 +329,11 @@ hierarchical_kernel(const float* __restrict__ z, const float* __restrict__ weigh
       s_sort[i] = zi;
       if (i < nbins) s_bins[i] = __fmul_rn(0.5f, __fadd_rn(zr[i + 1], zi));
     }
-    warp_build_cdf(weights + (int64_t)r * s0 + 1, nbins - 1, s_cdf, lane);
-    const int p2 = floor_pow2(nbins);
+    warp_build_cdf(weights + (int64_t)r * s0 + 1, nbins - 1, rs.cdf, lane);
+    warp_build_guide(rs, s_bins, nbins, lane);
     for (int j = lane; j < s1; j += 32) {
       int ind;
-      float sv = invert_one<false>(s_cdf, s_bins, nbins, p2, u[(int64_t)r * s1 + j], &ind);
+      float sv = invert_one<false>(rs, u[(int64_t)r * s1 + j], &ind);
       z_samples[(int64_t)r * s1 + j] = sv;
       s_sort[s0 + j] = sv;
     }
@@ -229,9 +370,19 @@ static int launch_sample_pdf(const float* bins, int64_t bs, const float* w, int6
   if (n == 0) return 0;
   if (n < 0 || nbins < 2 || nsamp < 1 || !bins || !u || !samples) return IBLN_EINVAL;
   DeviceGuard g(device);
-  size_t smem = (size_t)SP_WARPS * 2 * nbins * sizeof(float);
+  if (nbins > 65535) return IBLN_EINVAL;
+  size_t smem = (size_t)SP_WARPS * ray_smem_floats(nbins) * sizeof(float);
   if (smem > 200 * 1024) return IBLN_EINVAL;
   int grid = ray_grid(n, device, SP_WARPS, 16);
+  if (nbins <= 64 && nsamp <= 128) {     // register-prefetching kernel (N_samples = 64, N_importance = 128 of every shipped config)
+    if (cdf != nullptr)
+      sample_pdf_small_kernel<true, 0, 0><<<grid, SP_WARPS * 32, smem, (cudaStream_t)stream>>>(bins, bs, w, ws, cdf, u, n, nbins, nsamp, inds, samples);
+    else if (nbins == 63 && nsamp == 128)
+      sample_pdf_small_kernel<false, 63, 128><<<grid, SP_WARPS * 32, smem, (cudaStream_t)stream>>>(bins, bs, w, ws, cdf, u, n, nbins, nsamp, inds, samples);
+    else
+      sample_pdf_small_kernel<false, 0, 0><<<grid, SP_WARPS * 32, smem, (cudaStream_t)stream>>>(bins, bs, w, ws, cdf, u, n, nbins, nsamp, inds, samples);
+    IBLN_RETURN_LAST();
+  }
   if (cdf != nullptr) {   // explicit-CDF entry: bit-exact arithmetic
     if (smem > 48 * 1024) IBLN_CUDA(cudaFuncSetAttribute(sample_pdf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     sample_pdf_kernel<true><<<grid, SP_WARPS * 32, smem, (cudaStream_t)stream>>>(bins, bs, w, ws, cdf, u, n, nbins, nsamp, inds, samples);
@@ -276,7 +427,7 @@ extern "C" int ibln_hierarchical_sample(const float* z, const float* weights, co
   if (n < 0 || s0 < 4 || s1 < 1 || !z || !weights || !u || !z_samples || !z_merged) return IBLN_EINVAL;
   DeviceGuard g(device);
   int npad = next_pow2(s0 + s1);
-  size_t smem = (size_t)SP_WARPS * (2 * s0 + npad) * sizeof(float);
+  size_t smem = (size_t)SP_WARPS * hier_smem_floats(s0, npad) * sizeof(float);
   if (smem > 200 * 1024) return IBLN_EINVAL;
   if (smem > 48 * 1024) IBLN_CUDA(cudaFuncSetAttribute(hierarchical_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   hierarchical_kernel<<<ray_grid(n, device, SP_WARPS, 16), SP_WARPS * 32, smem, (cudaStream_t)stream>>>(z, weights, u, n, s0, s1, npad, z_samples, z_merged);
