@@ -402,6 +402,89 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) mlp_dg
   if (warp == 1) { __syncwarp(); tmem_dealloc_pair(tmem_base, 512); }
 }
 
+// ---------------------------------------------------------------- freeze-mode head gradients
+// forward_freezed (ibl_nerf.py:88-152, iterations >= N_iter_freeze of the shipped schedule): only the albedo /
+// irradiance feature layers and heads (and the roughness head unless freeze_roughness) receive gradients, so the
+// dgrad chain collapses to the albedo|irradiance feature tile: dY_af = relu'(af) * (g_albedo W_alb | g_irr W_irr)
+// on CUDA cores, written with the G tile for the three wgrad jobs that remain.  One tile per 128-thread CTA pass.
+struct FreezeParams {
+  const uint8_t* packed; const uint8_t* saved; const float* g_out; uint8_t* dy; float* flat_grad;
+  long long P, n_tiles;
+  int train_roughness;
+};
+__global__ void __launch_bounds__(128, 2) mlp_dgrad_freeze_kernel(FreezeParams prm) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* act = smem;                                        // [4 K-blocks] dY_af tile (operand layout)
+  float* T_AF = reinterpret_cast<float*>(smem + ACT_BYTES);   // albedo [3][128] | irradiance [128]
+  const float* cst = reinterpret_cast<const float*>(prm.packed + PACKED_CONST_OFF);
+  for (int i = threadIdx.x; i < 128; i += 128)
+    for (int j = 0; j < 4; ++j) T_AF[4 * (i + 0) + j] = __ldg(cst + C_AF + 4 * i + j);
+  __syncthreads();
+  const int row = threadIdx.x, lane = threadIdx.x & 31;
+  const FlatOff fo = flat_offsets();
+  uint32_t off[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) off[q] = swz_offset(row, q);
+  for (long long tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x) {
+    const long long p = tile * TILE_M + row;
+    const bool valid = p < prm.P;
+    uint8_t* dy = prm.dy + (size_t)tile * DY_BYTES;
+    const uint32_t* masks = reinterpret_cast<const uint32_t*>(prm.saved + (size_t)tile * SV_BYTES + (size_t)SV_MASK * KB_BYTES) + row * 8;
+    float g[18];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+      float2 v = valid ? __ldg(reinterpret_cast<const float2*>(prm.g_out + p * 18) + j) : make_float2(0.f, 0.f);
+      g[2 * j] = v.x; g[2 * j + 1] = v.y;
+    }
+    {   // head-bias gradients (albedo, irradiance, roughness)
+      float s1 = warp_sum(g[1]), s2 = warp_sum(g[2]), s3 = warp_sum(g[3]), s4 = warp_sum(g[4]), s5 = warp_sum(g[5]);
+      if (lane == 0) {
+        atomicAdd(prm.flat_grad + fo.b[12], s1); atomicAdd(prm.flat_grad + fo.b[12] + 1, s2); atomicAdd(prm.flat_grad + fo.b[12] + 2, s3);
+        atomicAdd(prm.flat_grad + fo.b[15], s5);
+        if (prm.train_roughness) atomicAdd(prm.flat_grad + fo.b[13], s4);
+      }
+    }
+    {   // G tile (channels 1..5 are the only ones the remaining jobs read; write all 18 like the full kernel)
+      float e[64];
+#pragma unroll
+      for (int j = 0; j < 64; ++j) e[j] = j < 18 ? g[j] : 0.f;
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch)
+        store_tile4(dy + (size_t)DY_G * KB_BYTES, 0, swz_offset(row, ch),
+                    make_uint4(pack_bf16x2(e[8 * ch], e[8 * ch + 1]), pack_bf16x2(e[8 * ch + 2], e[8 * ch + 3]),
+                               pack_bf16x2(e[8 * ch + 4], e[8 * ch + 5]), pack_bf16x2(e[8 * ch + 6], e[8 * ch + 7])));
+    }
+    const uint4 mw0 = __ldg(reinterpret_cast<const uint4*>(masks + 8 * 1024));
+    const uint4 mw1 = __ldg(reinterpret_cast<const uint4*>(masks + 8 * 1024) + 1);
+    const uint32_t mw[8] = {mw0.x, mw0.y, mw0.z, mw0.w, mw1.x, mw1.y, mw1.z, mw1.w};
+    for (int cc = 0; cc < 8; ++cc) {
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      if (cc < 4) {
+#pragma unroll
+        for (int q = 0; q < 3; ++q) axpy32(v, g[1 + q], T_AF + q * 128 + cc * 32);
+      } else {
+        axpy32(v, g[5], T_AF + 384 + (cc - 4) * 32);
+      }
+      const uint32_t m = mw[cc];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = ((m >> j) & 1u) ? v[j] : 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        store_tile4(act, cc >> 1, off[(cc & 1) * 4 + q],
+                    make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
+                               pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7])));
+    }
+    __syncthreads();
+    const uint4* src = reinterpret_cast<const uint4*>(act);
+    uint4* dst = reinterpret_cast<uint4*>(dy + (size_t)DY_AF * KB_BYTES);
+#pragma unroll 8
+    for (int i = threadIdx.x; i < ACT_BYTES / 16; i += 128) __stcs(dst + i, src[i]);
+    __syncthreads();
+  }
+}
+
 // ---------------------------------------------------------------- wgrad kernel
 // D[m][n] += sum_pt A[pt][m] * B[pt][n].  A = 2 adjacent 16 KB blocks of a record (128 "m" columns), B = nb
 // adjacent blocks (64*nb "n" columns), both read as MN-major SWIZZLE_128B operands straight from the stash /
@@ -604,8 +687,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) mlp_wgrad_kernel(const __grid_c
   if (warp == 1) { __syncwarp(); tmem_dealloc(tmem_base, 512); }
 }
 
-// the 21 GEMMs of one network's weight gradient
-static WgradParams make_wgrad_jobs() {
+// the 21 GEMMs of one network's weight gradient (freeze = 0), or the 2-3 that remain in the freeze modes
+// (1: freeze_radiance, 2: freeze_radiance + freeze_roughness)
+static WgradParams make_wgrad_jobs(int freeze) {
   WgradParams P;
   memset(&P, 0, sizeof(P));
   const FlatOff fo = flat_offsets();
@@ -621,6 +705,25 @@ static WgradParams make_wgrad_jobs() {
     o.off = off; o.m_lo = m_lo; o.m_hi = m_hi; o.n_lo = n_lo; o.n_hi = n_hi; o.stride_m = stride_m; o.stride_n = stride_n;
   };
   constexpr int DYR = 0, SVR = 1;
+  if (freeze) {
+    {   // albedo / irradiance feature linears: dY_af x h7
+      WJob& p = job(DYR, DY_AF, 2, SVR, SV_H(7), 4, 256, 1);
+      add_out(p, fo.w[11], 0, 128, 0, 256, 256, 1);
+      add_out(p, fo.w[14], 128, 256, 0, 256, 256, 1);
+      add_out(p, fo.b[11], 0, 128, 256, 257, 1, 0);
+      add_out(p, fo.b[14], 128, 256, 256, 257, 1, 0);
+    }
+    {   // albedo / irradiance heads from AF
+      WJob& p = job(SVR, SV_AF, 2, DYR, DY_G, 1, 64, 0);
+      add_out(p, fo.w[12], 0, 128, 1, 4, 1, 128);
+      add_out(p, fo.w[15], 128, 256, 5, 6, 1, 0);
+    }
+    if (freeze == 1) {   // roughness head from h7
+      WJob& p = job(SVR, SV_H(7), 2, DYR, DY_G, 1, 64, 0);
+      add_out(p, fo.w[13], 0, 256, 4, 5, 1, 0);
+    }
+    return P;
+  }
   // trunk layers: dW_l = dY_l^T X_l (+ bias through the ones column)
   for (int l = 0; l < 8; ++l) {
     const int ld = l == 0 ? 63 : (l == 5 ? 319 : 256);
@@ -695,27 +798,38 @@ using namespace ibln::mlp;
 extern "C" int64_t ibln_mlp_bwd_workspace_bytes(int64_t n_pts) { return ((n_pts + TILE_M - 1) / TILE_M) * DY_BYTES; }
 
 extern "C" int ibln_mlp_bwd(const void* packed, const void* saved, const float* g_out, int64_t n_pts, float* flat_grad,
-                            void* workspace, int device, void* stream_) {
+                            void* workspace, int freeze_mode, int device, void* stream_) {
   if (n_pts == 0) return 0;
-  if (!packed || !saved || !g_out || !flat_grad || !workspace || n_pts < 0) return IBLN_EINVAL;
+  if (!packed || !saved || !g_out || !flat_grad || !workspace || n_pts < 0 || freeze_mode < 0 || freeze_mode > 2) return IBLN_EINVAL;
   DeviceGuard guard(device);
   cudaStream_t stream = (cudaStream_t)stream_;
   const long long n_tiles = (n_pts + TILE_M - 1) / TILE_M;
-  // ---- dgrad chain
-  DgradParams dp;
-  dp.packed = (const uint8_t*)packed; dp.saved = (const uint8_t*)saved; dp.g_out = g_out; dp.dy = (uint8_t*)workspace;
-  dp.flat_grad = flat_grad; dp.P = n_pts; dp.n_tiles = n_tiles; dp.dbg = g_dbg_host; dp.tl = (unsigned long long*)g_timeline;
-  IBLN_CUDA(cudaFuncSetAttribute(mlp_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_REQUEST));
   const int sms = num_sms(device);
-  long long grid = (long long)(sms & ~1);                      // CTA pairs
-  if (((n_tiles + 1) & ~1LL) < grid) grid = (n_tiles + 1) & ~1LL;
-  { int rc = make_chunk_stream_map(&dp.wmap, (const uint8_t*)packed + PACKED_BWD_OFF, N_CHUNKS_BWD); if (rc != 0) return rc; }
-  if (!(g_dbg_host & 16)) mlp_dgrad_kernel<<<(unsigned)grid, N_THREADS, SMEM_REQUEST, stream>>>(dp);
-  IBLN_CUDA(cudaGetLastError());
-  if (g_dbg_host & 32) return 0;
+  if (freeze_mode == 0) {
+    // ---- dgrad chain
+    DgradParams dp;
+    dp.packed = (const uint8_t*)packed; dp.saved = (const uint8_t*)saved; dp.g_out = g_out; dp.dy = (uint8_t*)workspace;
+    dp.flat_grad = flat_grad; dp.P = n_pts; dp.n_tiles = n_tiles; dp.dbg = g_dbg_host; dp.tl = (unsigned long long*)g_timeline;
+    IBLN_CUDA(cudaFuncSetAttribute(mlp_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_REQUEST));
+    long long grid = (long long)(sms & ~1);                      // CTA pairs
+    if (((n_tiles + 1) & ~1LL) < grid) grid = (n_tiles + 1) & ~1LL;
+    { int rc = make_chunk_stream_map(&dp.wmap, (const uint8_t*)packed + PACKED_BWD_OFF, N_CHUNKS_BWD); if (rc != 0) return rc; }
+    if (!(g_dbg_host & 16)) mlp_dgrad_kernel<<<(unsigned)grid, N_THREADS, SMEM_REQUEST, stream>>>(dp);
+    IBLN_CUDA(cudaGetLastError());
+    if (g_dbg_host & 32) return 0;
+  } else {
+    FreezeParams fp;
+    fp.packed = (const uint8_t*)packed; fp.saved = (const uint8_t*)saved; fp.g_out = g_out; fp.dy = (uint8_t*)workspace;
+    fp.flat_grad = flat_grad; fp.P = n_pts; fp.n_tiles = n_tiles; fp.train_roughness = freeze_mode == 1;
+    const int smem = ACT_BYTES + 2048 + 1024;
+    IBLN_CUDA(cudaFuncSetAttribute(mlp_dgrad_freeze_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    long long grid = n_tiles < 2LL * sms ? n_tiles : 2LL * sms;
+    mlp_dgrad_freeze_kernel<<<(unsigned)grid, 128, smem, stream>>>(fp);
+    IBLN_CUDA(cudaGetLastError());
+  }
   // ---- all weight-gradient GEMMs in one persistent launch
-  static const WgradParams job_table = make_wgrad_jobs();
-  WgradParams wp = job_table;
+  static const WgradParams job_tables[3] = {make_wgrad_jobs(0), make_wgrad_jobs(1), make_wgrad_jobs(2)};
+  WgradParams wp = job_tables[freeze_mode];
   wp.sv = (const uint8_t*)saved; wp.dy = (const uint8_t*)workspace; wp.flat = flat_grad; wp.n_tiles = n_tiles;
   IBLN_CUDA(cudaFuncSetAttribute(mlp_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_REQUEST));
   long long pairs = sms / 2;

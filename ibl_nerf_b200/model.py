@@ -38,7 +38,15 @@ class _MLPTc(torch.autograd.Function):
         ctx.packed, ctx.stash, ctx.P = packed, saved, P
         ctx.sink = getattr(net, "_grad_sink", None)
         ctx.shapes = [p.shape for p in params]
-        ctx.need = [p.requires_grad for p in params]
+        # forward_freezed (ibl_nerf.py:88-152): with freeze_radiance only these layers are outside torch.no_grad()
+        ctx.freeze = 0 if not net.freeze_radiance else (2 if net.freeze_roughness else 1)
+        trainable = None
+        if ctx.freeze:
+            names = {"albedo_feature_linear", "albedo_linear", "irradiance_feature_linear", "irradiance_linear"}
+            if ctx.freeze == 1:
+                names.add("roughness_linear")
+            trainable = [name in names for name, _, _ in mlp.PARAM_ORDER for _ in (0, 1)]
+        ctx.need = [p.requires_grad and (trainable is None or trainable[i]) for i, p in enumerate(params)]
         return out
 
     @staticmethod
@@ -50,7 +58,7 @@ class _MLPTc(torch.autograd.Function):
         # accumulates straight into the optimizer's flat buffer and autograd sees no per-tensor gradients.
         flat = ctx.sink if ctx.sink is not None else torch.zeros(FLAT_PARAMS, dtype=torch.float32, device=dev)
         ws = torch.empty(h.ibln_mlp_bwd_workspace_bytes(ctx.P), dtype=torch.uint8, device=dev)
-        call("ibln_mlp_bwd", dev, ptr(ctx.packed), ptr(ctx.stash), ptr(g_out), ctx.P, ptr(flat), ptr(ws),
+        call("ibln_mlp_bwd", dev, ptr(ctx.packed), ptr(ctx.stash), ptr(g_out), ctx.P, ptr(flat), ptr(ws), ctx.freeze,
              flops=2.0 * ctx.P * FLOP_FULL)
         ctx.stash = None
         if ctx.sink is not None:
@@ -155,9 +163,9 @@ class IBLNeRF(nn.Module):
         return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
 
     def _tc_grad_ok(self):
-        """Gradient passes run on the tensor-core backward unless a freeze mode is active (forward_freezed,
-        ibl_nerf.py:88-152, trains only a few heads: handled by the fp32 path)."""
-        return self.effective_precision() == "bf16" and not self.freeze_radiance
+        """Gradient passes run on the tensor-core backward, including the freeze modes of forward_freezed
+        (ibl_nerf.py:88-152: only the albedo / irradiance / roughness heads train)."""
+        return self.effective_precision() == "bf16"
 
     def query_points(self, pts, viewdirs):
         """run_network semantics: pts [N,S,3], viewdirs [N,3] or None -> [N,S,18] / [N,S,1]."""

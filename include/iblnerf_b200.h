@@ -183,13 +183,16 @@ int64_t ibln_mlp_saved_bytes(int64_t n_pts);
 int ibln_mlp_fwd(const void* packed, int mode, const float* pts, const float* rays_o, const float* rays_d,
                  const float* z, int64_t n_rays, int n_samples, float eps, int sigma_only,
                  float* out, void* saved, int device, void* stream);
-/* Backward (dgrad chain kernel + split-K wgrad kernels): g_out [P,18]; ACCUMULATES (red.global.add) into the
+/* Backward (dgrad chain kernel + one persistent wgrad kernel): g_out [P,18]; ACCUMULATES (red.global.add) into the
  * flat fp32 gradient image flat_grad (798 994 floats, state-dict order, each tensor row-major: weight then
  * bias per Linear).  `saved` is the stash written by ibln_mlp_fwd for the same points;
- * workspace >= ibln_mlp_bwd_workspace_bytes(P) (per-layer dY tiles). */
+ * workspace >= ibln_mlp_bwd_workspace_bytes(P) (per-layer dY tiles).
+ * freeze_mode mirrors IBLNeRF.forward_freezed (ibl_nerf.py:88-152, train.py:275-283): 0 = everything trains;
+ * 1 = freeze_radiance (only albedo/irradiance feature layers + heads and the roughness head get gradients);
+ * 2 = freeze_radiance + freeze_roughness (roughness head frozen too).  Frozen entries of flat_grad are untouched. */
 int64_t ibln_mlp_bwd_workspace_bytes(int64_t n_pts);
 int ibln_mlp_bwd(const void* packed, const void* saved, const float* g_out, int64_t n_pts,
-                 float* flat_grad, void* workspace, int device, void* stream);
+                 float* flat_grad, void* workspace, int freeze_mode, int device, void* stream);
 
 /* ---- training-step tail ------------------------------------------------------ */
 

@@ -56,6 +56,34 @@ def test_fp32_mlp_freeze_modes():
     assert coarse.roughness_linear.weight.grad is None
 
 
+@pytest.mark.parametrize("freeze_roughness", [False, True])
+def test_tc_freeze_mode_backward_matches_fp32_path(freeze_roughness):
+    """forward_freezed gradients (ibl_nerf.py:88-152) on the tensor-core backward vs the exact fp32 SIMT path:
+    same trainable set, per-tensor rel. L2 <= 4e-2 (bf16 operands), frozen parameters get no gradient."""
+    grads = {}
+    g = torch.Generator().manual_seed(11)
+    pts = (torch.rand(40, 24, 3, generator=g) * 4 - 2).to(DEV)
+    vd = torch.randn(40, 3, generator=g).to(DEV)
+    go = torch.randn(40, 24, 18, generator=g).to(DEV)
+    for prec in ("bf16", "fp32"):
+        net, _ = build_nets(DEV, structured=True, precision=prec)
+        net.freeze_radiance, net.freeze_roughness = True, freeze_roughness
+        q = ib.NetworkQuery(ib.get_embedder(10)[0], ib.get_embedder(4)[0], 65536)
+        (q(pts, vd, net) * go).sum().backward()
+        grads[prec] = {k: p.grad for k, p in net.named_parameters()}
+    want = {"albedo_feature_linear", "albedo_linear", "irradiance_feature_linear", "irradiance_linear"}
+    if not freeze_roughness:
+        want.add("roughness_linear")
+    for k, ref in grads["fp32"].items():
+        got = grads["bf16"][k]
+        if k.rsplit(".", 1)[0] in want:
+            assert got is not None and ref is not None, k
+            err = (got - ref).norm() / (ref.norm() + 1e-12)
+            assert err < 4e-2, (k, err.item())
+        else:
+            assert got is None and ref is None, k
+
+
 @pytest.mark.parametrize("n,k", [(128, 64), (256, 256), (128, 128)])
 def test_umma_selftest(n, k):
     gen = torch.Generator().manual_seed(n + k)
@@ -234,7 +262,7 @@ def test_tc_stash_and_dgrad_tiles():
     flat = torch.zeros(798994, device=DEV)
     ws = torch.zeros(h.ibln_mlp_bwd_workspace_bytes(P), dtype=torch.uint8, device=DEV)
     g_d = g.to(DEV)
-    call("ibln_mlp_bwd", out.device, ptr(packed), ptr(stash), ptr(g_d), P, ptr(flat), ptr(ws))
+    call("ibln_mlp_bwd", out.device, ptr(packed), ptr(stash), ptr(g_d), P, ptr(flat), ptr(ws), 0)
     torch.cuda.synchronize()
     for name, blk, nblk, cols, ref in (("addf01", 0, 4, 256, addf_pre.grad[:, :256]), ("addf2", 4, 2, 128, addf_pre.grad[:, 256:]),
                                        ("view", 6, 4, 256, hv_pre.grad), ("feat", 10, 4, 256, feat_f.grad), ("af", 14, 4, 256, af_pre.grad),

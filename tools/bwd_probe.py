@@ -22,7 +22,7 @@ g = torch.randn(P, 18, device=dev)
 packed = net.packed_weights()
 call("ibln_mlp_fwd", dev, ptr(packed), 1, None, ptr(o), ptr(d), ptr(z), n, s, 0.0, 0, ptr(out), ptr(stash))
 def run():
-    call("ibln_mlp_bwd", dev, ptr(packed), ptr(stash), ptr(g), P, ptr(flat), ptr(ws))
+    call("ibln_mlp_bwd", dev, ptr(packed), ptr(stash), ptr(g), P, ptr(flat), ptr(ws), 0)
 for flags, name in ((0, "dgrad+wgrad"), (32, "dgrad only"),  (16, "wgrad only")):
     h.ibln_debug_set(flags)
     for _ in range(2): run()

@@ -22,5 +22,5 @@ g = torch.randn(P, 18, device=dev)
 packed = net.packed_weights()
 for _ in range(2):
     call("ibln_mlp_fwd", dev, ptr(packed), 1, None, ptr(o), ptr(d), ptr(z), n, s, 0.0, 0, ptr(out), ptr(stash))
-    call("ibln_mlp_bwd", dev, ptr(packed), ptr(stash), ptr(g), P, ptr(flat), ptr(ws))
+    call("ibln_mlp_bwd", dev, ptr(packed), ptr(stash), ptr(g), P, ptr(flat), ptr(ws), 0)
 torch.cuda.synchronize()

@@ -23,11 +23,11 @@ g = torch.randn(P, 18, device=dev)
 packed = net.packed_weights()
 call("ibln_mlp_fwd", dev, ptr(packed), 1, None, ptr(o), ptr(d), ptr(z), n, s, 0.0, 0, ptr(out), ptr(stash))
 h.ibln_debug_set(32)
-call("ibln_mlp_bwd", dev, ptr(packed), ptr(stash), ptr(g), P, ptr(flat), ptr(ws))
+call("ibln_mlp_bwd", dev, ptr(packed), ptr(stash), ptr(g), P, ptr(flat), ptr(ws), 0)
 torch.cuda.synchronize()
 tl = torch.zeros(3072, dtype=torch.int64, device=dev)
 h.ibln_debug_timeline(ctypes.c_void_p(tl.data_ptr()))
-call("ibln_mlp_bwd", dev, ptr(packed), ptr(stash), ptr(g), P, ptr(flat), ptr(ws))
+call("ibln_mlp_bwd", dev, ptr(packed), ptr(stash), ptr(g), P, ptr(flat), ptr(ws), 0)
 torch.cuda.synchronize()
 h.ibln_debug_timeline(None)
 t = tl.cpu().tolist()
