@@ -120,3 +120,53 @@ extern "C" int ibln_adam_step(float* param, const float* grad, float* exp_avg, f
                                                                                   beta1, beta2, eps, inv_sqrt_bc2, grad_scale);
   IBLN_RETURN_LAST();
 }
+
+// ---------------------------------------------------------------- ray generation + target gather
+// One launch per training batch instead of ~15 small ATen launches: get_rays_few (nerf_renderer_helper.py:14-23)
+// for N random pixels of one image + NerfDataset.get_info pixel gathers (dataset_interface.py:178-197) of the
+// target image and its prefiltered copies.
+namespace ibln {
+struct GatherArgs { const float* img[8]; float* out[8]; int ch[8]; int n_img; };
+__global__ void __launch_bounds__(256)
+sample_rays_kernel(const int* __restrict__ u, const int* __restrict__ v, int n, int H, int W, float fx, float fy, float cx,
+                   float cy, const float* __restrict__ c2w /* [3,4] row-major */, float* __restrict__ rays_o,
+                   float* __restrict__ rays_d, GatherArgs ga) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const int ui = u[r], vi = v[r];
+  // dirs = ((i - cx)/fx, -(j - cy)/fy, -1);  rays_d = sum_k dirs[k] * c2w[:, k]  (un-contracted, summed k = 0,1,2)
+  const float d0 = __fdiv_rn(__fsub_rn((float)ui, cx), fx);
+  const float d1 = -__fdiv_rn(__fsub_rn((float)vi, cy), fy);
+  const float d2 = -1.0f;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float s = __fadd_rn(__fadd_rn(__fmul_rn(d0, c2w[4 * a]), __fmul_rn(d1, c2w[4 * a + 1])), __fmul_rn(d2, c2w[4 * a + 2]));
+    rays_d[3 * r + a] = s;
+    rays_o[3 * r + a] = c2w[4 * a + 3];
+  }
+  const bool inside = ui >= 0 && ui < W && vi >= 0 && vi < H;
+  for (int k = 0; k < ga.n_img; ++k) {
+    const int ch = ga.ch[k];
+    const float* src = ga.img[k] + ((size_t)vi * W + ui) * ch;      // height is first (image[v, u, :])
+    for (int c = 0; c < ch; ++c) ga.out[k][(size_t)r * ch + c] = inside ? src[c] : 0.f;
+  }
+}
+}  // namespace ibln
+
+extern "C" int ibln_sample_rays(const int* u, const int* v, int n, int height, int width, float fx, float fy, float cx, float cy,
+                                const float* c2w, float* rays_o, float* rays_d, const float* const* images,
+                                float* const* outputs, const int* channels, int n_images, int device, void* stream) {
+  if (n == 0) return 0;
+  if (n < 0 || !u || !v || !c2w || !rays_o || !rays_d || n_images < 0 || n_images > 8 || height < 1 || width < 1) return IBLN_EINVAL;
+  if (n_images > 0 && (!images || !outputs || !channels)) return IBLN_EINVAL;
+  ibln::GatherArgs ga;
+  ga.n_img = n_images;
+  for (int k = 0; k < n_images; ++k) {
+    if (!images[k] || !outputs[k] || channels[k] < 1) return IBLN_EINVAL;
+    ga.img[k] = images[k]; ga.out[k] = outputs[k]; ga.ch[k] = channels[k];
+  }
+  DeviceGuard g(device);
+  ibln::sample_rays_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(u, v, n, height, width, fx, fy, cx, cy, c2w, rays_o,
+                                                                             rays_d, ga);
+  IBLN_RETURN_LAST();
+}

@@ -71,3 +71,37 @@ def sample_pdf(bins, weights, N_samples, det=False, pytest=False):
     b2, w2 = bins.reshape(-1, bins.shape[-1]), weights.reshape(-1, weights.shape[-1])
     u = sample_u(b2.shape[0], N_samples, det, pytest, device=bins.device)
     return ops.sample_pdf_u(b2, w2, u).reshape(*lead, N_samples)
+
+
+def sample_training_rays(u, v, K, c2w, images):
+    """One-launch replacement of the per-iteration ray generation + target gather of the reference's sample
+    generator (utils/generator_utils.py:108-142 -> get_rays_few + NerfDataset.get_info): pixel columns `u`, rows `v`
+    (int tensors or numpy arrays, N each) of one training view with intrinsics K [3,3] and pose c2w [3,4];
+    `images` = dict name -> device image [H,W,C] of that view (rgb, rgb_1.., albedo, normal ...).
+    Returns (rays_o [N,3], rays_d [N,3], {name: [N,C]})."""
+    import ctypes
+    from ._lib import call, ptr
+    names = list(images)
+    first = images[names[0]] if names else None
+    dev = first.device if first is not None else torch.as_tensor(c2w).device
+    to_i32 = lambda x: torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x).to(device=dev, dtype=torch.int32).contiguous()
+    u, v = to_i32(u), to_i32(v)
+    n = u.shape[0]
+    c2w = torch.as_tensor(c2w, dtype=torch.float32, device=dev)[:3, :4].contiguous()
+    imgs = [images[k] if (images[k].dtype == torch.float32 and images[k].is_contiguous()) else images[k].float().contiguous() for k in names]
+    imgs = [im if im.dim() == 3 else im[..., None] for im in imgs]
+    H, W = (imgs[0].shape[0], imgs[0].shape[1]) if imgs else (1 << 30, 1 << 30)
+    outs = [torch.empty(n, im.shape[2], dtype=torch.float32, device=dev) for im in imgs]
+    rays_o = torch.empty(n, 3, dtype=torch.float32, device=dev)
+    rays_d = torch.empty(n, 3, dtype=torch.float32, device=dev)
+    k = len(imgs)
+    ip = (ctypes.c_void_p * max(k, 1))(*[ctypes.c_void_p(im.data_ptr()) for im in imgs])
+    op = (ctypes.c_void_p * max(k, 1))(*[ctypes.c_void_p(o.data_ptr()) for o in outs])
+    ch = (ctypes.c_int * max(k, 1))(*[im.shape[2] for im in imgs])
+    Kf = [[float(K[a][b]) for b in range(3)] for a in range(2)]
+    call("ibln_sample_rays", dev, ptr(u), ptr(v), n, int(H), int(W), Kf[0][0], Kf[1][1], Kf[0][2], Kf[1][2], ptr(c2w), ptr(rays_o),
+         ptr(rays_d), ip, op, ch, k)
+    res = {}
+    for name, o, im0 in zip(names, outs, [images[kk] for kk in names]):
+        res[name] = o if im0.dim() == 3 else o[:, 0]
+    return rays_o, rays_d, res

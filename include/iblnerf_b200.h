@@ -213,6 +213,15 @@ int ibln_phase_b_loss(const float* maps_srgb, const float* shade_srgb, const flo
 int ibln_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                    float beta1, float beta2, float eps, int step, float grad_scale, int device, void* stream);
 
+/* Ray generation + target gather for one training batch: get_rays_few
+ * (nerf_renderer_helper.py:14-23) for pixels (u[i], v[i]) of a camera (intrinsics fx, fy, cx, cy; c2w [3,4]
+ * row-major, device) -> rays_o, rays_d [N,3], and NerfDataset.get_info pixel gathers
+ * (dataset_interface.py:178-197): outputs[k][i,:] = images[k][v[i], u[i], :] for n_images (<= 8) device images
+ * [H,W,channels[k]].  images / outputs / channels are HOST arrays (of device pointers / ints). */
+int ibln_sample_rays(const int* u, const int* v, int n, int height, int width, float fx, float fy, float cx, float cy,
+                     const float* c2w, float* rays_o, float* rays_d, const float* const* images,
+                     float* const* outputs, const int* channels, int n_images, int device, void* stream);
+
 /* Self-test of the tcgen05 building block: D[128,N] = A[128,K] * B[N,K]^T with bf16 inputs staged
  * through the same swizzled shared-memory layout the MLP kernels use. a,b fp32 (rounded to bf16
  * inside), d fp32.  variant selects descriptor hypotheses (0 = production). */

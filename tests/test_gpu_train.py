@@ -80,3 +80,29 @@ def test_fused_train_step_matches_torch_tail():
     num = sum((a - b).double().pow(2).sum() for a, b in zip(runs[0][1], runs[1][1])).sqrt().item()
     upd = sum((a - b).double().pow(2).sum() for a, b in zip(runs[1][1], runs[1][2])).sqrt().item()
     assert upd > 0 and num <= 0.05 * upd, (num, upd)
+
+
+def test_sample_training_rays_matches_reference_ops():
+    """ibln_sample_rays == get_rays_few (nerf_renderer_helper.py:14-23) + NerfDataset.get_info gathers
+    (dataset_interface.py:178-197) on a synthetic view: rays bit-exact, targets exact copies."""
+    import math
+    import numpy as np
+    from ibl_nerf_b200 import helper
+    H, W, n = 96, 128, 4096
+    g = torch.Generator().manual_seed(8)
+    images = {"rgb": torch.rand(H, W, 3, generator=g).to(DEV), "rgb_1": torch.rand(H, W, 3, generator=g).to(DEV),
+              "rgb_2": torch.rand(H, W, 3, generator=g).to(DEV), "rgb_3": torch.rand(H, W, 3, generator=g).to(DEV),
+              "roughness": torch.rand(H, W, generator=g).to(DEV)}
+    focal = .5 * W / math.tan(.5 * math.radians(60))
+    K = np.array([[focal, 0, .5 * W], [0, focal, .5 * H], [0, 0, 1]], np.float32)
+    a = 0.7
+    c2w = torch.tensor([[math.cos(a), 0.1, math.sin(a), 1.5], [0., 1., 0.2, -0.3], [-math.sin(a), 0.05, math.cos(a), 2.0]])
+    rs = np.random.RandomState(0)
+    u, v = rs.randint(0, W, n), rs.randint(0, H, n)          # generator_utils.py:108-109
+    ro, rd, tg = helper.sample_training_rays(u, v, K, c2w.to(DEV), images)
+    uv = torch.tensor(np.stack([u, v], 1), dtype=torch.float32)
+    want_o, want_d = helper.get_rays_few(uv, K, c2w)          # torch CPU, the reference's expression
+    close(rd, want_d, rtol=1e-6, atol=1e-7, name="rays_d")
+    assert torch.equal(ro.cpu(), want_o.contiguous())
+    for k, im in images.items():
+        assert torch.equal(tg[k].cpu(), im.cpu()[v, u]), k
