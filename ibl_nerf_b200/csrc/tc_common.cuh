@@ -162,12 +162,15 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// one arrival on the barrier at the same shared-memory offset in CTA `cta` of the cluster
+// one arrival on the barrier at the same shared-memory offset in CTA `cta` of the cluster.  Default (cta-scope)
+// release like CUTLASS' ClusterBarrier::arrive(cta_id): the callers have already made their shared-memory writes
+// visible to the async proxy (fence.proxy.async) and fenced their TMEM reads (tcgen05.fence::before_thread_sync);
+// a cluster-scope release would add MEMBAR.GPU + ERRBAR to every publish (12 % of the sigma kernel's samples).
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
       ::"r"(smem_u32(bar)), "r"(cta)
       : "memory");
 }

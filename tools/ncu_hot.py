@@ -3,10 +3,11 @@
 import csv, subprocess, sys
 rep, kern = sys.argv[1], sys.argv[2]
 topn = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+blk = int(sys.argv[4]) if len(sys.argv) > 4 else 0          # which matching launch / view (SASS and source views alternate)
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kern], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hi = [i for i, r in enumerate(rows) if r and r[0] == "Address"]
-start = hi[0]; end = hi[1] - 1 if len(hi) > 1 else len(rows)
+start = hi[blk]; end = hi[blk + 1] - 1 if len(hi) > blk + 1 else len(rows)
 h = rows[start]
 si = h.index("Warp Stall Sampling (All Samples)"); ii = h.index("Instructions Executed"); src = h.index("Source")
 body = [r for r in rows[start + 1:end] if len(r) > si and r[si].isdigit()]
