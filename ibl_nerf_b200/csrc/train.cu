@@ -170,3 +170,42 @@ extern "C" int ibln_sample_rays(const int* u, const int* v, int n, int height, i
                                                                              rays_d, ga);
   IBLN_RETURN_LAST();
 }
+
+// ---------------------------------------------------------------- test-render export
+// to8b (nerf_renderer_helper.py:10) of all output maps of an image into ONE packed uint8 atlas: one launch and one
+// D2H copy instead of ~30 .cpu().numpy() + host conversions per image (ibl_nerf_renderer.py:840-900).
+// transform 0: identity; 1: (x + 1) / 2 (normal / tangent maps); 2: 1 / max(1e-10, x / scale) (depth maps).
+namespace ibln {
+struct PackArgsU8 { const float* src[32]; long long off[33]; int transform[32]; float scale[32]; int n; };
+__global__ void __launch_bounds__(256) pack_u8_kernel(PackArgsU8 a, uint8_t* __restrict__ out) {
+  const long long total = a.off[a.n];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int k = 0;
+    while (i >= a.off[k + 1]) ++k;
+    float x = a.src[k][i - a.off[k]];
+    if (a.transform[k] == 1) x = __fmul_rn(__fadd_rn(x, 1.0f), 0.5f);
+    else if (a.transform[k] == 2) x = __fdiv_rn(1.0f, fmaxf(1e-10f, __fdiv_rn(x, a.scale[k])));
+    const float c = fminf(fmaxf(x, 0.0f), 1.0f);            // np.clip(x, 0, 1); NaN -> 0 after the cast, like numpy on x86
+    out[i] = (uint8_t)__fmul_rn(255.0f, c);                 // .astype(np.uint8) truncates
+  }
+}
+}  // namespace ibln
+
+extern "C" int ibln_pack_u8(const float* const* maps, const int64_t* sizes, const int* transforms, const float* scales, int n_maps,
+                            uint8_t* out, int device, void* stream) {
+  if (n_maps == 0) return 0;
+  if (n_maps < 0 || n_maps > 32 || !maps || !sizes || !transforms || !scales || !out) return IBLN_EINVAL;
+  ibln::PackArgsU8 a;
+  a.n = n_maps;
+  a.off[0] = 0;
+  for (int k = 0; k < n_maps; ++k) {
+    if (!maps[k] || sizes[k] < 0 || transforms[k] < 0 || transforms[k] > 2) return IBLN_EINVAL;
+    a.src[k] = maps[k]; a.off[k + 1] = a.off[k] + sizes[k]; a.transform[k] = transforms[k]; a.scale[k] = scales[k];
+  }
+  if (a.off[n_maps] == 0) return 0;
+  DeviceGuard g(device);
+  long long blocks = (a.off[n_maps] + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  ibln::pack_u8_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a, out);
+  IBLN_RETURN_LAST();
+}

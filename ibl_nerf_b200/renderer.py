@@ -12,6 +12,7 @@ import torch
 import torch.nn.functional as F
 
 from . import ops
+from ._lib import IblnError, call, f32c, ptr
 from .helper import get_rays, sample_u, to8b
 from .model import IBLNeRF, NetworkQuery
 
@@ -429,19 +430,73 @@ def render_decomp_path(dataset_test, hwf, K, chunk, render_kwargs, savedir=None,
     K = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]]).astype(np.float32)
     results = {}
 
+    # Export path.  The reference does ~30 x (.cpu().numpy() + to8b + PNG encode) per image on the
+    # render thread (ibl_nerf_renderer.py:840-900).  Here the maps of an image are queued, converted to uint8 by ONE
+    # kernel into a packed atlas (ibln_pack_u8), fetched with ONE pinned D2H copy each for the float values (the
+    # function's return value) and the atlas, and the PNGs are encoded by a small thread pool while the next image
+    # renders.  Values and PNG bytes are identical to the reference expression.
+    pending = []            # (out_name, index, tensor, transform, scale)
+    writers = []
+    pool = None
+    if savedir is not None:
+        from concurrent.futures import ThreadPoolExecutor
+        pool = ThreadPoolExecutor(max_workers=4)
+
     def append_result(res, key_name, index, out_name):
         img = res.get(key_name)
         if img is None:
             return
+        transform, scale = 0, 1.0
         if "normal" in out_name or 'tangent' in out_name:
-            img = (img + 1) * 0.5
+            transform = 1
         elif "depth" in key_name:
-            img = img / (dataset_test.far * 0.1)
-            img = 1. / torch.max(1e-10 * torch.ones_like(img), img)
-        results.setdefault(out_name, []).append(img.cpu().numpy())
+            transform, scale = 2, float(dataset_test.far * 0.1)
+        pending.append((out_name, index, img.detach() if torch.is_tensor(img) else img, transform, scale))
+
+    def flush(index):
+        if not pending:
+            return
+        import ctypes
+        cuda = [p[2] for p in pending if torch.is_tensor(p[2]) and p[2].is_cuda]
+        if not cuda:
+            raise IblnError("render_decomp_path needs CUDA tensors; there is no CPU path")
+        dev = cuda[0].device
+        for j, p in enumerate(pending):       # e.g. the host-side normal-from-depth map of the reference's utils
+            if not (torch.is_tensor(p[2]) and p[2].is_cuda):
+                pending[j] = (p[0], p[1], torch.as_tensor(p[2], dtype=torch.float32).to(dev), p[3], p[4])
+        vals = []
+        for out_name, _, img, transform, scale in pending:      # float values exactly as the reference computes them
+            if transform == 1:
+                img = (img + 1) * 0.5
+            elif transform == 2:
+                img = img / scale
+                img = 1. / torch.max(1e-10 * torch.ones_like(img), img)
+            vals.append(f32c(img))
+        sizes = [v.numel() for v in vals]
+        flat = torch.cat([v.reshape(-1) for v in vals])
+        host = torch.empty(flat.shape, dtype=torch.float32, pin_memory=True)
+        host.copy_(flat, non_blocking=True)
+        atlas_h = None
         if savedir is not None:
-            import imageio
-            imageio.imwrite(os.path.join(savedir, (out_name + '_{:03d}.png').format(index)), to8b(results[out_name][-1]))
+            srcs = [f32c(p[2]) for p in pending]
+            k = len(srcs)
+            atlas = torch.empty(sum(sizes), dtype=torch.uint8, device=dev)
+            call("ibln_pack_u8", dev, (ctypes.c_void_p * k)(*[ctypes.c_void_p(t.data_ptr()) for t in srcs]),
+                 (ctypes.c_int64 * k)(*sizes), (ctypes.c_int * k)(*[p[3] for p in pending]),
+                 (ctypes.c_float * k)(*[p[4] for p in pending]), k, ptr(atlas))
+            atlas_h = torch.empty(atlas.shape, dtype=torch.uint8, pin_memory=True)
+            atlas_h.copy_(atlas, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        arr, a8 = host.numpy(), (atlas_h.numpy() if atlas_h is not None else None)
+        off = 0
+        for (out_name, idx, img, _, _), v, n in zip(pending, vals, sizes):
+            results.setdefault(out_name, []).append(arr[off:off + n].reshape(tuple(v.shape)).copy())
+            if savedir is not None:
+                import imageio
+                png = a8[off:off + n].reshape(tuple(v.shape)).copy()
+                writers.append(pool.submit(imageio.imwrite, os.path.join(savedir, (out_name + '_{:03d}.png').format(idx)), png))
+            off += n
+        pending.clear()
 
     try:
         from tqdm import tqdm
@@ -474,4 +529,9 @@ def render_decomp_path(dataset_test, hwf, K, chunk, render_kwargs, savedir=None,
                 append_result(res, "normal_map_from_depth_map", i, "normal_from_depth")
             except ImportError:
                 pass
+        flush(i)
+    for w in writers:
+        w.result()
+    if pool is not None:
+        pool.shutdown()
     return {k: np.stack(v, 0) for k, v in results.items()}

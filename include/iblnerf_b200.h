@@ -222,6 +222,13 @@ int ibln_sample_rays(const int* u, const int* v, int n, int height, int width, f
                      const float* c2w, float* rays_o, float* rays_d, const float* const* images,
                      float* const* outputs, const int* channels, int n_images, int device, void* stream);
 
+/* Test-render export: to8b (nerf_renderer_helper.py:10) of n_maps (<= 32) fp32 device maps into one
+ * packed uint8 atlas (map k at offset sum(sizes[:k])).  transforms[k]: 0 identity, 1 (x+1)/2 (normal maps),
+ * 2 1/max(1e-10, x/scales[k]) (depth maps), as in ibl_nerf_renderer.py:840-848.  maps/sizes/transforms/scales are
+ * HOST arrays. */
+int ibln_pack_u8(const float* const* maps, const int64_t* sizes, const int* transforms, const float* scales, int n_maps,
+                 uint8_t* out, int device, void* stream);
+
 /* Self-test of the tcgen05 building block: D[128,N] = A[128,K] * B[N,K]^T with bf16 inputs staged
  * through the same swizzled shared-memory layout the MLP kernels use. a,b fp32 (rounded to bf16
  * inside), d fp32.  variant selects descriptor hypotheses (0 = production). */

@@ -152,3 +152,51 @@ def test_full_size_mlp_properties():
     assert torch.equal(sub, a[1000:1010])                      # a point's result does not depend on its tile neighbours
     assert torch.allclose(sig[..., 0], a[..., 0], rtol=1e-5, atol=1e-5)   # sigma-only program == channel 0 of the full program
     assert torch.isfinite(a).all()
+
+
+def test_render_decomp_path_export(tmp_path):
+    """Export path (ibl_nerf_renderer.py:819-910): returned float stacks == the maps of render_decomp, PNG files ==
+    to8b of them (uint8 atlas kernel + batched D2H + threaded PNG writers)."""
+    import os
+    import sys
+    import numpy as np
+    try:
+        import imageio
+    except ImportError:
+        sys.path.append(os.path.join(os.path.dirname(os.path.abspath(ib.__file__)), "shims"))
+        import imageio
+    coarse, fine = build_nets(DEV, structured=True, precision="bf16")
+    lut = fx.load_lut().to(DEV)
+    kw = kwargs_for(coarse, fine, lut, perturb=0., pytest=False)
+    kw["coarse_radiance_number"] = 3
+    H, W, focal = 12, 16, 14.0
+
+    class FakeTestSet:
+        far = fx.FAR
+        poses = [torch.tensor([[1., 0., 0., 0.1], [0., 1., 0., 0.], [0., 0., 1., 2.0]], device=DEV),
+                 torch.tensor([[0., 0., 1., 1.0], [0., 1., 0., 0.2], [-1., 0., 0., 0.5]], device=DEV)]
+
+        def get_resized_normal_albedo(self, factor, i):
+            return {}
+
+    kw2 = {k: v for k, v in kw.items() if k not in ("near", "far")}
+    with torch.no_grad():           # as test.py:140-150 does
+        out = ib.render_decomp_path(FakeTestSet(), (H, W, focal), None, 1 << 16, kw2, savedir=str(tmp_path), near=fx.NEAR,
+                                    far=fx.FAR, approximate_radiance=True)
+    K = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]]).astype(np.float32)
+    for i, c2w in enumerate(FakeTestSet.poses):
+        with torch.no_grad():
+            res = ib.render_decomp(H, W, K, chunk=1 << 16, c2w=c2w[:3, :4], gt_values={}, near=fx.NEAR, far=fx.FAR,
+                                   approximate_radiance=True, **kw2)
+        for key, name in (("color_map", "rgb"), ("radiance_map", "radiance"), ("albedo_map", "albedo"), ("roughness_map", "roughness")):
+            want = res[key].cpu().numpy()
+            assert np.array_equal(out[name][i], want), name
+            png = imageio.imread(os.path.join(str(tmp_path), "%s_%03d.png" % (name, i)))
+            assert np.array_equal(png, (255 * np.clip(want, 0, 1)).astype(np.uint8)), name
+        want = ((res["target_normal_map"] + 1) * 0.5).cpu().numpy()
+        assert np.array_equal(out["target_normal_map"][i], want)
+        d = res["depth_map"] / (fx.FAR * 0.1)
+        want = (1. / torch.max(1e-10 * torch.ones_like(d), d)).cpu().numpy()
+        assert np.array_equal(out["depth"][i], want)
+        png = imageio.imread(os.path.join(str(tmp_path), "depth_%03d.png" % i))
+        assert np.array_equal(png, (255 * np.clip(want, 0, 1)).astype(np.uint8))
