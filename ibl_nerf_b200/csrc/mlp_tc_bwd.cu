@@ -528,7 +528,11 @@ constexpr int WG_NSTAGES = 8;
 constexpr int WG_SMEM_ONES = WG_NSTAGES * WG_STAGE_BYTES;  // [WG_STAGE_PTS rows][64] ones tile
 constexpr int WG_SMEM_BAR = WG_SMEM_ONES + WG_BLK_BYTES;
 constexpr int WG_SMEM_REQUEST = WG_SMEM_BAR + 256 + 1024;
-constexpr int WG_THREADS = 192;                  // warp 0 producer, warp 1 MMA, warps 2-5 epilogue
+// warps 0..3 producers (stage i of the running stage counter belongs to producer i % 4: one thread issuing the
+// 3-6 bulk copies of every 32-point slice was the pacing item -- ncu: the lone producer busy 85 % of the time, the
+// MMA thread waiting for data 55 %), warp 4 MMA, warps 5-8 epilogue
+constexpr int WG_PRODUCERS = 4;
+constexpr int WG_THREADS = (WG_PRODUCERS + 5) * 32;
 
 // tile range [t0, t1) and m-half of job j for CTA (pair, r); pairs = number of CTA pairs in the grid
 struct WSeg { long long t0, t1; int cls; };
@@ -571,7 +575,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) mlp_wgrad_kernel(const __grid_c
     mbar_init(acc_free, 4);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_ptr, 512);
+  if (warp == WG_PRODUCERS) tmem_alloc(tmem_ptr, 512);
   // ones tile: column 0 of every row = 1.0 (bf16), everything else 0
   for (int e = threadIdx.x; e < WG_STAGE_PTS * 8; e += blockDim.x) {
     int rr = e >> 3, c16 = e & 7;
@@ -583,9 +587,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) mlp_wgrad_kernel(const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == 0) {
+  if (warp < WG_PRODUCERS) {
     if (elect_one()) {
-      long long i = 0, job_start = 0;           // i: running tile counter of this CTA (ring position)
+      long long i = 0, job_start = 0;           // i: running stage counter of this CTA (ring position)
       for (int j = 0; j < prm.n_jobs; ++j) {
         const WJob& jb = prm.job[j];
         const WSeg sg = wgrad_segment(prm, j, job_start, w_total, pair, pairs, r);
@@ -598,6 +602,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) mlp_wgrad_kernel(const __grid_c
           const uint8_t* a_src = a_base + (size_t)t * a_stride;
           const uint8_t* b_src = b_base + (size_t)t * b_stride;
           for (int q = 0; q < WG_SUB; ++q, ++i) {
+            if ((int)(i % WG_PRODUCERS) != warp) continue;
             const int stage = (int)(i % WG_NSTAGES);
             const uint32_t ph = (uint32_t)((i / WG_NSTAGES) & 1);
             mbar_wait(&empty[stage], ph ^ 1);
@@ -611,7 +616,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) mlp_wgrad_kernel(const __grid_c
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == WG_PRODUCERS) {
     if (elect_one()) {
       const uint32_t idesc1 = make_idesc_bf16(128, 64, 1, 1);   // whole 64-wide swizzle atom; only column 0 is non-zero
       const uint32_t ones_addr = smem_u32(smem + WG_SMEM_ONES);
@@ -684,7 +689,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) mlp_wgrad_kernel(const __grid_c
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) { __syncwarp(); tmem_dealloc(tmem_base, 512); }
+  if (warp == WG_PRODUCERS) { __syncwarp(); tmem_dealloc(tmem_base, 512); }
 }
 
 // the 21 GEMMs of one network's weight gradient (freeze = 0), or the 2-3 that remain in the freeze modes
