@@ -32,7 +32,21 @@ def _worker(rank, world, port, q):
     ts.allreduce_grads()
     want = [sum(r + 1 + i for r in range(world)) / world for i in range(2)]
     ok_grad = all(torch.allclose(p.grad, torch.full_like(p, w)) for p, w in zip(params, want))
-    q.put((rank, ok_cover, ok_grad))
+    # (3) the fused path: both networks' gradients live in ONE flat buffer (training.FlatParameters) that is
+    # all-reduced in place; the modules' p.grad views see the reduced values and the parameters stay views
+    torch.manual_seed(1)
+    nets = [training.IBLNeRF(**training.KITCHEN_ARCH) for _ in range(2)]
+    ref = [p.detach().clone() for net in nets for p in net.ordered_params()]
+    flat = training.FlatParameters(nets)
+    ok_flat = flat.n == 2 * 798994 and all(torch.equal(p.detach(), r) for p, r in
+                                           zip([p for net in nets for p in net.ordered_params()], ref))
+    flat.grad.fill_(float(rank + 1))
+    dist.all_reduce(flat.grad, op=dist.ReduceOp.SUM)
+    tot = float(sum(range(1, world + 1)))
+    ok_flat = ok_flat and all(bool((p.grad == tot).all()) and p.grad.data_ptr() >= flat.grad.data_ptr()
+                              for net in nets for p in net.parameters())
+    ok_flat = ok_flat and nets[1]._grad_sink.data_ptr() == flat.grad.data_ptr() + 4 * 798994
+    q.put((rank, ok_cover, ok_grad and ok_flat))
     dist.destroy_process_group()
 
 
