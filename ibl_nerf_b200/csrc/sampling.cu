@@ -54,16 +54,16 @@ constexpr int GUIDE_CELLS = 256;
 struct RaySmem {            // per-warp carve-up (floats)
   float* cdf;               // [nbins]
   float4* rec;              // [nbins + 1]
-  uint32_t* guide;          // [GUIDE_CELLS / 2] packed u16 inclusive counts
+  uint32_t* guide;          // [GUIDE_CELLS / 2 + 64] packed u16 inclusive counts (or byte histogram + pair table)
   float* bins;              // [nbins] staging copy (register-prefetching kernel only)
 };
-__host__ __device__ inline int ray_smem_floats(int nbins) { return 2 * ((nbins + 3) & ~3) + 4 * (nbins + 1) + GUIDE_CELLS / 2; }
+__host__ __device__ inline int ray_smem_floats(int nbins) { return 2 * ((nbins + 3) & ~3) + 4 * (nbins + 1) + GUIDE_CELLS / 2 + 64; }
 __device__ __forceinline__ RaySmem carve(float* base, int nbins) {
   RaySmem r;
   r.rec = reinterpret_cast<float4*>(base);
   r.cdf = base + 4 * (nbins + 1);
   r.guide = reinterpret_cast<uint32_t*>(r.cdf + ((nbins + 3) & ~3));
-  r.bins = reinterpret_cast<float*>(r.guide + GUIDE_CELLS / 2);
+  r.bins = reinterpret_cast<float*>(r.guide + GUIDE_CELLS / 2 + 64);
   return r;
 }
 
@@ -111,6 +111,61 @@ __device__ __forceinline__ float invert_one(const RaySmem& sm, float u, int* ind
   const uint16_t* g16 = reinterpret_cast<const uint16_t*>(sm.guide);
   const int m = guide_cell(u);
   int lo = m ? (int)g16[m - 1] : 0, hi = (int)g16[m];
+  while (lo < hi) {                       // only for samples whose cell holds cdf entries
+    const int mid = (lo + hi) >> 1;
+    if (sm.cdf[mid] <= u) lo = mid + 1; else hi = mid;
+  }
+  *ind_out = lo;
+  const float4 r = sm.rec[lo];
+  float den = __fsub_rn(r.y, r.x);
+  if (den < 1e-5f) den = 1.0f;
+  const float t = EXACT ? __fdiv_rn(__fsub_rn(u, r.x), den) : __fdividef(__fsub_rn(u, r.x), den);
+  return __fadd_rn(r.z, __fmul_rn(t, __fsub_rn(r.w, r.z)));
+}
+
+// nbins <= 64 variant (every shipped config): counts fit a byte, so the table is 256 packed (G[m] << 8 | G[m-1])
+// 16-bit entries built from two 32-bit histogram words per lane, and ONE 2-byte load gives a sample both ends of
+// its search range.  Uses guide[0..63] as the byte histogram and guide[64..191] for the pair table.
+__device__ __forceinline__ void warp_build_guide_small(const RaySmem& sm, const float* __restrict__ bins, int nbins, int lane) {
+  sm.guide[lane] = 0u;
+  sm.guide[lane + 32] = 0u;
+  __syncwarp();
+  for (int i = lane; i <= nbins; i += 32) {
+    const int below = max(i - 1, 0), above = min(i, nbins - 1);
+    sm.rec[i] = make_float4(sm.cdf[below], sm.cdf[above], bins[below], bins[above]);
+    if (i < nbins) {
+      const int c = guide_cell(sm.cdf[i]);
+      atomicAdd(&sm.guide[c >> 2], 1u << (8 * (c & 3)));
+    }
+  }
+  __syncwarp();
+  uint32_t w0 = sm.guide[2 * lane], w1 = sm.guide[2 * lane + 1];      // cells 8*lane .. 8*lane+7, one byte each
+  w0 += w0 << 8; w0 += w0 << 16;
+  w1 += w1 << 8; w1 += w1 << 16;
+  w1 += (w0 >> 24) * 0x01010101u;
+  uint32_t tot = w1 >> 24, inc = tot;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t v = __shfl_up_sync(FULL, inc, o);
+    if (lane >= o) inc += v;
+  }
+  const uint32_t base = inc - tot;            // entries in the cells before this lane's = G[8*lane - 1]
+  w0 += base * 0x01010101u;
+  w1 += base * 0x01010101u;
+  // pair table: entry m = G[m] << 8 | G[m-1]
+  const uint32_t prev0 = (w0 << 8) | base, prev1 = (w1 << 8) | (w0 >> 24);     // G[m-1] for the 4 cells of each word
+  uint32_t* pair = sm.guide + 64 + 4 * lane;
+  pair[0] = __byte_perm(prev0, w0, 0x5140);   // cells 0,1: bytes {prev0.0, w0.0, prev0.1, w0.1}
+  pair[1] = __byte_perm(prev0, w0, 0x7362);   // cells 2,3
+  pair[2] = __byte_perm(prev1, w1, 0x5140);
+  pair[3] = __byte_perm(prev1, w1, 0x7362);
+  __syncwarp();
+}
+template <bool EXACT>
+__device__ __forceinline__ float invert_one_small(const RaySmem& sm, float u, int* ind_out) {
+  const uint16_t* g16 = reinterpret_cast<const uint16_t*>(sm.guide + 64);
+  const uint32_t e = g16[guide_cell(u)];
+  int lo = (int)(e & 0xffu), hi = (int)(e >> 8);
   while (lo < hi) {                       // only for samples whose cell holds cdf entries
     const int mid = (lo + hi) >> 1;
     if (sm.cdf[mid] <= u) lo = mid + 1; else hi = mid;
@@ -231,9 +286,9 @@ sample_pdf_small_kernel(const float* __restrict__ bins, int64_t bins_stride, con
     return q;
   };
   int r = blockIdx.x * SP_WARPS + warp;
-  RayRegs cur = fetch(r);
-  for (; r < n; r += stride) {
-    const RayRegs nxt = fetch(r + stride);
+  RayRegs cur = fetch(r), nx1 = fetch(r + stride);     // two rays in flight: one ray (~400 warp instructions) does not
+  for (; r < n; r += stride) {                         // cover the loaded DRAM latency (ncu: 19 % of samples on the first use)
+    const RayRegs nx2 = fetch(r + 2 * stride);
     if (cdf_in != nullptr) {
       if (lane < nbins) rs.cdf[lane] = cur.w0;
       if (lane + 32 < nbins) rs.cdf[lane + 32] = cur.w1;
@@ -257,12 +312,12 @@ sample_pdf_small_kernel(const float* __restrict__ bins, int64_t bins_stride, con
     if (lane < nbins) rs.bins[lane] = cur.b0;
     if (lane + 32 < nbins) rs.bins[lane + 32] = cur.b1;
     __syncwarp();
-    warp_build_guide(rs, rs.bins, nbins, lane);
+    warp_build_guide_small(rs, rs.bins, nbins, lane);
     float* orow = samples + (int64_t)r * nsamp;
     float sv[4];
     int ind[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) sv[k] = invert_one<EXACT>(rs, cur.u[k], &ind[k]);
+    for (int k = 0; k < 4; ++k) sv[k] = invert_one_small<EXACT>(rs, cur.u[k], &ind[k]);
 #pragma unroll
     for (int k = 0; k < 4; ++k)
       if (lane + 32 * k < nsamp) {
@@ -270,7 +325,8 @@ sample_pdf_small_kernel(const float* __restrict__ bins, int64_t bins_stride, con
         if (inds_out != nullptr) inds_out[(int64_t)r * nsamp + lane + 32 * k] = ind[k];
       }
     __syncwarp();
-    cur = nxt;
+    cur = nx1;
+    nx1 = nx2;
   }
 }
 
