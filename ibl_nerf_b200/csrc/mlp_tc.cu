@@ -108,7 +108,8 @@ __device__ __forceinline__ void process_chunk(const EpiCtx& c, Heads& hd, const 
     const uint32_t m = (pm[0] & 0xffu) | ((pm[1] & 0xffu) << 8) | ((pm[2] & 0xffu) << 16) | (pm[3] << 24);
     mask_word = ~m;
   }
-  constexpr bool kWriteAct = KIND == K_RELU_ACT || KIND == K_L7_FULL || KIND == K_FEATURE || KIND == K_VIEW;
+  // (stash mode: the last step's features also go through the activation tile -- its A operand is dead by then)
+  constexpr bool kWriteAct = KIND == K_RELU_ACT || KIND == K_L7_FULL || KIND == K_FEATURE || KIND == K_VIEW || (STASH && KIND == K_ADD2);
   constexpr bool kNeedF32Relu = KIND != K_RELU_ACT && KIND != K_FEATURE;     // heads consume fp32 relu(h)
   if (kNeedF32Relu) {
 #pragma unroll
@@ -333,7 +334,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) mlp_fw
       for (int i = gtid; i < heads_n4(s); i += 128) dst[i] = __ldg(src + i);
     };
     auto publish = [&]() {
-      fence_proxy_async();
+      if (!STASH) fence_proxy_async();       // stash mode: the writers fenced before the group barrier already
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&act_ready[slot], 0);     // the leader's barrier counts both CTAs' warps
@@ -464,8 +465,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) mlp_fw
         }
       }
       // ---- tile boundary: free the slot's shared tables, start the next tile, then store this tile's outputs
-      if (STASH && gtid == 0) bulk_wait_read0();
+      if (STASH) fence_proxy_async();
       named_bar_sync(1 + slot, 128);         // everyone is done with the last step's bias row / head table
+      if (STASH) stash_tile(c.act, SV_ADDF + 4, 2);   // coarse-radiance feature 2 (written into the dead hv tile)
       tc_fence_before();                     // order this tile's TMEM reads before the next tile's act_ready arrival
       if (k + 2 < pair_tiles) begin_tile(nxt, k + 2, bias0);
       if (valid) {

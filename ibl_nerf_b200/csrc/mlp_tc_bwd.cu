@@ -279,12 +279,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) mlp_dg
       }
       // ---- phase writers for the CUDA-core produced gradient tiles
       // heads: 0 = coarse radiance 0|1 (256 cols), 1 = coarse radiance 2 (128 cols), 2 = albedo|irradiance features
+      // relu bit masks of the phase that writes the NEXT tile are fetched one phase ahead (the 32-byte row load is an
+      // exposed DRAM round trip otherwise).  Phase t >= 0 is step t; slot of the mask record it applies:
+      auto mask_slot = [](int t) { return t == 0 ? 11 : t == 1 ? 9 : t == 2 ? -1 : t == 3 ? 8 : t == 4 ? 7 : 11 - t; };
+      auto fetch_masks = [&](int mslot, uint4& a, uint4& b) {
+        a = b = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+        if (mslot >= 0 && real) {
+          a = __ldg(reinterpret_cast<const uint4*>(masks + mslot * 1024));
+          b = __ldg(reinterpret_cast<const uint4*>(masks + mslot * 1024) + 1);
+        }
+      };
+      uint4 cm0, cm1, nm0, nm1;               // masks of the current / next phase
+      fetch_masks(10, cm0, cm1);
+      fetch_masks(mask_slot(0), nm0, nm1);
       auto write_head_tile = [&](int which) {
         const int ncc = which == 1 ? 4 : 8;
-        const int mslot = which == 0 ? 10 : which == 1 ? 11 : 8;
-        uint4 mw0 = __ldg(reinterpret_cast<const uint4*>(masks + mslot * 1024));
-        uint4 mw1 = __ldg(reinterpret_cast<const uint4*>(masks + mslot * 1024) + 1);
-        const uint32_t mw[8] = {mw0.x, mw0.y, mw0.z, mw0.w, mw1.x, mw1.y, mw1.z, mw1.w};
+        const uint32_t mw[8] = {cm0.x, cm0.y, cm0.z, cm0.w, cm1.x, cm1.y, cm1.z, cm1.w};
         for (int cc = 0; cc < ncc; ++cc) {
           float v[32];
 #pragma unroll
@@ -341,22 +351,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) mlp_dg
         acc_phase ^= 1;
         tc_fence_after();
         tl_mark(tl, tl_base, tl_n, 10 + 2 * t);
+        cm0 = nm0; cm1 = nm1;
+        if (t + 1 < N_STEPS_BWD) fetch_masks(mask_slot(t + 1), nm0, nm1);
         pre_write();
         if (t == 0) { write_head_tile(1); publish(DY_ADDF2, 2, true); tl_mark(tl, tl_base, tl_n, 11 + 2 * t); continue; }
         if (t == 3) { write_head_tile(2); publish(DY_AF, 4, true); tl_mark(tl, tl_base, tl_n, 11 + 2 * t); continue; }
         // drain: t=1 -> dY_view (mask HV, + radiance term); t=2 -> dY_feat (no mask); t=4 -> dY_7 (+ sigma/rough terms);
         // t>=5 -> dY_{11-t} (mask h_{11-t})
-        const int mslot = t == 1 ? 9 : t == 2 ? -1 : t == 4 ? 7 : 11 - t;
         const int dblk = t == 1 ? DY_VIEW : t == 2 ? DY_FEAT : t == 4 ? DY_H(7) : DY_H(11 - t);
-        uint32_t mw[8];
-        if (mslot >= 0) {
-          uint4 mw0 = __ldg(reinterpret_cast<const uint4*>(masks + mslot * 1024));
-          uint4 mw1 = __ldg(reinterpret_cast<const uint4*>(masks + mslot * 1024) + 1);
-          mw[0] = mw0.x; mw[1] = mw0.y; mw[2] = mw0.z; mw[3] = mw0.w; mw[4] = mw1.x; mw[5] = mw1.y; mw[6] = mw1.z; mw[7] = mw1.w;
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) mw[i] = 0xffffffffu;
-        }
+        const uint32_t mw[8] = {cm0.x, cm0.y, cm0.z, cm0.w, cm1.x, cm1.y, cm1.z, cm1.w};
         const bool last = (t == N_STEPS_BWD - 1);
         auto chunk = [&](const uint32_t (&raw)[32], int cc) {
           float v[32];
