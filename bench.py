@@ -45,7 +45,7 @@ def synth_rays(n, seed, device="cpu", pin=False):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 20 ms DURING the timed regions (resident + end-to-end)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -53,7 +53,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                       "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
@@ -200,7 +200,6 @@ def main():
     _lib.PROFILE = {}
     sampler = ClockSampler(local) if rank == 0 else None
     ms_total = timed(step_resident, args.steps)
-    clocks = sampler.stop() if sampler else None
     prof = _lib.PROFILE
     _lib.PROFILE = None
     ms_step = ms_total / args.steps
@@ -210,6 +209,7 @@ def main():
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps) / args.steps
     e2e_val = world * n / (ms_e2e * 1e-3)
+    clocks = sampler.stop() if sampler else None
 
     if rank == 0:
         torch.cuda.synchronize()
