@@ -70,3 +70,27 @@ def test_sample_pdf_large_properties():
     assert torch.equal(s1, s2)
     assert (s1[:, 1:] >= s1[:, :-1] - 1e-5).all()
     assert (s1 >= mids[:, :1] - 1e-5).all() and (s1 <= mids[:, -1:] + 1e-5).all()
+
+
+@pytest.mark.parametrize("nbins,nsamp", [(63, 128), (191, 384), (511, 1024), (2, 5), (64, 33)])
+def test_inverse_cdf_bit_exact_vs_searchsorted(nbins, nsamp):
+    """Guide-table search == torch.searchsorted(cdf, u, right=True) bit-exact (north-star criterion), for skewed CDFs
+    (many entries inside one guide cell), repeated entries, and u hitting entries, 0 and 1 exactly."""
+    n = 257
+    g = torch.Generator().manual_seed(nbins)
+    w = torch.rand(n, nbins - 1, generator=g) ** 8                      # a few dominant bins, the rest ~1e-5 floor
+    w[::7] = 0.0                                                         # all-floor rays (uniform CDF)
+    pdf = (w + 1e-5) / (w + 1e-5).sum(-1, keepdim=True)
+    cdf = torch.cat([torch.zeros(n, 1), torch.cumsum(pdf, -1)], -1)
+    cdf[1::5, nbins // 2:] = cdf[1::5, nbins // 2:nbins // 2 + 1]        # plateaus: repeated entries
+    bins = torch.sort(torch.rand(n, nbins, generator=g) * 7 + 0.5, -1)[0]
+    u = torch.rand(n, nsamp, generator=g)
+    u[:, 0] = 0.0
+    u[:, -1] = 1.0
+    k = min(nsamp - 2, nbins)
+    u[:, 1:1 + k] = cdf[:, :k]                                           # exactly on entries
+    inds, samples = ib.ops.inverse_cdf(cdf.to(DEV), bins.to(DEV), u.to(DEV))
+    want = torch.searchsorted(cdf.contiguous(), u.contiguous(), right=True)
+    assert torch.equal(inds.cpu(), want)
+    _, want_s = orc.inverse_cdf(cdf, bins, u)
+    assert torch.equal(samples.cpu(), want_s)
