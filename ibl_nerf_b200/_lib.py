@@ -52,6 +52,7 @@ _PLAIN = {  # no device/stream tail
     "ibln_mlp_bwd_workspace_bytes": ([c_i64], c_i64),
 }
 
+ABI_VERSION = 2      # include/iblnerf_b200.h: IBLN_ABI_VERSION
 _lib = None
 # kernels launched per entry point (for bench.py's gpu_launches); default 1
 KERNELS_PER_CALL = {"ibln_sgemm_wgrad": 2, "ibln_mlp_pack_weights": 3, "ibln_mlp_bwd": 2}
@@ -75,6 +76,10 @@ def lib():
             raise IblnError("%s not found: build it with `python -m ibl_nerf_b200.build` (nvcc, sm_100a). "
                             "There is no CPU fallback." % LIB_PATH)
         h = ctypes.CDLL(LIB_PATH)
+        h.ibln_abi_version.restype = c_int
+        if h.ibln_abi_version() != ABI_VERSION:
+            raise IblnError("%s has ABI version %d, this package binds version %d: rebuild it (python -m ibl_nerf_b200.build --force)"
+                            % (LIB_PATH, h.ibln_abi_version(), ABI_VERSION))
         for name, at in _SIGS.items():
             fn = getattr(h, name)
             fn.argtypes = at + [c_int, c_p]
