@@ -176,11 +176,15 @@ composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
 // sample) and the maps the non-linear outputs need; pass 2 streams the rows again in reverse (L2 hits) for the
 // suffix sum  sum_{k>i} gw_k w_k, builds each row of g_raw in place in the row buffer and writes it out with
 // coalesced 16-byte stores.
+// FIXED = true: the reference's layout (C = 18 channels, 3 coarse-radiance heads, sigmoid radiance) as compile-time
+// constants -- the kernel is instruction-issue bound and the run-time channel / activation switches cost ~15 %.
+template <bool FIXED>
 __global__ void __launch_bounds__(256)
 composite_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays_d,
                      const float* __restrict__ noise, const float* __restrict__ g_weights,
-                     const float* __restrict__ g_maps, const float* __restrict__ g_srgb, int n, int S, int C, int nc,
-                     int sigm, float* __restrict__ g_raw) {
+                     const float* __restrict__ g_maps, const float* __restrict__ g_srgb, int n, int S, int C_rt, int nc_rt,
+                     int sigm_rt, float* __restrict__ g_raw) {
+  const int C = FIXED ? 18 : C_rt, nc = FIXED ? 3 : nc_rt, sigm = FIXED ? 1 : sigm_rt;
   extern __shared__ __align__(16) float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rowf = ROW * C;
@@ -438,12 +442,18 @@ extern "C" int ibln_composite_bwd(const float* raw, const float* z, const float*
   while (warps > 1 && warps * per_warp > 200 * 1024) warps >>= 1;
   size_t smem = warps * per_warp;
   if (smem > 220 * 1024) return IBLN_EINVAL;
-  IBLN_CUDA(cudaFuncSetAttribute(composite_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = (int)((200 * 1024) / (smem + 1024));
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 6) per_sm = 6;
-  composite_bwd_kernel<<<comp_grid(n, device, per_sm, warps), warps * 32, smem, (cudaStream_t)stream>>>(
-      raw, z, rays_d, noise, g_weights, g_maps, g_maps_srgb, n, S, C, nc, sigm, g_raw);
+  if (C == 18 && nc == 3 && sigm == 1) {
+    IBLN_CUDA(cudaFuncSetAttribute(composite_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    composite_bwd_kernel<true><<<comp_grid(n, device, per_sm, warps), warps * 32, smem, (cudaStream_t)stream>>>(
+        raw, z, rays_d, noise, g_weights, g_maps, g_maps_srgb, n, S, C, nc, sigm, g_raw);
+  } else {
+    IBLN_CUDA(cudaFuncSetAttribute(composite_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    composite_bwd_kernel<false><<<comp_grid(n, device, per_sm, warps), warps * 32, smem, (cudaStream_t)stream>>>(
+        raw, z, rays_d, noise, g_weights, g_maps, g_maps_srgb, n, S, C, nc, sigm, g_raw);
+  }
   IBLN_RETURN_LAST();
 }
 
