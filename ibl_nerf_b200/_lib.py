@@ -56,8 +56,10 @@ ABI_VERSION = 2      # include/iblnerf_b200.h: IBLN_ABI_VERSION
 _lib = None
 # kernels launched per entry point (for bench.py's gpu_launches); default 1
 KERNELS_PER_CALL = {"ibln_sgemm_wgrad": 2, "ibln_mlp_pack_weights": 3, "ibln_mlp_bwd": 2}
-# bench.py sets this to {} to collect per-entry launch counts, CUDA-event pairs and algorithmic FLOPs
+# bench.py sets this to {} to collect per-entry launch counts, CUDA-event pairs and algorithmic FLOPs;
+# PROFILE_EVENTS (None = every entry) limits the CUDA-event bracketing to the named entry points
 PROFILE = None
+PROFILE_EVENTS = None
 
 
 class IblnError(RuntimeError):
@@ -110,13 +112,16 @@ def call(name, device, *args, flops=0.0):
     stream = torch.cuda.current_stream(dev).cuda_stream
     if PROFILE is not None:
         rec = PROFILE.setdefault(name, {"launches": 0, "events": [], "flops": 0.0})
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(torch.cuda.current_stream(dev))
-        rc = getattr(h, name)(*args, dev, c_p(stream))
-        e1.record(torch.cuda.current_stream(dev))
         rec["launches"] += KERNELS_PER_CALL.get(name, 1)
-        rec["events"].append((e0, e1))
         rec["flops"] += flops
+        if PROFILE_EVENTS is None or name in PROFILE_EVENTS:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(torch.cuda.current_stream(dev))
+            rc = getattr(h, name)(*args, dev, c_p(stream))
+            e1.record(torch.cuda.current_stream(dev))
+            rec["events"].append((e0, e1))
+        else:
+            rc = getattr(h, name)(*args, dev, c_p(stream))
     else:
         rc = getattr(h, name)(*args, dev, c_p(stream))
     if rc != 0:
