@@ -128,7 +128,8 @@ __device__ __forceinline__ void process_chunk(const EpiCtx& c, Heads& hd, const 
                         pack_bf16x2(h[8 * q + 4], h[8 * q + 5]), pack_bf16x2(h[8 * q + 6], h[8 * q + 7]));
       const uint32_t o = c.off[(cc & 1) * 4 + q];
       if (kWriteAct) *reinterpret_cast<uint4*>(c.act + kb * KB_BYTES + o) = pk;
-      else if (c.rec != nullptr) __stcs(reinterpret_cast<uint4*>(c.rec + (size_t)(sv_blk + kb) * KB_BYTES + o), pk);   // STASH only (AF / ADD): no smem copy exists
+      else if (c.rec != nullptr)      // STASH only (AF / ADD01): no smem copy exists -> slice-interleaved no-swizzle image, coalesced per warp
+        __stcs(reinterpret_cast<uint4*>(c.rec + (size_t)(sv_blk + kb) * KB_BYTES + (c.row >> 5) * 4096 + ((cc & 1) * 4 + q) * 512 + (c.row & 31) * 16), pk);
     }
   }
   const float* T = c.heads_s;     // this step's head rows (staged in the idle encoding tile)

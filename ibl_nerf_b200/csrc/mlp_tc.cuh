@@ -74,6 +74,11 @@ static_assert(PACKED_BWD_OFF % 16 == 0, "bwd chunk stream must stay 16-byte alig
 // like the shared-memory tiles so the wgrad kernel can bulk-copy them straight into UMMA operands).
 constexpr int SV_PE = 0;                     // positional encoding (1 block)
 __host__ __device__ constexpr int SV_H(int l) { return 1 + 4 * l; }   // h0..h7, 4 blocks each
+// The two feature tiles that have no shared-memory home in the forward kernel (their A operand is still live when
+// they are produced: SV_AF and the first four SV_ADDF blocks) are written straight from registers and therefore use
+// a layout in which a warp's store is contiguous: the MN-major NO-swizzle operand image, interleaved per
+// 32-point slice --  byte offset of (point p, column c) in a block = (p / 32) * 4096 + (c / 8) * 512 + (p % 32) * 16
+// + (c % 8) * 2.  The wgrad kernel reads these blocks with make_desc_mnmajor_noswz (LBO 128 B, SBO 512 B).
 constexpr int SV_AF = 33;                    // relu(albedo_feature | irradiance_feature)
 constexpr int SV_FEAT = 37;                  // feature_linear output (no relu)
 constexpr int SV_DE = 41;                    // view-direction encoding (32 of 64 columns used)

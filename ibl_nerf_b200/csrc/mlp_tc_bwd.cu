@@ -508,6 +508,7 @@ struct WJob {
   int nb;                // B blocks (1..4)
   int n_total;           // N of the main MMA (multiple of 16, <= 256)
   int with_ones;
+  int a_noswz;           // A blocks are in the slice-interleaved no-swizzle layout (SV_AF, SV_ADDF 0..3)
   int cost;              // relative streaming cost of one tile for a CTA pair
   int n_out;
   WOut out[4];
@@ -643,7 +644,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) mlp_wgrad_kernel(const __grid_c
             const uint32_t b_addr = a_addr + 2 * WG_BLK_BYTES;
             for (int ks = 0; ks < WG_STAGE_PTS / 16; ++ks) {       // 16 points per MMA
               const uint32_t acc = (t > sg.t0 || q > 0 || ks > 0) ? 1u : 0u;
-              const uint64_t da = make_desc_mnmajor_sw128(a_addr + ks * 2048, WG_BLK_BYTES);
+              const uint64_t da = jb.a_noswz ? make_desc_mnmajor_noswz(a_addr + ks * 256, 128, 512)
+                                             : make_desc_mnmajor_sw128(a_addr + ks * 2048, WG_BLK_BYTES);
               umma_bf16(tmem_base, da, make_desc_mnmajor_sw128(b_addr + ks * 2048, WG_BLK_BYTES), idesc, acc);
               if (jb.with_ones) umma_bf16(tmem_base + 256, da, make_desc_mnmajor_sw128(ones_addr + ks * 2048, WG_BLK_BYTES), idesc1, acc);
             }
@@ -704,7 +706,7 @@ static WgradParams make_wgrad_jobs(int freeze) {
   auto job = [&](int a_sv, int a_blk, int m_halves, int b_sv, int b_blk, int nb, int n_total, int with_ones) -> WJob& {
     WJob& j = P.job[P.n_jobs++];
     j.a_sv = a_sv; j.a_blk = a_blk; j.m_halves = m_halves; j.b_sv = b_sv; j.b_blk = b_blk; j.nb = nb; j.n_total = n_total;
-    j.with_ones = with_ones; j.n_out = 0;
+    j.with_ones = with_ones; j.n_out = 0; j.a_noswz = 0;
     j.cost = (2 + nb) * (m_halves == 2 ? 2 : 1);
     return j;
   };
@@ -723,6 +725,7 @@ static WgradParams make_wgrad_jobs(int freeze) {
     }
     {   // albedo / irradiance heads from AF
       WJob& p = job(SVR, SV_AF, 2, DYR, DY_G, 1, 64, 0);
+      p.a_noswz = 1;
       add_out(p, fo.w[12], 0, 128, 1, 4, 1, 128);
       add_out(p, fo.w[15], 128, 256, 5, 6, 1, 0);
     }
@@ -783,6 +786,7 @@ static WgradParams make_wgrad_jobs(int freeze) {
   }
   {   // albedo (cols 0..127 x channels 1..3) / irradiance (cols 128..255 x channel 5) from AF
     WJob& p = job(SVR, SV_AF, 2, DYR, DY_G, 1, 64, 0);
+    p.a_noswz = 1;
     add_out(p, fo.w[12], 0, 128, 1, 4, 1, 128);
     add_out(p, fo.w[15], 128, 256, 5, 6, 1, 0);
   }
@@ -792,6 +796,7 @@ static WgradParams make_wgrad_jobs(int freeze) {
   }
   for (int k = 0; k < 3; ++k) {   // coarse radiance heads from ADDF block pair k
     WJob& p = job(SVR, SV_ADDF + 2 * k, 1, DYR, DY_G, 1, 64, 0);
+    p.a_noswz = k < 2;      // feature 2 leaves the forward kernel through the activation tile (swizzled image)
     add_out(p, fo.w[20 + k], 0, 128, 9 + 3 * k, 12 + 3 * k, 1, 128);
   }
   return P;

@@ -130,6 +130,17 @@ __device__ __forceinline__ uint64_t make_desc_mnmajor_sw128(uint32_t smem_addr, 
   return d;
 }
 
+// MN-major, NO swizzle ("interleave"): 16-byte vectors of 8 MN elements; the 8 k-rows of a core matrix are 16 B
+// apart, LBO = byte distance between 8-k groups, SBO = byte distance between 8-element MN chunks.
+__device__ __forceinline__ uint64_t make_desc_mnmajor_noswz(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+
 // kind::f16 instruction descriptor: bf16 x bf16 -> fp32
 __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t m, uint32_t n, uint32_t a_mn_major, uint32_t b_mn_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn_major << 15) | (b_mn_major << 16) | ((n >> 3) << 17) | ((m >> 4) << 24);

@@ -176,9 +176,14 @@ def test_tc_repack_after_parameter_update():
 
 
 # ----------------------------------------------------------------------------- tensor-core backward
-def decode_blocks(buf, tile, rec_bytes, blk, nblk):
-    """Un-swizzle nblk 16 KB operand blocks of one tile record into a [128, 64*nblk] fp32 matrix."""
+def decode_blocks(buf, tile, rec_bytes, blk, nblk, noswz=False):
+    """Un-swizzle nblk 16 KB operand blocks of one tile record into a [128, 64*nblk] fp32 matrix.
+    noswz: the slice-interleaved no-swizzle image of the register-written stash blocks (mlp_tc.cuh, SV_AF):
+    offset(p, c) = (p / 32) * 4096 + (c / 8) * 512 + (p % 32) * 16 + (c % 8) * 2."""
     base = tile * rec_bytes + blk * 16384
+    if noswz:
+        raw = buf[base:base + nblk * 16384].view(torch.bfloat16).reshape(nblk, 4, 8, 32, 8)  # block, slice, col chunk, point, elem
+        return raw.permute(1, 3, 0, 2, 4).reshape(128, 64 * nblk).float()
     raw = buf[base:base + nblk * 16384].view(torch.bfloat16).reshape(nblk, 128, 8, 8)      # block, row, chunk position, elem
     rows = torch.arange(128, device=buf.device)
     out = []
@@ -250,13 +255,14 @@ def test_tc_stash_and_dgrad_tiles():
     SV, DYB = 55 * 16384, 51 * 16384
     errs = {}
 
-    def gather(buf, rec, blk, nblk, cols):
-        return torch.cat([decode_blocks(buf, t, rec, blk, nblk) for t in range(3)], 0)[:P, :cols].cpu()
+    def gather(buf, rec, blk, nblk, cols, noswz=False):
+        return torch.cat([decode_blocks(buf, t, rec, blk, nblk, noswz) for t in range(3)], 0)[:P, :cols].cpu()
     # stash: bf16-level agreement with the fp32 activations
     for name, blk, nblk, cols, ref in (("pe", 0, 1, 63, xp), ("h0", 1, 4, 256, inter["h0"]), ("h4", 17, 4, 256, inter["h4"]),
                                        ("h7", 29, 4, 256, h7), ("af", 33, 4, 256, af), ("feat", 37, 4, 256, feat),
-                                       ("de", 41, 1, 27, xd), ("hv", 42, 4, 256, hv), ("addf", 46, 6, 384, addf)):
-        got = gather(stash, SV, blk, nblk, cols)
+                                       ("de", 41, 1, 27, xd), ("hv", 42, 4, 256, hv), ("addf01", 46, 4, 256, addf[:, :256]),
+                                       ("addf2", 50, 2, 128, addf[:, 256:])):
+        got = gather(stash, SV, blk, nblk, cols, noswz=name in ("af", "addf01"))
         errs["stash " + name] = (rel_l2(got, ref.detach()), 2e-2)
     # backward
     flat = torch.zeros(798994, device=DEV)
