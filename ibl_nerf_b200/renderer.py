@@ -349,10 +349,11 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
                 **kwargs):
     """ibl_nerf_renderer.py:629-732."""
     N_rays = ray_batch.shape[0]
-    rays_o, rays_d = ray_batch[:, 0:3], ray_batch[:, 3:6]
+    # contiguous once: every kernel wrapper below would otherwise copy these column slices again (f32c)
+    rays_o, rays_d = ray_batch[:, 0:3].contiguous(), ray_batch[:, 3:6].contiguous()
     viewdirs = ray_batch[:, -3:] if ray_batch.shape[-1] > 8 else None
     bounds = torch.reshape(ray_batch[..., 6:8], [-1, 1, 2])
-    near, far = bounds[..., 0], bounds[..., 1]
+    near, far = bounds[..., 0].contiguous(), bounds[..., 1].contiguous()
 
     t_rand = None
     if perturb > 0.:                                                                           # :678-692
