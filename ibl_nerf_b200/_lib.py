@@ -42,6 +42,7 @@ _SIGS = {
     "ibln_umma_mn_selftest": [c_p, c_p, c_p, c_int],
     "ibln_umma_pair_selftest": [c_p, c_p, c_p, c_int],
     "ibln_store_probe": [c_p, c_i64, c_int, c_int],
+    "ibln_tmem_probe": [c_p, c_int, c_int, c_int],
 }
 _PLAIN = {  # no device/stream tail
     "ibln_abi_version": ([], c_int),
@@ -50,6 +51,8 @@ _PLAIN = {  # no device/stream tail
     "ibln_mlp_packed_bytes": ([], c_i64),
     "ibln_mlp_saved_bytes": ([c_i64], c_i64),
     "ibln_mlp_bwd_workspace_bytes": ([c_i64], c_i64),
+    "ibln_debug_set": ([c_int], c_int),
+    "ibln_debug_timeline": ([c_p], c_int),
 }
 
 ABI_VERSION = 2      # include/iblnerf_b200.h: IBLN_ABI_VERSION
