@@ -178,7 +178,9 @@ composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
 // coalesced 16-byte stores.
 // FIXED = true: the reference's layout (C = 18 channels, 3 coarse-radiance heads, sigmoid radiance) as compile-time
 // constants -- the kernel is instruction-issue bound and the run-time channel / activation switches cost ~15 %.
-template <bool FIXED>
+// FULL = true: S is a multiple of 32 (every shipped / benchmarked sample count), so every row is complete: the
+// per-sample validity predicates and the ragged row copies fold away.
+template <bool FIXED, bool FULL>
 __global__ void __launch_bounds__(256)
 composite_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays_d,
                      const float* __restrict__ noise, const float* __restrict__ g_weights,
@@ -202,7 +204,22 @@ composite_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
   int r = blockIdx.x * nwarps + warp;
   if (r >= n) return;
   // flat task stream per ray: t in [0, 2*nrows): row(t) = t < nrows ? t : 2*nrows-1-t
-  row_load_async(buf, raw, r, 0, S, C, lane, vec_ok);
+  auto load_row = [&](float* dst, int64_t rr, int kk) {
+    if (FIXED && FULL) {          // 32 samples x 18 channels = 144 float4 per row: 4.5 per lane, fully unrolled
+      const float* src = raw + ((int64_t)rr * S + (int64_t)kk * ROW) * 18;
+      if (vec_ok) {
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+          const int e = lane + 32 * j;
+          if (j < 4 || e < 144) cp_async16(dst + 4 * e, src + 4 * e);
+        }
+        cp_async_commit();
+        return;
+      }
+    }
+    row_load_async(dst, raw, rr, kk, S, C, lane, vec_ok);
+  };
+  load_row(buf, r, 0);
   int it = 0;
   for (; r < n; r += stride) {
     const float dx = rays_d[3 * r], dy = rays_d[3 * r + 1], dz = rays_d[3 * r + 2];
@@ -221,12 +238,12 @@ composite_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
       const bool more = t + 1 < 2 * nrows;
       const int rn = more ? r : r + stride;
       const int tn = more ? t + 1 : 0;
-      if (rn < n) { row_load_async(nxt, raw, rn, tn < nrows ? tn : 2 * nrows - 1 - tn, S, C, lane, vec_ok); cp_async_wait<1>(); }
+      if (rn < n) { load_row(nxt, rn, tn < nrows ? tn : 2 * nrows - 1 - tn); cp_async_wait<1>(); }
       else cp_async_wait<0>();
       __syncwarp();
       const int k = t < nrows ? t : 2 * nrows - 1 - t;
       const int i = k * ROW + lane;
-      const bool valid = i < S;
+      const bool valid = FULL ? true : (i < S);
       const float zi = valid ? zr[i] : 0.f;
       float* px = cur + (size_t)(valid ? lane : 0) * C;
 
@@ -340,9 +357,15 @@ composite_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
           for (int c = 18; c < C; ++c) px[c] = 0.f;
         }
         __syncwarp();
-        const int n_float = min(ROW, S - k * ROW) * C;
+        const int n_float = FULL ? ROW * C : min(ROW, S - k * ROW) * C;
         float* dst = g_raw + ((int64_t)r * S + (int64_t)k * ROW) * C;
-        if (vec_ok) {
+        if (FIXED && FULL && vec_ok) {
+#pragma unroll
+          for (int j = 0; j < 5; ++j) {
+            const int e = lane + 32 * j;
+            if (j < 4 || e < 144) reinterpret_cast<float4*>(dst)[e] = reinterpret_cast<float4*>(cur)[e];
+          }
+        } else if (vec_ok) {
           for (int e = lane; e < (n_float >> 2); e += 32) reinterpret_cast<float4*>(dst)[e] = reinterpret_cast<float4*>(cur)[e];
         } else {
           for (int e = lane; e < n_float; e += 32) dst[e] = cur[e];
@@ -445,15 +468,17 @@ extern "C" int ibln_composite_bwd(const float* raw, const float* z, const float*
   int per_sm = (int)((200 * 1024) / (smem + 1024));
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 6) per_sm = 6;
-  if (C == 18 && nc == 3 && sigm == 1) {
-    IBLN_CUDA(cudaFuncSetAttribute(composite_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    composite_bwd_kernel<true><<<comp_grid(n, device, per_sm, warps), warps * 32, smem, (cudaStream_t)stream>>>(
+  auto launch = [&](auto kern) -> int {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    kern<<<comp_grid(n, device, per_sm, warps), warps * 32, smem, (cudaStream_t)stream>>>(
         raw, z, rays_d, noise, g_weights, g_maps, g_maps_srgb, n, S, C, nc, sigm, g_raw);
-  } else {
-    IBLN_CUDA(cudaFuncSetAttribute(composite_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    composite_bwd_kernel<false><<<comp_grid(n, device, per_sm, warps), warps * 32, smem, (cudaStream_t)stream>>>(
-        raw, z, rays_d, noise, g_weights, g_maps, g_maps_srgb, n, S, C, nc, sigm, g_raw);
-  }
+    return 0;
+  };
+  const bool fixed = C == 18 && nc == 3 && sigm == 1, full = S % 32 == 0;
+  int rc = fixed ? (full ? launch(composite_bwd_kernel<true, true>) : launch(composite_bwd_kernel<true, false>))
+                 : (full ? launch(composite_bwd_kernel<false, true>) : launch(composite_bwd_kernel<false, false>));
+  if (rc != 0) return rc;
   IBLN_RETURN_LAST();
 }
 
