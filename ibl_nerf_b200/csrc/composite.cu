@@ -65,12 +65,15 @@ __device__ __forceinline__ void row_load_async(float* dst, const float* __restri
   cp_async_commit();
 }
 
-template <bool SIMPLE>
+// FIXED: the reference's channel layout (C = 18, 3 coarse heads, sigmoid radiance) at compile time; FULL: S % 32 == 0
+// (complete rows: no validity predicates, unrolled row copies) -- see composite_bwd_kernel.
+template <bool SIMPLE, bool FIXED, bool FULL>
 __global__ void __launch_bounds__(256)
 composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays_d,
-                     const float* __restrict__ noise, int n, int S, int C, int nc, int sigm,
+                     const float* __restrict__ noise, int n, int S, int C_rt, int nc_rt, int sigm_rt,
                      float* __restrict__ weights, float* __restrict__ maps, float* __restrict__ maps_srgb,
                      float* __restrict__ pre_out) {
+  const int C = FIXED ? 18 : C_rt, nc = FIXED ? 3 : nc_rt, sigm = FIXED ? 1 : sigm_rt;
   extern __shared__ __align__(16) float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rowf = ROW * C;
@@ -83,7 +86,22 @@ composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
   const int nrows = (S + ROW - 1) / ROW;
   int r = blockIdx.x * nwarps + warp;
   if (r >= n) return;
-  row_load_async(buf, raw, r, 0, S, C, lane, vec_ok);
+  auto load_row = [&](float* dst, int64_t rr, int kk) {
+    if (FIXED && FULL) {          // 144 float4 per row: 4.5 per lane, fully unrolled
+      const float* src = raw + ((int64_t)rr * S + (int64_t)kk * ROW) * 18;
+      if (vec_ok) {
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+          const int e = lane + 32 * j;
+          if (j < 4 || e < 144) cp_async16(dst + 4 * e, src + 4 * e);
+        }
+        cp_async_commit();
+        return;
+      }
+    }
+    row_load_async(dst, raw, rr, kk, S, C, lane, vec_ok);
+  };
+  load_row(buf, r, 0);
   int it = 0;
   for (; r < n; r += stride) {
     const float dx = rays_d[3 * r], dy = rays_d[3 * r + 1], dz = rays_d[3 * r + 2];
@@ -101,12 +119,12 @@ composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
       // prefetch the next row of the stream
       const bool more_rows = k + 1 < nrows;
       const int rn = more_rows ? r : r + stride;
-      if (rn < n) { row_load_async(nxt, raw, rn, more_rows ? k + 1 : 0, S, C, lane, vec_ok); cp_async_wait<1>(); }
+      if (rn < n) { load_row(nxt, rn, more_rows ? k + 1 : 0); cp_async_wait<1>(); }
       else cp_async_wait<0>();
       __syncwarp();
 
       const int i = k * ROW + lane;
-      const bool valid = i < S;
+      const bool valid = FULL ? true : (i < S);
       const float zi = valid ? zr[i] : 0.f;
       float dist = (valid && i < S - 1) ? (zr[i + 1] - zi) : 1e10f;
       dist *= dnorm;
@@ -428,13 +446,20 @@ static int launch_fwd(const float* raw, const float* z, const float* d, const fl
   DeviceGuard g(device);
   const int warps = 8;
   size_t smem = (size_t)warps * (2 * (size_t)ROW * C + 32) * sizeof(float);
-  auto kern = composite_fwd_kernel<SIMPLE>;
-  IBLN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = (int)((200 * 1024) / (smem + 1024));
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 6) per_sm = 6;
-  kern<<<comp_grid(n, device, per_sm, warps), warps * 32, smem, (cudaStream_t)stream>>>(raw, z, d, noise, n, S, C, nc, sigm,
-                                                                                   weights, maps, maps_srgb, pre);
+  auto launch = [&](auto kern) -> int {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    kern<<<comp_grid(n, device, per_sm, warps), warps * 32, smem, (cudaStream_t)stream>>>(raw, z, d, noise, n, S, C, nc, sigm,
+                                                                                     weights, maps, maps_srgb, pre);
+    return 0;
+  };
+  const bool fixed = C == 18 && nc == 3 && sigm == 1, full = S % 32 == 0;
+  int rc = fixed ? (full ? launch(composite_fwd_kernel<SIMPLE, true, true>) : launch(composite_fwd_kernel<SIMPLE, true, false>))
+                 : (full ? launch(composite_fwd_kernel<SIMPLE, false, true>) : launch(composite_fwd_kernel<SIMPLE, false, false>));
+  if (rc != 0) return rc;
   IBLN_RETURN_LAST();
 }
 
