@@ -249,6 +249,8 @@ sample_pdf_kernel(const float* __restrict__ bins, int64_t bins_stride, const flo
 // generic kernel exposes three dependent global-load round trips per ray (ncu: 53 % long-scoreboard stalls).
 struct RayRegs { float w0, w1, b0, b1, u[4]; };
 // NB / NS: compile-time nbins / nsamp (0 = run-time); the shipped 63 / 128 instantiation folds every bounds test.
+// EXACT instantiations are the explicit-CDF entry (ibln_inverse_cdf: cdf_in given, indices optionally returned);
+// the others build the CDF from the weights and return samples only.
 template <bool EXACT, int NB, int NS>
 __global__ void __launch_bounds__(SP_WARPS * 32)
 sample_pdf_small_kernel(const float* __restrict__ bins, int64_t bins_stride, const float* __restrict__ weights,
@@ -268,7 +270,7 @@ sample_pdf_small_kernel(const float* __restrict__ bins, int64_t bins_stride, con
     if (r < n) {
       const float* brow = bins + (int64_t)r * bins_stride;
       const float* urow = u + (int64_t)r * nsamp;
-      if (cdf_in != nullptr) {          // explicit CDF: w0/w1 carry cdf[lane], cdf[lane + 32]
+      if (EXACT) {                      // explicit CDF entry (always EXACT): w0/w1 carry cdf[lane], cdf[lane + 32]
         const float* crow = cdf_in + (int64_t)r * nbins;
         if (lane < nbins) q.w0 = crow[lane];
         if (lane + 32 < nbins) q.w1 = crow[lane + 32];
@@ -289,7 +291,7 @@ sample_pdf_small_kernel(const float* __restrict__ bins, int64_t bins_stride, con
   RayRegs cur = fetch(r), nx1 = fetch(r + stride);     // two rays in flight: one ray (~400 warp instructions) does not
   for (; r < n; r += stride) {                         // cover the loaded DRAM latency (ncu: 19 % of samples on the first use)
     const RayRegs nx2 = fetch(r + 2 * stride);
-    if (cdf_in != nullptr) {
+    if (EXACT) {
       if (lane < nbins) rs.cdf[lane] = cur.w0;
       if (lane + 32 < nbins) rs.cdf[lane + 32] = cur.w1;
     } else {              // same arithmetic / summation order as warp_build_cdf
@@ -322,7 +324,7 @@ sample_pdf_small_kernel(const float* __restrict__ bins, int64_t bins_stride, con
     for (int k = 0; k < 4; ++k)
       if (lane + 32 * k < nsamp) {
         orow[lane + 32 * k] = sv[k];
-        if (inds_out != nullptr) inds_out[(int64_t)r * nsamp + lane + 32 * k] = ind[k];
+        if (EXACT && inds_out != nullptr) inds_out[(int64_t)r * nsamp + lane + 32 * k] = ind[k];
       }
     __syncwarp();
     cur = nx1;
