@@ -85,7 +85,9 @@ struct EpiCtx {
 enum Kind : int { K_RELU_ACT, K_L7_SIGMA, K_L7_FULL, K_AF, K_FEATURE, K_VIEW, K_ADD01, K_ADD2 };
 
 // One 32-column chunk of the accumulator: bias, activation, pack, store, small-head dot products.
-template <int KIND, bool STASH>
+// `cc` is a run-time value (the drain loop is NOT unrolled, see drain()); what must be static is: ODD = cc & 1
+// (selects the register-held swizzle offsets) and HALF = cc >= 4 (selects the head group of K_AF / K_ADD01).
+template <int KIND, bool STASH, bool ODD, int HALF>
 __device__ __forceinline__ void process_chunk(const EpiCtx& c, Heads& hd, const uint32_t (&v)[32], int cc, int sv_blk,
                                               uint32_t& mask_word) {
   float h[32];
@@ -126,10 +128,10 @@ __device__ __forceinline__ void process_chunk(const EpiCtx& c, Heads& hd, const 
       else
         pk = make_uint4(pack_bf16x2(h[8 * q], h[8 * q + 1]), pack_bf16x2(h[8 * q + 2], h[8 * q + 3]),
                         pack_bf16x2(h[8 * q + 4], h[8 * q + 5]), pack_bf16x2(h[8 * q + 6], h[8 * q + 7]));
-      const uint32_t o = c.off[(cc & 1) * 4 + q];
+      const uint32_t o = c.off[(ODD ? 4 : 0) + q];
       if (kWriteAct) *reinterpret_cast<uint4*>(c.act + kb * KB_BYTES + o) = pk;
       else if (c.rec != nullptr)      // STASH only (AF / ADD01): no smem copy exists -> slice-interleaved no-swizzle image, coalesced per warp
-        __stcs(reinterpret_cast<uint4*>(c.rec + (size_t)(sv_blk + kb) * KB_BYTES + (c.row >> 5) * 4096 + ((cc & 1) * 4 + q) * 512 + (c.row & 31) * 16), pk);
+        __stcs(reinterpret_cast<uint4*>(c.rec + (size_t)(sv_blk + kb) * KB_BYTES + (c.row >> 5) * 4096 + ((ODD ? 4 : 0) + q) * 512 + (c.row & 31) * 16), pk);
     }
   }
   const float* T = c.heads_s;     // this step's head rows (staged in the idle encoding tile)
@@ -139,7 +141,7 @@ __device__ __forceinline__ void process_chunk(const EpiCtx& c, Heads& hd, const 
     dot32(hd.sigma, h, T + cc * 32);
     dot32(hd.rough, h, T + 256 + cc * 32);
   } else if (KIND == K_AF) {
-    if (cc < 4) {
+    if (HALF == 0) {
 #pragma unroll
       for (int q = 0; q < 3; ++q) dot32(hd.alb[q], h, T + q * 128 + cc * 32);
     } else {
@@ -149,7 +151,7 @@ __device__ __forceinline__ void process_chunk(const EpiCtx& c, Heads& hd, const 
 #pragma unroll
     for (int q = 0; q < 3; ++q) dot32(hd.rad[0][q], h, T + q * 256 + cc * 32);
   } else if (KIND == K_ADD01) {
-    if (cc < 4) {
+    if (HALF == 0) {
 #pragma unroll
       for (int q = 0; q < 3; ++q) dot32(hd.rad[1][q], h, T + q * 128 + cc * 32);
     } else {
@@ -162,27 +164,36 @@ __device__ __forceinline__ void process_chunk(const EpiCtx& c, Heads& hd, const 
   }
 }
 
-// Drain NCHUNK*32 accumulator columns with the TMEM loads software-pipelined one chunk ahead.
-template <int KIND, bool STASH, int NCHUNK>
+// Drain chunks [CC0, CC0 + NCHUNK) of the accumulator (32 columns each) with the TMEM loads software-pipelined one
+// chunk ahead.  In the stash instantiation the chunk-pair loop of the head steps is deliberately NOT unrolled:
+// fully unrolled, those six steps were ~120 KB of straight-line code executed once per tile and 30 % of the epilogue
+// warps' stall samples there were instruction-fetch misses (stall_no_inst); rolled: stash forward 1.59 -> 1.53 ms.
+// Everywhere else unrolling wins (inference forward 1.00 ms unrolled, 1.05 heads rolled, 1.22 all rolled).
+template <int KIND, bool STASH> constexpr bool drain_rolled() { return STASH && KIND != K_RELU_ACT; }
+template <int KIND, bool STASH, int CC0, int NCHUNK>
 __device__ __forceinline__ void drain(const EpiCtx& c, Heads& hd, int sv_blk, int sv_mask) {
-  uint32_t mw[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) mw[i] = 0;
+  constexpr int HALF = CC0 >= 4 ? 1 : 0;
+  uint32_t* mdst = nullptr;
+  if (STASH && KIND != K_FEATURE && c.rec != nullptr)       // [mask slot][word 0..7][row]: a warp's store of one word = 4 full sectors
+    mdst = reinterpret_cast<uint32_t*>(c.rec + (size_t)SV_MASK * KB_BYTES + sv_mask * 4096) + c.row;
   uint32_t va[32], vb[32];
-  tmem_ld32(c.t_lane, va);
-#pragma unroll
-  for (int cc = 0; cc < NCHUNK; cc += 2) {
+  tmem_ld32(c.t_lane + CC0 * 32, va);
+  auto pair = [&](int cc) {
+    uint32_t m0 = 0, m1 = 0;
     tmem_wait_ld();
     tmem_ld32(c.t_lane + (cc + 1) * 32, vb);
-    process_chunk<KIND, STASH>(c, hd, va, cc, sv_blk, mw[cc]);
+    process_chunk<KIND, STASH, false, HALF>(c, hd, va, cc, sv_blk, m0);
     tmem_wait_ld();
-    if (cc + 2 < NCHUNK) tmem_ld32(c.t_lane + (cc + 2) * 32, va);
-    process_chunk<KIND, STASH>(c, hd, vb, cc + 1, sv_blk, mw[cc + 1]);
-  }
-  if (STASH && KIND != K_FEATURE && c.rec != nullptr) {      // one full 32-byte sector per row: [mask slot][row][8 words]
-    uint4* dst = reinterpret_cast<uint4*>(c.rec + (size_t)SV_MASK * KB_BYTES + sv_mask * 4096 + c.row * 32);
-    __stcs(dst, make_uint4(mw[0], mw[1], mw[2], mw[3]));
-    __stcs(dst + 1, make_uint4(mw[4], mw[5], mw[6], mw[7]));
+    if (cc + 2 < CC0 + NCHUNK) tmem_ld32(c.t_lane + (cc + 2) * 32, va);
+    process_chunk<KIND, STASH, true, HALF>(c, hd, vb, cc + 1, sv_blk, m1);
+    if (mdst != nullptr) { __stcs(mdst + cc * 128, m0); __stcs(mdst + (cc + 1) * 128, m1); }
+  };
+  if (drain_rolled<KIND, STASH>()) {
+#pragma unroll 1
+    for (int cc = CC0; cc < CC0 + NCHUNK; cc += 2) pair(cc);
+  } else {
+#pragma unroll
+    for (int cc = CC0; cc < CC0 + NCHUNK; cc += 2) pair(cc);
   }
 }
 
@@ -432,20 +443,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) mlp_fw
           }
         }
         named_bar_sync(1 + slot, 128);       // bias row (+ head table) of this step are in smem
+        if (s == 3 || s == 12) tl_mark(tl, tl_base, tl_n, 50 + s);
         switch (s) {
           case 7:
-            if (SIGMA_ONLY) drain<K_L7_SIGMA, false, 8>(c, hd, 0, 0);
-            else drain<K_L7_FULL, STASH, 8>(c, hd, SV_H(7), 7);
+            if (SIGMA_ONLY) drain<K_L7_SIGMA, false, 0, 8>(c, hd, 0, 0);
+            else drain<K_L7_FULL, STASH, 0, 8>(c, hd, SV_H(7), 7);
             break;
-          case 8: drain<K_AF, STASH, 8>(c, hd, SV_AF, 8); break;
+          case 8: drain<K_AF, STASH, 0, 4>(c, hd, SV_AF, 8); drain<K_AF, STASH, 4, 4>(c, hd, SV_AF, 8); break;
           case 9:
-            drain<K_FEATURE, STASH, 8>(c, hd, SV_FEAT, 0);
+            drain<K_FEATURE, STASH, 0, 8>(c, hd, SV_FEAT, 0);
             write_encoding<4, 4>(aux, row, dir);   // view encoding for step 10
             break;
-          case 10: drain<K_VIEW, STASH, 8>(c, hd, SV_HV, 9); break;
-          case 11: drain<K_ADD01, STASH, 8>(c, hd, SV_ADDF, 10); break;
-          case 12: drain<K_ADD2, STASH, 4>(c, hd, SV_ADDF + 4, 11); break;
-          default: drain<K_RELU_ACT, STASH, 8>(c, hd, SV_H(s), s); break;
+          case 10: drain<K_VIEW, STASH, 0, 8>(c, hd, SV_HV, 9); break;
+          case 11: drain<K_ADD01, STASH, 0, 4>(c, hd, SV_ADDF, 10); drain<K_ADD01, STASH, 4, 4>(c, hd, SV_ADDF, 10); break;
+          case 12: drain<K_ADD2, STASH, 0, 4>(c, hd, SV_ADDF + 4, 11); break;
+          default: drain<K_RELU_ACT, STASH, 0, 8>(c, hd, SV_H(s), s); break;
         }
         if (s + 1 < n_steps) {
           if (STASH) fence_proxy_async();
@@ -466,11 +478,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) mlp_fw
         }
       }
       // ---- tile boundary: free the slot's shared tables, start the next tile, then store this tile's outputs
+      tl_mark(tl, tl_base, tl_n, 40);
       if (STASH) fence_proxy_async();
       named_bar_sync(1 + slot, 128);         // everyone is done with the last step's bias row / head table
       if (STASH) stash_tile(c.act, SV_ADDF + 4, 2);   // coarse-radiance feature 2 (written into the dead hv tile)
       tc_fence_before();                     // order this tile's TMEM reads before the next tile's act_ready arrival
+      tl_mark(tl, tl_base, tl_n, 41);
       if (k + 2 < pair_tiles) begin_tile(nxt, k + 2, bias0);
+      tl_mark(tl, tl_base, tl_n, 42);
       if (valid) {
         auto sum2 = [](float2 v) { return v.x + v.y; };
         if (SIGMA_ONLY) {
@@ -493,6 +508,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) mlp_fw
           for (int j = 0; j < 9; ++j) dst[j] = make_float2(r[2 * j], r[2 * j + 1]);
         }
       }
+      tl_mark(tl, tl_base, tl_n, 43);
       cur = nxt;
     }
     if (STASH && gtid == 0) bulk_wait0();

@@ -84,7 +84,7 @@ constexpr int SV_FEAT = 37;                  // feature_linear output (no relu)
 constexpr int SV_DE = 41;                    // view-direction encoding (32 of 64 columns used)
 constexpr int SV_HV = 42;                    // relu(views_linears.0)
 constexpr int SV_ADDF = 46;                  // relu(additional_radiance_feature_linear.{0,1,2}), 6 blocks
-constexpr int SV_MASK = 52;                  // relu bit masks: 12 x [128 rows][8 words] (h0..h7, AF, HV, ADD01, ADD2)
+constexpr int SV_MASK = 52;                  // relu bit masks: 12 x [8 words][128 rows] (h0..h7, AF, HV, ADD01, ADD2)
 constexpr int SV_BLOCKS = 55;
 constexpr int64_t SV_BYTES = (int64_t)SV_BLOCKS * KB_BYTES;
 // gradient record per tile written by the dgrad kernel for the wgrad kernel

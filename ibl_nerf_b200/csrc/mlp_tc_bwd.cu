@@ -240,7 +240,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) mlp_dg
       const bool valid = real && p < prm.P;
       uint8_t* dy = prm.dy + (size_t)(real ? tile : 0) * DY_BYTES;
       const uint8_t* rec = prm.saved + (size_t)(real ? tile : 0) * SV_BYTES;
-      const uint32_t* masks = reinterpret_cast<const uint32_t*>(rec + (size_t)SV_MASK * KB_BYTES) + row * 8;   // + m * 1024 words
+      const uint32_t* masks = reinterpret_cast<const uint32_t*>(rec + (size_t)SV_MASK * KB_BYTES) + row;   // + m * 1024 + word * 128
       float g[18];
 #pragma unroll
       for (int j = 0; j < 9; ++j) {
@@ -285,8 +285,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) mlp_dg
       auto fetch_masks = [&](int mslot, uint4& a, uint4& b) {
         a = b = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
         if (mslot >= 0 && real) {
-          a = __ldg(reinterpret_cast<const uint4*>(masks + mslot * 1024));
-          b = __ldg(reinterpret_cast<const uint4*>(masks + mslot * 1024) + 1);
+          const uint32_t* m = masks + mslot * 1024;      // word-major: a warp's load of one word is 128 contiguous bytes
+          a = make_uint4(__ldg(m), __ldg(m + 128), __ldg(m + 256), __ldg(m + 384));
+          b = make_uint4(__ldg(m + 512), __ldg(m + 640), __ldg(m + 768), __ldg(m + 896));
         }
       };
       uint4 cm0, cm1, nm0, nm1;               // masks of the current / next phase
@@ -432,7 +433,7 @@ __global__ void __launch_bounds__(128, 2) mlp_dgrad_freeze_kernel(FreezeParams p
     const long long p = tile * TILE_M + row;
     const bool valid = p < prm.P;
     uint8_t* dy = prm.dy + (size_t)tile * DY_BYTES;
-    const uint32_t* masks = reinterpret_cast<const uint32_t*>(prm.saved + (size_t)tile * SV_BYTES + (size_t)SV_MASK * KB_BYTES) + row * 8;
+    const uint32_t* masks = reinterpret_cast<const uint32_t*>(prm.saved + (size_t)tile * SV_BYTES + (size_t)SV_MASK * KB_BYTES) + row;
     float g[18];
 #pragma unroll
     for (int j = 0; j < 9; ++j) {
@@ -457,9 +458,9 @@ __global__ void __launch_bounds__(128, 2) mlp_dgrad_freeze_kernel(FreezeParams p
                     make_uint4(pack_bf16x2(e[8 * ch], e[8 * ch + 1]), pack_bf16x2(e[8 * ch + 2], e[8 * ch + 3]),
                                pack_bf16x2(e[8 * ch + 4], e[8 * ch + 5]), pack_bf16x2(e[8 * ch + 6], e[8 * ch + 7])));
     }
-    const uint4 mw0 = __ldg(reinterpret_cast<const uint4*>(masks + 8 * 1024));
-    const uint4 mw1 = __ldg(reinterpret_cast<const uint4*>(masks + 8 * 1024) + 1);
-    const uint32_t mw[8] = {mw0.x, mw0.y, mw0.z, mw0.w, mw1.x, mw1.y, mw1.z, mw1.w};
+    uint32_t mw[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mw[j] = __ldg(masks + 8 * 1024 + j * 128);
     for (int cc = 0; cc < 8; ++cc) {
       float v[32];
 #pragma unroll

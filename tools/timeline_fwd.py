@@ -42,6 +42,6 @@ def show(name, ev, lo, hi):
     for tag, c in ev[lo:hi]:
         print("  tag %3d  t=%8d  d=%6s" % (tag, c - t0, "" if prev is None else c - prev))
         prev = c
-per = 2 * nst - 1
+per = 2 * nst - 1 + 4 + (2 if not sigma else 1)
 show("rank0 epilogue slot 0 (10+2s acc ready, 11+2s published)", e0, 2 * per, 3 * per + 2)
 show("leader MMA (100+2s+slot act ready; 200+2s+slot issued)", mm, 4 * 2 * nst, 4 * 2 * nst + 4 * nst)
