@@ -37,6 +37,7 @@ _SIGS = {
     "ibln_phase_b_loss": [c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_f, c_p, c_p, c_p],
     "ibln_sample_rays": [c_p, c_p, c_int, c_int, c_int, c_f, c_f, c_f, c_f, c_p, c_p, c_p, c_p, c_p, c_p, c_int],
     "ibln_pack_u8": [c_p, c_p, c_p, c_p, c_int, c_p],
+    "ibln_depth_to_normal": [c_p, c_int, c_int, c_f, c_f, c_f, c_f, c_p, c_p],
     "ibln_adam_step": [c_p, c_p, c_p, c_p, c_i64, c_f, c_f, c_f, c_f, c_int, c_f],
     "ibln_umma_selftest": [c_p, c_p, c_p, c_int, c_int, c_int],
     "ibln_umma_mn_selftest": [c_p, c_p, c_p, c_int],

@@ -209,3 +209,68 @@ extern "C" int ibln_pack_u8(const float* const* maps, const int64_t* sizes, cons
   ibln::pack_u8_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a, out);
   IBLN_RETURN_LAST();
 }
+
+// ---------------------------------------------------------------- normal map from a rendered depth image
+// utils/depth_to_normal_utils.py:9-46 (depth_to_position + depth_to_normal_image_space), which the export path calls
+// once per test image (ibl_nerf_renderer.py:903-906) on the host in numpy: unit camera rays * depth -> world
+// positions, edge-replicated central differences along x and y, normalise, cross(vb, va), normalise.
+// One thread per pixel; the four neighbour positions are recomputed from their depths (4 loads instead of a
+// position image round trip).  Degenerate differences give NaN exactly like the numpy 0/0.
+namespace ibln {
+struct Cam { float fx, fy, cx, cy; float r[9]; float t[3]; };
+__device__ __forceinline__ void pixel_position(const Cam& c, const float* __restrict__ depth, int width, int x, int y, float (&p)[3]) {
+  float d0 = __fdiv_rn((float)x - c.cx, c.fx), d1 = -__fdiv_rn((float)y - c.cy, c.fy), d2 = -1.0f;
+  const float nrm = fmaxf(__fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), 1.0f)), 1e-12f);   // F.normalize
+  d0 = __fdiv_rn(d0, nrm); d1 = __fdiv_rn(d1, nrm); d2 = __fdiv_rn(d2, nrm);
+  const float z = depth[(long long)y * width + x];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const float rd = __fadd_rn(__fadd_rn(__fmul_rn(d0, c.r[3 * i]), __fmul_rn(d1, c.r[3 * i + 1])), __fmul_rn(d2, c.r[3 * i + 2]));
+    p[i] = __fadd_rn(c.t[i], __fmul_rn(rd, z));
+  }
+}
+__device__ __forceinline__ void unit3(float (&v)[3]) {
+  const float n = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(v[0], v[0]), __fmul_rn(v[1], v[1])), __fmul_rn(v[2], v[2])));
+#pragma unroll
+  for (int i = 0; i < 3; ++i) v[i] = __fdiv_rn(v[i], n);
+}
+__global__ void __launch_bounds__(256) depth_to_normal_kernel(Cam c, const float* __restrict__ depth, int height, int width,
+                                                              float* __restrict__ normal) {
+  const long long total = (long long)height * width;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int y = (int)(i / width), x = (int)(i - (long long)y * width);
+    float l[3], r[3], u[3], b[3];
+    pixel_position(c, depth, width, max(x - 1, 0), y, l);
+    pixel_position(c, depth, width, min(x + 1, width - 1), y, r);
+    pixel_position(c, depth, width, x, max(y - 1, 0), u);
+    pixel_position(c, depth, width, x, min(y + 1, height - 1), b);
+    float va[3], vb[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { va[k] = __fsub_rn(r[k], l[k]); vb[k] = __fsub_rn(b[k], u[k]); }
+    unit3(va); unit3(vb);
+    float vc[3] = {__fsub_rn(__fmul_rn(vb[1], va[2]), __fmul_rn(vb[2], va[1])),
+                   __fsub_rn(__fmul_rn(vb[2], va[0]), __fmul_rn(vb[0], va[2])),
+                   __fsub_rn(__fmul_rn(vb[0], va[1]), __fmul_rn(vb[1], va[0]))};
+    unit3(vc);
+    normal[3 * i] = vc[0]; normal[3 * i + 1] = vc[1]; normal[3 * i + 2] = vc[2];
+  }
+}
+}  // namespace ibln
+
+extern "C" int ibln_depth_to_normal(const float* depth, int height, int width, float fx, float fy, float cx, float cy,
+                                    const float* c2w_host, float* normal, int device, void* stream) {
+  if (height < 0 || width < 0) return IBLN_EINVAL;
+  if (height == 0 || width == 0) return 0;
+  if (!depth || !c2w_host || !normal) return IBLN_EINVAL;
+  ibln::Cam c;
+  c.fx = fx; c.fy = fy; c.cx = cx; c.cy = cy;
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) c.r[3 * i + j] = c2w_host[4 * i + j];
+    c.t[i] = c2w_host[4 * i + 3];
+  }
+  DeviceGuard g(device);
+  long long blocks = ((long long)height * width + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  ibln::depth_to_normal_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(c, depth, height, width, normal);
+  IBLN_RETURN_LAST();
+}

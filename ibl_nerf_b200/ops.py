@@ -196,3 +196,20 @@ def shade(rays_d, normal, albedo, rough, irr, mip_rough, depth, near, far, prefi
     return _Shade.apply(rays_d, normal, albedo, rough.reshape(-1), irr.reshape(-1), mip_rough.reshape(-1),
                         depth.reshape(-1), near.reshape(-1), far.reshape(-1), prefiltered, lut,
                         0 if lut_coefficient == "F" else 1, correct_depth, want_srgb)
+
+
+# ----------------------------------------------------------------------------- export helpers
+def depth_to_normal_image_space(depth_map, pose, K):
+    """utils/depth_to_normal_utils.py:26-46 on the device (one kernel instead of a host numpy pass per test image):
+    depth_map [H,W] device fp32, pose = c2w (>= [3,4]; tensor, array or nested list), K intrinsics [3,3].
+    Returns the [H,W,3] normal image on depth_map's device (the reference returns a CPU tensor)."""
+    import numpy as np
+    depth_map = f32c(depth_map.detach())
+    if depth_map.dim() != 2:
+        raise ValueError("depth_map must be [H,W], got %s" % (tuple(depth_map.shape),))
+    h, w = depth_map.shape
+    c2w = np.ascontiguousarray(np.asarray(pose.detach().cpu() if torch.is_tensor(pose) else pose, dtype=np.float32)[:3, :4])
+    out = _new(depth_map, h, w, 3)
+    call("ibln_depth_to_normal", depth_map.device, ptr(depth_map), int(h), int(w), float(K[0][0]), float(K[1][1]), float(K[0][2]),
+         float(K[1][2]), ctypes.c_void_p(c2w.ctypes.data), ptr(out))
+    return out

@@ -523,13 +523,9 @@ def render_decomp_path(dataset_test, hwf, K, chunk, render_kwargs, savedir=None,
                           ("inferred_depth_map", "inferred_disp"), ("disp_map", "disp"), ("depth_map", "depth"),
                           ("target_depth_map", "target_depth")):
             append_result(res, key, i, name)
-        if "depth_map" in res:
-            try:
-                from utils.depth_to_normal_utils import depth_to_normal_image_space
-                res["normal_map_from_depth_map"] = depth_to_normal_image_space(res["depth_map"], c2w[:3, :4], K)
-                append_result(res, "normal_map_from_depth_map", i, "normal_from_depth")
-            except ImportError:
-                pass
+        if "depth_map" in res:     # ibl_nerf_renderer.py:903-906 (host numpy stencil there; one kernel here)
+            res["normal_map_from_depth_map"] = ops.depth_to_normal_image_space(res["depth_map"], c2w[:3, :4], K)
+            append_result(res, "normal_map_from_depth_map", i, "normal_from_depth")
         flush(i)
     for w in writers:
         w.result()

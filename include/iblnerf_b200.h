@@ -229,6 +229,13 @@ int ibln_sample_rays(const int* u, const int* v, int n, int height, int width, f
 int ibln_pack_u8(const float* const* maps, const int64_t* sizes, const int* transforms, const float* scales, int n_maps,
                  uint8_t* out, int device, void* stream);
 
+/* Normal map from a rendered depth image for the test-render export:
+ * utils/depth_to_normal_utils.py:9-46 (depth_to_position + depth_to_normal_image_space, called at
+ * ibl_nerf_renderer.py:903-906).  depth [height,width] device fp32; c2w HOST [3,4] row-major; intrinsics fx, fy, cx,
+ * cy; normal [height,width,3] device fp32.  Edge pixels replicate their neighbours (np.pad 'edge'). */
+int ibln_depth_to_normal(const float* depth, int height, int width, float fx, float fy, float cx, float cy,
+                         const float* c2w_host, float* normal, int device, void* stream);
+
 /* Self-test of the tcgen05 building block: D[128,N] = A[128,K] * B[N,K]^T with bf16 inputs staged
  * through the same swizzled shared-memory layout the MLP kernels use. a,b fp32 (rounded to bf16
  * inside), d fp32.  variant selects descriptor hypotheses (0 = production). */

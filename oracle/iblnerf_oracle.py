@@ -341,3 +341,23 @@ def render_rays(rays, p_coarse, p_fine, lut, n_samples=64, n_importance=128, per
         res[k + "0"] = v
     res["z_std"] = torch.std(zs, dim=-1, unbiased=False)
     return res
+
+
+def depth_to_normal(depth, c2w, K):
+    """utils/depth_to_normal_utils.py:9-46: depth_to_position (unit camera rays through integer pixel centres, rotated
+    by c2w[:3,:3], scaled by the depth, translated by c2w[:3,3]) then depth_to_normal_image_space (edge-padded central
+    differences, normalise, cross(vb, va), normalise).  depth [H,W], c2w [3,4], K [3,3] numpy -> [H,W,3] float32."""
+    depth = np.asarray(depth, dtype=np.float32)
+    c2w = np.asarray(c2w, dtype=np.float32)
+    h, w = depth.shape
+    i, j = np.meshgrid(np.arange(w, dtype=np.float32), np.arange(h, dtype=np.float32), indexing="xy")
+    dirs = np.stack([(i - np.float32(K[0][2])) / np.float32(K[0][0]), -(j - np.float32(K[1][2])) / np.float32(K[1][1]),
+                     -np.ones_like(i)], -1).astype(np.float32)
+    dirs = dirs / np.maximum(np.linalg.norm(dirs, axis=-1, keepdims=True), np.float32(1e-12))
+    rays_d = np.sum(dirs[..., None, :] * c2w[:3, :3], -1, dtype=np.float32)
+    pos = (c2w[:3, -1] + rays_d * depth[..., None]).astype(np.float32)
+    pad = np.pad(pos, ((1, 1), (1, 1), (0, 0)), "edge")
+    va = pad[1:-1, 2:, :] - pad[1:-1, :-2, :]
+    vb = pad[2:, 1:-1, :] - pad[:-2, 1:-1, :]
+    unit = lambda x: x / np.linalg.norm(x, axis=-1, keepdims=True)
+    return unit(np.cross(unit(vb), unit(va), axis=-1)).astype(np.float32)

@@ -218,8 +218,21 @@ def g_render_rays():
     npz("render_rays_test.npz", rays=rays, **{k: v for k, v in res.items()})
 
 
+def g_depth_to_normal():
+    from utils.depth_to_normal_utils import depth_to_normal_image_space      # utils/depth_to_normal_utils.py:26-46
+    g = torch.Generator().manual_seed(33)
+    h, w = 24, 40
+    yy, xx = torch.meshgrid(torch.linspace(-1, 1, h), torch.linspace(-1, 1, w), indexing="ij")
+    depth = 3.0 + 0.8 * torch.sin(2.5 * xx) * torch.cos(1.7 * yy) + 0.05 * torch.rand(h, w, generator=g)
+    ang = 0.4
+    c2w = torch.tensor([[np.cos(ang), 0., np.sin(ang), 0.3], [0., 1., 0., -0.2], [-np.sin(ang), 0., np.cos(ang), 1.5]], dtype=torch.float32)
+    K = np.array([[35.0, 0, w / 2], [0, 35.0, h / 2], [0, 0, 1]], dtype=np.float32)
+    n = depth_to_normal_image_space(depth, c2w, K)
+    npz("depth_to_normal.npz", depth=depth, c2w=c2w, K=K, normal=n)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["lut", "posenc", "sample_pdf", "composite", "shading", "mlp", "render_rays"]
+    which = sys.argv[1:] or ["lut", "posenc", "sample_pdf", "composite", "shading", "mlp", "render_rays", "depth_to_normal"]
     for w in which:
         {"lut": dump_lut, "posenc": g_posenc, "sample_pdf": g_sample_pdf, "composite": g_composite,
-         "shading": g_shading, "mlp": g_mlp, "render_rays": g_render_rays}[w]()
+         "shading": g_shading, "mlp": g_mlp, "render_rays": g_render_rays, "depth_to_normal": g_depth_to_normal}[w]()

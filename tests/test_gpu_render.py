@@ -200,3 +200,35 @@ def test_render_decomp_path_export(tmp_path):
         assert np.array_equal(out["depth"][i], want)
         png = imageio.imread(os.path.join(str(tmp_path), "depth_%03d.png" % i))
         assert np.array_equal(png, (255 * np.clip(want, 0, 1)).astype(np.uint8))
+
+        # normal image from the rendered depth (utils/depth_to_normal_utils.py:26-46, ibl_nerf_renderer.py:903-906)
+        from oracle import iblnerf_oracle as orc
+        want = (orc.depth_to_normal(res["depth_map"].cpu().numpy(), c2w[:3, :4].cpu().numpy(), K) + 1) * 0.5
+        got = out["normal_from_depth"][i]
+        assert got.shape == want.shape == (H, W, 3)
+        # the stencil divides differences of nearly equal positions: a few 1e-6 in the positions is 1e-4 in the normal
+        assert np.allclose(got, want, atol=2e-3), np.abs(got - want).max()
+        assert os.path.exists(os.path.join(str(tmp_path), "normal_from_depth_%03d.png" % i))
+
+
+def test_depth_to_normal_kernel_vs_reference_golden_and_oracle():
+    """ibln_depth_to_normal vs the reference's own output (golden) and, at a full image size, vs the oracle."""
+    import numpy as np
+    from oracle import iblnerf_oracle as orc
+    from ibl_nerf_b200 import ops
+    g = G("depth_to_normal.npz", DEV)
+    n = ops.depth_to_normal_image_space(g["depth"], g["c2w"], g["K"].cpu().numpy())
+    assert n.shape == g["normal"].shape and n.is_cuda
+    close(n, g["normal"], rtol=0, atol=5e-5, name="normal_from_depth")     # ill-conditioned differences, see the oracle test
+    # full-size image (the kitchen test views are 640 x 480), smooth depth + edge columns/rows
+    h, w = 480, 640
+    yy, xx = torch.meshgrid(torch.linspace(-1, 1, h), torch.linspace(-1, 1, w), indexing="ij")
+    depth = (4.0 + torch.sin(3 * xx) * torch.cos(2 * yy)).to(DEV)
+    c2w = torch.tensor([[0.8, 0., 0.6, 0.1], [0., 1., 0., 0.3], [-0.6, 0., 0.8, -1.0]])
+    K = np.array([[500.0, 0, w / 2], [0, 500.0, h / 2], [0, 0, 1]], dtype=np.float32)
+    got = ops.depth_to_normal_image_space(depth, c2w, K).cpu().numpy()
+    want = orc.depth_to_normal(depth.cpu().numpy(), c2w.numpy(), K)
+    assert np.allclose(np.linalg.norm(got, axis=-1), 1.0, atol=1e-5)
+    assert np.abs(got - want).max() < 5e-3 and np.abs(got - want).mean() < 1e-4
+    # empty image: no launch, no error
+    assert ops.depth_to_normal_image_space(torch.empty(0, 5, device=DEV), c2w, K).shape == (0, 5, 3)

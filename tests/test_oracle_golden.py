@@ -174,3 +174,12 @@ def test_render_rays_test_time():
         res = orc.render_rays(g["rays"], c, f, fx.load_lut(), perturb=0., approximate_radiance=True)
     for k in res:
         close(res[k], g[k], rtol=2e-3, atol=2e-4, name=k)
+
+
+def test_depth_to_normal():
+    """utils/depth_to_normal_utils.py:26-46 (export path): oracle vs the reference's output on a seeded depth image."""
+    g = G("depth_to_normal.npz")
+    n = orc.depth_to_normal(g["depth"].numpy(), g["c2w"].numpy(), g["K"].numpy())
+    # differences of nearly equal fp32 positions: summation-order ulps (1e-7 * |position|) show up as ~1e-5 in the unit vectors
+    close(n, g["normal"], rtol=0, atol=2e-5, name="normal_from_depth")
+    assert np.allclose(np.linalg.norm(n, axis=-1), 1.0, atol=1e-5)
