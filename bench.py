@@ -104,6 +104,52 @@ def cpu_reference_step(n_rays, threads):
     return time.perf_counter() - t0
 
 
+def eager_cuda_reference(n_rays, steps=2):
+    """The same reference algorithm (oracle port) in PyTorch EAGER mode on cuda:0 -- what a user of the reference gets
+    on this GPU without this package ("the oracle in eager CUDA fp32 as the reference-on-B200
+    bar").  A reported baseline like cpu_baseline: fp32 matmuls (parity setting) and TF32 matmuls (the setting of the
+    reference authors' Ampere GPUs, torch 1.11 default).  Returns {"fp32": rays/s, "tf32": rays/s}."""
+    import fixtures as fx
+    from oracle import iblnerf_oracle as orc
+    dev = torch.device("cuda:0")
+    out = {}
+    o, d, tg = synth_rays(n_rays, 1, dev)
+    lut = fx.load_lut().to(dev)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    try:
+        with torch.device(dev):         # the oracle (like the reference) allocates with bare factory calls
+            torch.manual_seed(0)
+            nets = []
+            for _ in range(2):
+                p = {}
+                for name, oo, ii in orc.PARAM_SHAPES_INIT_ORDER:
+                    lin = torch.nn.Linear(ii, oo)
+                    p[name + ".weight"], p[name + ".bias"] = lin.weight, lin.bias
+                nets.append(p)
+            rays = torch.cat([o, d, torch.full((n_rays, 1), 0.5), torch.full((n_rays, 1), 8.0), d / d.norm(dim=-1, keepdim=True)], -1)
+            for tag, tf32 in (("fp32", False), ("tf32", True)):
+                torch.backends.cuda.matmul.allow_tf32 = tf32
+                ts = []
+                for it in range(steps + 1):
+                    for p in nets:
+                        for v in p.values():
+                            v.grad = None
+                    torch.cuda.synchronize(dev)
+                    t0 = time.perf_counter()
+                    res = orc.render_rays(rays, nets[0], nets[1], lut, perturb=1.0, approximate_radiance=True)
+                    loss = fx.phase_b_loss(res, tg)
+                    loss.backward()
+                    float(loss)
+                    torch.cuda.synchronize(dev)
+                    if it > 0:
+                        ts.append(time.perf_counter() - t0)
+                    del res, loss
+                out[tag] = n_rays / (sum(ts) / len(ts))
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    return out
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's own algorithm on the box's host cores (rank 0 only)."""
     if rank != 0:
@@ -135,6 +181,7 @@ def main():
     ap.add_argument("--n-rand", type=int, default=N_RAND)
     ap.add_argument("--precision", default=None, choices=[None, "bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true", help="skip the PyTorch-eager-on-GPU run of the oracle (N=1 only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -294,7 +341,7 @@ def main():
             per = len(mlp["events"]) // args.steps
             line["mlp_fwd_launch_ms"] = [round(sum(mlp["events"][i * per + j][0].elapsed_time(mlp["events"][i * per + j][1])
                                                    for i in range(args.steps)) / args.steps, 4) for j in range(per)]
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:     # reported at N=1 only
             threads = os.cpu_count() or 1
             sample = 1024
             cpu_reference_step(64, threads)
@@ -302,6 +349,15 @@ def main():
             sec = sum(secs) / len(secs)
             line["cpu_baseline"] = {"value": sample / sec, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": "2 steps of %d rays (fwd+bwd, %.1f s), oracle/iblnerf_oracle.py, torch CPU fp32" % (sample, sum(secs))}
+        if not args.no_eager_baseline and world == 1:
+            try:
+                eg = eager_cuda_reference(n)
+                line["eager_cuda_baseline"] = {"value": eg["fp32"], "value_tf32": eg["tf32"], "unit": UNIT, "kind": "port",
+                                               "sample": "2 steps of %d rays (fwd+bwd) after 1 warm-up, oracle/iblnerf_oracle.py in "
+                                                         "PyTorch eager mode on cuda:0 (fp32 and TF32 matmuls)" % n}
+            except Exception as e:      # a reported baseline must never take the bench line down
+                line["eager_cuda_baseline"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
+            torch.cuda.empty_cache()
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
