@@ -56,7 +56,7 @@ _PLAIN = {  # no device/stream tail
     "ibln_debug_timeline": ([c_p], c_int),
 }
 
-ABI_VERSION = 2      # include/iblnerf_b200.h: IBLN_ABI_VERSION
+ABI_VERSION = 3      # include/iblnerf_b200.h: IBLN_ABI_VERSION
 _lib = None
 # kernels launched per entry point (for bench.py's gpu_launches); default 1
 KERNELS_PER_CALL = {"ibln_sgemm_wgrad": 2, "ibln_mlp_pack_weights": 3, "ibln_mlp_bwd": 2}

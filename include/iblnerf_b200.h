@@ -24,7 +24,7 @@ extern "C" {
 #endif
 
 #define IBLN_EINVAL (-1)
-#define IBLN_ABI_VERSION 2   /* 2: ibln_mlp_bwd gained freeze_mode; training-tail / export entry points */
+#define IBLN_ABI_VERSION 3   /* 2: ibln_mlp_bwd gained freeze_mode; training-tail / export entry points. 3: ibln_depth_to_normal; word-major relu masks in the stash */
 
 /* packed per-ray output of the compositing kernels: one row of IBLN_MAPS_STRIDE floats per ray */
 #define IBLN_MAPS_STRIDE 24
