@@ -13,7 +13,7 @@ cols = [("gpu__time_duration.sum", "ms"), ("dram__bytes_read.sum", "dram read"),
 units = dict(zip(head, rows[1]))
 with open(prefix + "_ncu_full.md", "w") as f:
     f.write("# ncu --set full, MLP kernels of one training step, %s\n\n" % title)
-    f.write("`ncu --set full --clock-control none --import-source on -k regex:mlp_(fwd|dgrad|wgrad)_kernel -s 30 -c 10 python bench.py --steps 1 --warmup 3 --no-cpu-baseline`\n\n")
+    f.write("`ncu --set full --clock-control none --import-source on -k regex:mlp_(fwd|dgrad|wgrad)_kernel -s 30 -c 10 python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-eager-baseline`\n\n")
     f.write("The ten MLP launches of ONE training step (N_rand = 4096): coarse main (stash), coarse eps-normal (sigma-only), coarse reflected, "
             "fine main (stash), fine eps-normal, fine reflected, then the backward of the fine and of the coarse network (dgrad, wgrad). "
             "Per-launch times under ncu are cold-cache and serialised.\n\n")
@@ -38,7 +38,7 @@ for r in rows[hi + 2:]:
         a[0] += 1; a[1] += float(r[mi].replace(",", "")) / 1e6
 tot = sum(a[1] for a in agg.values())
 with open(prefix + "_launches_summary.md", "w") as f:
-    f.write("# ncu launch list, %s\n\n`ncu --metrics gpu__time_duration.sum --clock-control none python bench.py --steps 1 --warmup 3 --no-cpu-baseline`\n\n" % title)
+    f.write("# ncu launch list, %s\n\n`ncu --metrics gpu__time_duration.sum --clock-control none python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-eager-baseline`\n\n" % title)
     f.write("All launches of the run (3 warm-up + 1 timed + 2+1 end-to-end steps = 7 training steps); per-launch times are cold-cache and serialised, so compare SHARES.\n\n")
     f.write("| kernel | launches | total ms | share |\n|---|---:|---:|---:|\n")
     for k, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:24]:
