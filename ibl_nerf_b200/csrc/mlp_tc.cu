@@ -246,7 +246,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) mlp_fw
           const Step st = step_at(s);
           const int nkb = st.aux_first + st.kb_act + st.aux_last;
           const int halves = st.n == 256 ? 2 : 1;      // my N/2 weight rows of a K-block = 128 or 64 rows of 128 B
-          for (int slot = 0; slot < 2; ++slot) {
+          // A step whose K-blocks fit the ring is streamed ONCE per round: both tile slots' MMAs read the same stages
+          // (the second pass releases them).  Halves the L2 -> shared weight traffic, which in the stash launches
+          // competes with the stash stores for the chip-wide L2 throughput.
+          const int passes = nkb <= N_STAGES ? 1 : 2;
+          for (int slot = 0; slot < passes; ++slot) {
             if (2 * r + slot >= pair_tiles) continue;
             for (int kbi = 0; kbi < nkb; ++kbi) {
               const int row0 = st.n == 256 ? (st.chunk_base + 2 * kbi + (int)rank) * 128 : (st.chunk_base + kbi) * 128 + (int)rank * 64;
@@ -275,6 +279,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) mlp_fw
             const Step st = step_at(s);
             const int nkb = st.aux_first + st.kb_act + st.aux_last;
             const uint32_t idesc = st.n == 256 ? IDESC256 : IDESC128;
+            const bool shared = nkb <= N_STAGES;            // see the producer: one weight pass serves both slots
+            const bool has1 = 2 * r + 1 < pair_tiles;
             for (int slot = 0; slot < 2; ++slot) {
               if (2 * r + slot >= pair_tiles) continue;
               mbar_wait(&act_ready[slot], act_phase[slot]);
@@ -284,20 +290,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) mlp_fw
               const uint32_t act_addr = smem_u32(smem + SMEM_ACT + slot * ACT_BYTES);
               const uint32_t aux_addr = smem_u32(smem + SMEM_AUX + slot * AUX_BYTES);
               const uint32_t d_tmem = tmem_base + slot * 256;
+              const bool release = !shared || slot == 1 || !has1;   // last reader of these stages
+              int st_i = stage;
+              uint32_t ph_i = phase;
               for (int kbi = 0; kbi < nkb; ++kbi) {
                 const bool from_aux = (st.aux_first && kbi == 0) || (st.aux_last && kbi == nkb - 1);
                 const uint32_t a_addr = from_aux ? aux_addr : act_addr + (kbi - st.aux_first) * KB_BYTES;
                 const int ksteps = (st.aux_last && kbi == nkb - 1) ? 2 : 4;
-                mbar_wait(&w_full[stage], phase);
+                mbar_wait(&w_full[st_i], ph_i);
                 tc_fence_after();
-                const uint32_t b_addr = smem_u32(smem + SMEM_RING + stage * KB_BYTES);
+                const uint32_t b_addr = smem_u32(smem + SMEM_RING + st_i * KB_BYTES);
                 for (int ks = 0; ks < ksteps; ++ks)
                   umma_bf16_pair(d_tmem, make_desc_kmajor_sw128(a_addr + ks * 32), make_desc_kmajor_sw128(b_addr + ks * 32),
                                  idesc, (kbi > 0 || ks > 0) ? 1u : 0u);
-                umma_commit_pair(&w_empty[stage]);
-                if (++stage == N_STAGES) { stage = 0; phase ^= 1; }
+                if (release) umma_commit_pair(&w_empty[st_i]);      // covers the first pass's reads of the stage too
+                if (++st_i == N_STAGES) { st_i = 0; ph_i ^= 1; }
               }
               umma_commit_pair(&acc_ready[slot]);
+              if (release) { stage = st_i; phase = ph_i; }
               tl_mark(prm.tl, 2048, tl_n, 200 + 2 * s + slot);
             }
           }

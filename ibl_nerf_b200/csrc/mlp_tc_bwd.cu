@@ -158,8 +158,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) mlp_dg
       for (long long r = 0; r < rounds; ++r)
         for (int t = 0; t < N_STEPS_BWD; ++t) {
           const BStep st = bstep_at(t);
-          for (int slot = 0; slot < 2; ++slot) {
-            if (2 * r + slot >= pair_tiles) continue;
+          static_assert(N_STAGES >= 4, "every dgrad step (<= 4 K-blocks) must fit the ring");
+          // every step's K-blocks fit the ring: streamed ONCE per round, both tile slots' MMAs read the same stages
+          // (mlp_tc.cu, forward producer)
+          {
             for (int kbi = 0; kbi < st.nkb; ++kbi) {
               const int row0 = (st.chunk_base + 2 * kbi + (int)rank) * 128;     // my 128 of the 256 output rows
               mbar_wait(&w_empty[stage], phase ^ 1);
@@ -189,16 +191,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) mlp_dg
             tl_mark(prm.tl, 2048, tl_n, 100 + t * 2 + slot);
             const uint32_t act_addr = smem_u32(smem + SMEM_ACT + slot * ACT_BYTES);
             const uint32_t d_tmem = tmem_base + slot * 256;
+            const bool release = slot == 1 || 2 * r + 1 >= pair_tiles;     // last reader of these stages
+            int st_i = stage;
+            uint32_t ph_i = phase;
             for (int kbi = 0; kbi < st.nkb; ++kbi) {
-              mbar_wait(&w_full[stage], phase);
+              mbar_wait(&w_full[st_i], ph_i);
               tc_fence_after();
-              const uint32_t b_addr = smem_u32(smem + SMEM_RING + stage * KB_BYTES);
+              const uint32_t b_addr = smem_u32(smem + SMEM_RING + st_i * KB_BYTES);
               for (int ks = 0; ks < 4; ++ks)
                 umma_bf16_pair(d_tmem, make_desc_kmajor_sw128(act_addr + kbi * KB_BYTES + ks * 32),
                                make_desc_kmajor_sw128(b_addr + ks * 32), IDESC256, (st.accumulate || kbi > 0 || ks > 0) ? 1u : 0u);
-              umma_commit_pair(&w_empty[stage]);
-              if (++stage == N_STAGES) { stage = 0; phase ^= 1; }
+              if (release) umma_commit_pair(&w_empty[st_i]);
+              if (++st_i == N_STAGES) { st_i = 0; ph_i ^= 1; }
             }
+            if (release) { stage = st_i; phase = ph_i; }
             umma_commit_pair(&acc_ready[slot]);
             tl_mark(prm.tl, 2048, tl_n, 200 + t * 2 + slot);
           }
