@@ -316,9 +316,9 @@ def main():
             ach = mlp["flops"] / (dur_ms * 1e-3) / 1e12
             roof = {"bound": "tensor", "kernel": "mlp_fwd_kernel (fused encode + MLP, tcgen05)", "achieved": ach, "peak": peak,
                     "unit": "TFLOP/s", "frac": ach / peak,
-                    # dram__bytes_read+write per launch, mean over the 6 launches of one step (profiles/r1j_ncu_full.md);
+                    # dram__bytes_read+write per launch, mean over the 6 launches of one step (profiles/r1_final_ncu_full.md);
                     # 99.5 % of it is the activation stash written by the two gradient launches
-                    "traffic": 1.236e9, "traffic_unit": "B/launch",
+                    "traffic": 1.228e9, "traffic_unit": "B/launch",
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)",
                     "launches": len(mlp["events"]), "share_of_step": dur_ms / ms_total}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
