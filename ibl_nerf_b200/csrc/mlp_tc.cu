@@ -165,10 +165,12 @@ __device__ __forceinline__ void process_chunk(const EpiCtx& c, Heads& hd, const 
 }
 
 // Drain chunks [CC0, CC0 + NCHUNK) of the accumulator (32 columns each) with the TMEM loads software-pipelined one
-// chunk ahead.  In the stash instantiation the chunk-pair loop of the head steps is deliberately NOT unrolled:
-// fully unrolled, those six steps were ~120 KB of straight-line code executed once per tile and 30 % of the epilogue
-// warps' stall samples there were instruction-fetch misses (stall_no_inst); rolled: stash forward 1.59 -> 1.53 ms.
-// Everywhere else unrolling wins (inference forward 1.00 ms unrolled, 1.05 heads rolled, 1.22 all rolled).
+// chunk ahead.  In the stash instantiation the chunk-pair loop of the head steps is only unrolled by 2: fully
+// unrolled, those six steps were ~120 KB of straight-line code executed once per tile and 30 % of the epilogue
+// warps' stall samples there were instruction-fetch misses (stall_no_inst).  Same-box A/B of the stash forward
+// (786 k points): fully unrolled 1.63 ms, rolled 1.45 ms, unrolled by 2 1.41 ms.  Everywhere else full unrolling
+// wins or ties (inference forward 1.00 ms unrolled or by 2, 1.05 heads rolled, 1.22 all rolled).
+constexpr int kDrainUnroll = 2;
 template <int KIND, bool STASH> constexpr bool drain_rolled() { return STASH && KIND != K_RELU_ACT; }
 template <int KIND, bool STASH, int CC0, int NCHUNK>
 __device__ __forceinline__ void drain(const EpiCtx& c, Heads& hd, int sv_blk, int sv_mask) {
@@ -189,7 +191,7 @@ __device__ __forceinline__ void drain(const EpiCtx& c, Heads& hd, int sv_blk, in
     if (mdst != nullptr) { __stcs(mdst + cc * 128, m0); __stcs(mdst + (cc + 1) * 128, m1); }
   };
   if (drain_rolled<KIND, STASH>()) {
-#pragma unroll 1
+#pragma unroll kDrainUnroll
     for (int cc = CC0; cc < CC0 + NCHUNK; cc += 2) pair(cc);
   } else {
 #pragma unroll
