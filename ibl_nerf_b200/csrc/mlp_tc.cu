@@ -1,19 +1,21 @@
 // Fused positional-encoding + IBLNeRF MLP on the 5th-generation tensor cores (north-star
 // subsystems 2 and 3).
 //
-// One persistent CTA per SM, 10 warps:
-//   warp 0      weight producer : streams the pre-swizzled bf16 weight chunks (16 KB each, packed by
-//               ibln_mlp_pack_weights in consumption order) from L2 into a 4-stage shared-memory
-//               ring with 1-D bulk TMA copies (cp.async.bulk + mbarrier complete_tx)
-//   warp 1      MMA issuer      : one elected thread issues tcgen05.mma (M=128, N=128, K=16, bf16 ->
-//               fp32 in TMEM) for two tile slots in ping-pong order; tcgen05.commit frees ring stages
-//               and publishes finished accumulators
+// Persistent CTA PAIRS (cluster of 2 = the two SMs of a TPC), one CTA per SM, 10 warps each:
+//   warp 0      weight producer : streams its half of the pre-swizzled bf16 weight K-blocks (packed by
+//               ibln_mlp_pack_weights in consumption order) from L2 into a 4-stage shared-memory ring with
+//               tensor-map TMA (cp.async.bulk.tensor.2d.cta_group::2, both CTAs' bytes credited to the
+//               leader's mbarrier); a step's K-blocks are streamed once per round and read by both tile slots
+//   warp 1      MMA issuer      : (leader CTA) one elected thread issues tcgen05.mma.cta_group::2 (M=256 over
+//               the pair's two 128-point tiles, N=256 or 128, K=16, bf16 -> fp32 in TMEM) for two tile slots in
+//               ping-pong order; tcgen05.commit (multicast) frees ring stages and publishes accumulators
 //   warps 2-5   slot-0 epilogue : generate sample points + positional encoding straight into the
 //   warps 6-9   slot-1 epilogue   swizzled A-operand tile, drain TMEM (tcgen05.ld), bias + relu + bf16
 //               pack back into the A tile of the next layer, and the small heads (sigma, roughness,
 //               albedo, irradiance, radiance x4) as fp32 dot products on the un-rounded accumulators
 // Activations never leave the SM; a tile of 128 points flows through all layers while the other
-// slot's epilogue overlaps its MMAs.
+// slot's epilogue overlaps its MMAs.  STASH instantiation (training): every layer's activation tile, the relu
+// bit masks and the encodings are also copied to the per-tile stash record for dgrad / wgrad.
 #include "mlp_tc.cuh"
 
 namespace ibln {

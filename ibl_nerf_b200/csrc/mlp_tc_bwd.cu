@@ -1,8 +1,9 @@
 // Tensor-core backward of the IBLNeRF MLP (north-star subsystem 3, gradients).
 //
-//  dgrad kernel : same warp-specialised structure as the forward kernel (bulk-TMA weight producer,
-//                 single-thread tcgen05.mma issuer, two ping-pong tile slots with 4 epilogue warps
-//                 each).  Walks the layers in reverse: dX = dY * W as M=128 x N=256 GEMMs against
+//  dgrad kernel : same warp-specialised CTA-pair structure as the forward kernel (tensor-map TMA weight
+//                 producer streaming each step's K-blocks once per round for both tile slots, single-thread
+//                 tcgen05.mma.cta_group::2 issuer, two ping-pong tile slots with 4 epilogue warps
+//                 each).  Walks the layers in reverse: dX = dY * W as M=256 (pair) x N=256 GEMMs against
 //                 the TRANSPOSED packed weight stream, applies the relu bit masks stashed by the
 //                 forward pass, keeps the running gradient tile in shared memory as the next A
 //                 operand, and writes every dY tile (bf16, operand layout) for the wgrad kernel.
