@@ -27,6 +27,8 @@ import torch.distributed as dist  # noqa: E402
 
 METRIC = "train_rays_per_sec"
 UNIT = "rays/s"
+WORKLOAD = ("IBL-NeRF kitchen full-IBL training step (render_decomp + phase-B loss + backward + Adam), "
+            "N_rand=%d rays/GPU, 64 coarse + 128 fine samples")
 N_RAND = 4096
 FLOP_FULL, FLOP_SIGMA = 1591552, 982528          # algorithmic FLOP / point (unpadded)
 FLOP_PER_RAY_STEP = 2432139264                   # full-IBL training step
@@ -165,7 +167,9 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": world, "steps": steps,
             "warmup": 1, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic rays, random-init weights",
-            "config": {"workload": "kitchen full-IBL training step (fwd+bwd), 64+128 samples/ray", "n_rand_sample": sample},
+            # the product arm's workload (same string); each reference step is a bounded sample of it
+            "config": {"workload": WORKLOAD % args.n_rand, "n_rand_per_gpu": args.n_rand,
+                       "sample": "each step = fwd+bwd of %d of the %d rays (the reference algorithm scales linearly in rays)" % (sample, args.n_rand)},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": "%d rays x %d steps, oracle/iblnerf_oracle.py (torch CPU fp32)" % (sample, steps)},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -325,8 +329,7 @@ def main():
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16" if (args.precision or ib.mlp.default_precision()) == "bf16" else "f32",
                 "data": "synthetic rays (seeded), random-init weights of the kitchen architecture",
-                "config": {"workload": "IBL-NeRF kitchen full-IBL training step (render_decomp + phase-B loss + backward + Adam), "
-                                       "N_rand=%d rays/GPU, 64 coarse + 128 fine samples" % n,
+                "config": {"workload": WORKLOAD % n,
                            "n_rand_per_gpu": n, "parallelism": "ray-sharded dp%d, NCCL grad all-reduce" % world,
                            "l2": "per-step working set >> 126 MB L2 (no explicit flush)",
                            "step_tflops": world * n * FLOP_PER_RAY_STEP / (ms_step * 1e-3) / 1e12},
