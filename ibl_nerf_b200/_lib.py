@@ -8,7 +8,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libiblnerf_b200.so")
+# IBLN_LIB selects another build of the same ABI (tools/ use it for the diagnostics build, libiblnerf_b200_diag.so)
+LIB_PATH = os.environ.get("IBLN_LIB") or os.path.join(_HERE, "libiblnerf_b200.so")
 
 c_int, c_i64, c_f, c_p = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
 
@@ -42,8 +43,15 @@ _SIGS = {
     "ibln_umma_selftest": [c_p, c_p, c_p, c_int, c_int, c_int],
     "ibln_umma_mn_selftest": [c_p, c_p, c_p, c_int],
     "ibln_umma_pair_selftest": [c_p, c_p, c_p, c_int],
+}
+# include/iblnerf_b200_diag.h: bound only when the loaded library is the diagnostics build
+_SIGS_DIAG = {
     "ibln_store_probe": [c_p, c_i64, c_int, c_int],
     "ibln_tmem_probe": [c_p, c_int, c_int, c_int],
+}
+_PLAIN_DIAG = {
+    "ibln_debug_set": ([c_int], c_int),
+    "ibln_debug_timeline": ([c_p], c_int),
 }
 _PLAIN = {  # no device/stream tail
     "ibln_abi_version": ([], c_int),
@@ -52,11 +60,9 @@ _PLAIN = {  # no device/stream tail
     "ibln_mlp_packed_bytes": ([], c_i64),
     "ibln_mlp_saved_bytes": ([c_i64], c_i64),
     "ibln_mlp_bwd_workspace_bytes": ([c_i64], c_i64),
-    "ibln_debug_set": ([c_int], c_int),
-    "ibln_debug_timeline": ([c_p], c_int),
 }
 
-ABI_VERSION = 3      # include/iblnerf_b200.h: IBLN_ABI_VERSION
+ABI_VERSION = 4      # include/iblnerf_b200.h: IBLN_ABI_VERSION
 _lib = None
 # kernels launched per entry point (for bench.py's gpu_launches); default 1
 KERNELS_PER_CALL = {"ibln_sgemm_wgrad": 2, "ibln_mlp_pack_weights": 3, "ibln_mlp_bwd": 2}
@@ -94,6 +100,15 @@ def lib():
             fn = getattr(h, name)
             fn.argtypes = at
             fn.restype = rt
+        if hasattr(h, "ibln_debug_set"):
+            for name, at in _SIGS_DIAG.items():
+                fn = getattr(h, name)
+                fn.argtypes = at + [c_int, c_p]
+                fn.restype = c_int
+            for name, (at, rt) in _PLAIN_DIAG.items():
+                fn = getattr(h, name)
+                fn.argtypes = at
+                fn.restype = rt
         _lib = h
     return _lib
 

@@ -27,17 +27,27 @@ def needs_build():
     return any(os.path.getmtime(s) > t for s in srcs)
 
 
-def build_library(force=False, verbose=False):
+LIB_DIAG = os.path.join(HERE, "libiblnerf_b200_diag.so")
+
+
+def build_library(force=False, verbose=False, diag=False):
+    """diag=True builds the tuning library libiblnerf_b200_diag.so (same sources + -DIBLN_DIAGNOSTICS: bandwidth
+    probes, clock64 timelines, launch-skip switches; include/iblnerf_b200_diag.h) -- never loaded by the product."""
+    if diag:
+        return _build(LIB_DIAG, os.path.join(HERE, "build_diag"), ["-DIBLN_DIAGNOSTICS"], verbose)
     if not force and not needs_build():
         return LIB
+    return _build(LIB, os.path.join(HERE, "build"), [], verbose)
+
+
+def _build(LIB, odir, extra, verbose):
     objs = []
     procs = []
-    odir = os.path.join(HERE, "build")
     os.makedirs(odir, exist_ok=True)
     for src in sorted(glob.glob(os.path.join(CSRC, "*.cu"))):
         obj = os.path.join(odir, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
-        cmd = [_nvcc()] + NVCC_FLAGS + ["-c", src, "-o", obj]
+        cmd = [_nvcc()] + NVCC_FLAGS + extra + ["-c", src, "-o", obj]
         if verbose:
             print(" ".join(cmd))
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
@@ -51,4 +61,4 @@ def build_library(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose=True))
+    print(build_library(force="--force" in sys.argv, verbose=True, diag="--diag" in sys.argv))

@@ -21,8 +21,10 @@
 namespace ibln {
 namespace mlp {
 
+#ifdef IBLN_DIAGNOSTICS
 int g_dbg_host = 0;
-void* g_timeline = nullptr;   // diagnostics: device buffer set by ibln_debug_timeline
+void* g_timeline = nullptr;
+#endif
 
 int make_chunk_stream_map(CUtensorMap* map, const void* base, int n_chunks) {
   typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -664,9 +666,10 @@ umma_pair_selftest_kernel(const float* __restrict__ A, const float* __restrict__
 using namespace ibln;
 using namespace ibln::mlp;
 
+#ifdef IBLN_DIAGNOSTICS
 extern "C" int ibln_debug_timeline(void* device_buf) { ibln::mlp::g_timeline = device_buf; return 0; }
-// diagnostics (host side only: bit4 skip the dgrad launch, bit5 skip the wgrad launch)
 extern "C" int ibln_debug_set(int flags) { ibln::mlp::g_dbg_host = flags; return 0; }
+#endif
 
 extern "C" int64_t ibln_mlp_packed_bytes(void) { return PACKED_BYTES; }
 
@@ -704,7 +707,7 @@ extern "C" int ibln_mlp_fwd(const void* packed, int mode, const float* pts, cons
   prm.out = out;
   prm.saved = (uint8_t*)saved;
   prm.n_tiles = (prm.gen.P + TILE_M - 1) / TILE_M;
-  prm.tl = (unsigned long long*)g_timeline;
+  prm.tl = (unsigned long long*)IBLN_DBG_TIMELINE;
   { int rc = make_chunk_stream_map(&prm.wmap, packed, N_CHUNKS); if (rc != 0) return rc; }
   long long grid = (long long)(num_sms(device) & ~1);            // CTA pairs
   if (((prm.n_tiles + 1) & ~1LL) < grid) grid = (prm.n_tiles + 1) & ~1LL;

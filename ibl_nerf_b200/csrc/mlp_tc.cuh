@@ -181,7 +181,19 @@ static __global__ void pack_consts_kernel(PackArgs a, float* __restrict__ cst) {
 // defined in mlp_tc_bwd.cu: packs the transposed (dgrad) weight chunk stream at packed + PACKED_BWD_OFF
 int launch_pack_bwd(const PackArgs& a, uint8_t* packed, cudaStream_t stream);
 
-// diagnostics: blocks 0/1 append (tag << 48 | clock64) to a timeline buffer (ibln_debug_timeline)
+// Diagnostics exist only in the tuning build (-DIBLN_DIAGNOSTICS -> libiblnerf_b200_diag.so, include/iblnerf_b200_diag.h);
+// in the product library the switches are compile-time zero and the timeline pointer is always NULL.
+#ifdef IBLN_DIAGNOSTICS
+extern int g_dbg_host;        // host-side switches of ibln_mlp_bwd: bit4 skip the dgrad launch, bit5 skip the wgrad launch
+extern void* g_timeline;      // device buffer set by ibln_debug_timeline
+#define IBLN_DBG_FLAGS (::ibln::mlp::g_dbg_host)
+#define IBLN_DBG_TIMELINE (::ibln::mlp::g_timeline)
+#else
+#define IBLN_DBG_FLAGS 0
+#define IBLN_DBG_TIMELINE nullptr
+#endif
+
+// blocks 0/1 append (tag << 48 | clock64) to the timeline buffer
 __device__ __forceinline__ void tl_mark(unsigned long long* tl, int base, int& n, int tag) {
   if (tl != nullptr && blockIdx.x < 2 && n < 1000)
     tl[blockIdx.x * 4096 + base + n++] = ((unsigned long long)tag << 48) | ((unsigned long long)clock64() & 0xFFFFFFFFFFFFull);

@@ -17,8 +17,6 @@
 
 namespace ibln {
 namespace mlp {
-extern int g_dbg_host;
-extern void* g_timeline;   // diagnostics: device buffer set by ibln_debug_timeline (mlp_tc.cu)   // diagnostics (mlp_tc.cu): bit4 skip dgrad, bit5 skip wgrad
 
 // ---------------------------------------------------------------- dgrad step program
 constexpr int N_STEPS_BWD = 12;
@@ -830,14 +828,14 @@ extern "C" int ibln_mlp_bwd(const void* packed, const void* saved, const float* 
     // ---- dgrad chain
     DgradParams dp;
     dp.packed = (const uint8_t*)packed; dp.saved = (const uint8_t*)saved; dp.g_out = g_out; dp.dy = (uint8_t*)workspace;
-    dp.flat_grad = flat_grad; dp.P = n_pts; dp.n_tiles = n_tiles; dp.dbg = g_dbg_host; dp.tl = (unsigned long long*)g_timeline;
+    dp.flat_grad = flat_grad; dp.P = n_pts; dp.n_tiles = n_tiles; dp.dbg = IBLN_DBG_FLAGS; dp.tl = (unsigned long long*)IBLN_DBG_TIMELINE;
     IBLN_CUDA(cudaFuncSetAttribute(mlp_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_REQUEST));
     long long grid = (long long)(sms & ~1);                      // CTA pairs
     if (((n_tiles + 1) & ~1LL) < grid) grid = (n_tiles + 1) & ~1LL;
     { int rc = make_chunk_stream_map(&dp.wmap, (const uint8_t*)packed + PACKED_BWD_OFF, N_CHUNKS_BWD); if (rc != 0) return rc; }
-    if (!(g_dbg_host & 16)) mlp_dgrad_kernel<<<(unsigned)grid, N_THREADS, SMEM_REQUEST, stream>>>(dp);
+    if (!(IBLN_DBG_FLAGS & 16)) mlp_dgrad_kernel<<<(unsigned)grid, N_THREADS, SMEM_REQUEST, stream>>>(dp);
     IBLN_CUDA(cudaGetLastError());
-    if (g_dbg_host & 32) return 0;
+    if (IBLN_DBG_FLAGS & 32) return 0;
   } else {
     FreezeParams fp;
     fp.packed = (const uint8_t*)packed; fp.saved = (const uint8_t*)saved; fp.g_out = g_out; fp.dy = (uint8_t*)workspace;

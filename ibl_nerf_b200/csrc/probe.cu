@@ -1,4 +1,7 @@
-// Bandwidth probes (diagnostics used while tuning; not part of the product path).
+// Bandwidth probes: compiled only into the tuning build (-DIBLN_DIAGNOSTICS, python -m ibl_nerf_b200.build --diag);
+// the product library contains none of this.
+#ifdef IBLN_DIAGNOSTICS
+#include "../../include/iblnerf_b200_diag.h"
 #include "tc_common.cuh"
 
 namespace ibln {
@@ -90,3 +93,4 @@ extern "C" int ibln_tmem_probe(long long* out, int warps, int iters, int depth, 
   tmem_probe_kernel<<<1, warps * 32, 0, (cudaStream_t)stream>>>(out, iters, depth);
   IBLN_RETURN_LAST();
 }
+#endif  // IBLN_DIAGNOSTICS

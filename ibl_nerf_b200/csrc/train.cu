@@ -274,3 +274,12 @@ extern "C" int ibln_depth_to_normal(const float* depth, int height, int width, f
   ibln::depth_to_normal_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(c, depth, height, width, normal);
   IBLN_RETURN_LAST();
 }
+
+// ---------------------------------------------------------------- ABI bookkeeping
+extern "C" int ibln_abi_version(void) { return IBLN_ABI_VERSION; }
+
+extern "C" const char* ibln_error_string(int code) {
+  if (code == 0) return "success";
+  if (code == IBLN_EINVAL) return "iblnerf_b200: invalid argument";
+  return cudaGetErrorString((cudaError_t)code);
+}

@@ -33,6 +33,8 @@ def install(reference_src):
     for name in list(sys.modules):
         if name == "nerf_models" or name.startswith("nerf_models."):
             del sys.modules[name]
+    from . import factory
+    factory.REFERENCE_SRC = reference_src           # create_IBLNeRF runs the reference's own control-plane code from here
     # harmless replacement of the scratch module that train.py / test.py star-import (train.py:21)
     stub = types.ModuleType("miscellaneous.test_dataset_speed")
     stub.__all__ = []
@@ -48,8 +50,20 @@ def main(argv=None):
     os.chdir(src)                                    # the reference uses paths relative to src/ (../data, ../configs)
     sys.argv = [argv[1] + ".py"] + argv[2:]
     mod = importlib.import_module(argv[1])
-    args = mod.recursive_config_parser().parse_args()
+    args = prepare_args(mod, mod.recursive_config_parser().parse_args())
     getattr(mod, argv[1])(args)
+
+
+def prepare_args(mod, args):
+    """The prologue of the drivers' own `__main__` blocks (train.py:530-541, test.py:160-174), which importing
+    the module does not execute: the device, the experiment name derived from the config file name, and (test.py)
+    the export directory."""
+    args.device = mod.device
+    if args.expname is None:
+        args.expname = args.config.split("/")[-1].split(".")[0]
+    if hasattr(args, "export_basedir") and args.export_basedir is None and mod.__name__ == "test":
+        args.export_basedir = args.basedir.replace("logs", "logs_eval")
+    return args
 
 
 if __name__ == "__main__":

@@ -36,6 +36,7 @@ class _MLPTc(torch.autograd.Function):
         call("ibln_mlp_fwd", dev, ptr(packed), mode, ptr(pts), ptr(o), ptr(d), ptr(z), n, s, 0.0, 0, ptr(out), ptr(saved),
              flops=P * FLOP_FULL)
         ctx.packed, ctx.stash, ctx.P = packed, saved, P
+        ctx.net, ctx.pack_gen = net, net._pack_gen      # the packed image is rewritten IN PLACE on a re-pack
         ctx.sink = getattr(net, "_grad_sink", None)
         ctx.shapes = [p.shape for p in params]
         # forward_freezed (ibl_nerf.py:88-152): with freeze_radiance only these layers are outside torch.no_grad()
@@ -54,6 +55,9 @@ class _MLPTc(torch.autograd.Function):
         dev = g_out.device
         h = _lib.lib()
         g_out = f32c(g_out)
+        if ctx.net._pack_gen != ctx.pack_gen:
+            raise _lib.IblnError("IBLNeRF parameters were re-packed between this forward and its backward (optimizer step or "
+                                 "load_state_dict while the graph was alive): dgrad would run with the new weights")
         # flat gradient image (state-dict order).  With a gradient sink (training.FlatParameters) the kernel
         # accumulates straight into the optimizer's flat buffer and autograd sees no per-tensor gradients.
         flat = ctx.sink if ctx.sink is not None else torch.zeros(FLAT_PARAMS, dtype=torch.float32, device=dev)
@@ -103,6 +107,7 @@ class IBLNeRF(nn.Module):
         self.precision = None          # None -> mlp.default_precision()
         self._packed = None
         self._packed_key = None
+        self._pack_gen = 0
 
     def __str__(self):
         return "\n".join(["[NeRFDecomp", "\t- depth : {}".format(self.D), "\t- width : {}".format(self.W),
@@ -137,6 +142,7 @@ class IBLNeRF(nn.Module):
             arr = (ctypes.c_void_p * 46)(*[ctypes.c_void_p(f32c(p.detach()).data_ptr()) for p in ps])
             call("ibln_mlp_pack_weights", dev, arr, ptr(self._packed))
             self._packed_key = key
+            self._pack_gen += 1
         return self._packed
 
     def invalidate_packed(self):

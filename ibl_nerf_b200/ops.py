@@ -193,6 +193,11 @@ def shade(rays_d, normal, albedo, rough, irr, mip_rough, depth, near, far, prefi
     """Split-sum shading; returns (out [N,16], out_srgb [N,16] or empty); columns SH_*."""
     if lut_coefficient not in ("F", "F0"):
         raise ValueError
+    if torch.is_grad_enabled() and normal.requires_grad:
+        # the reference lets colour gradients reach a trainable normal (target_normal_map_for_radiance_calculation =
+        # "inferred_normal_map", ibl_nerf_renderer.py:374-375); ibln_shade_bwd has no d/d normal -- refuse, do not drop it
+        raise NotImplementedError("split-sum shading with a differentiable normal map is not supported "
+                                  "(no shipped config trains normals through the shading)")
     return _Shade.apply(rays_d, normal, albedo, rough.reshape(-1), irr.reshape(-1), mip_rough.reshape(-1),
                         depth.reshape(-1), near.reshape(-1), far.reshape(-1), prefiltered, lut,
                         0 if lut_coefficient == "F" else 1, correct_depth, want_srgb)

@@ -122,15 +122,21 @@ def raw2outputs(rays_o, rays_d, z_vals, z_vals_constant, network_query_fn, netwo
     coarse_radiance_maps = [col(maps, ops.MAP_COARSE + 3 * k, ops.MAP_COARSE + 3 * k + 3) for k in range(n_coarse)]
     fused_gamma = gamma_correct and is_radiance_sigmoid      # kernel already produced pow(x+eps, 1/2.2)
 
-    target_depth_map = depth_map
-    if kwargs.get("depth_map_from_ground_truth", False):
-        target_depth_map = gt_values["depth"][..., 0]
+    # The reference edits `target_depth_map` IN PLACE while it still aliases `depth_map` (:249-256), and evaluates
+    # `disp_map` (:258), the mip level (:458-459) and the returned depth_map after that write: masked pixels of all
+    # three carry the edited depth unless the depth came from the ground truth (no alias then).
+    depth_aliased = not kwargs.get("depth_map_from_ground_truth", False)
+    target_depth_map = depth_map if depth_aliased else gt_values["depth"][..., 0]
+    depth_override = None
     if kwargs.get("edit_intrinsic", False) and kwargs.get("edit_depth", False):
-        target_depth_map = target_depth_map.clone()
-        target_depth_map[mask_all] = gt_values["edit_depth"][..., 0][mask_all]
+        depth_override = gt_values["edit_depth"][..., 0]
     if kwargs.get("insert_object", False):
-        target_depth_map = target_depth_map.clone()
-        target_depth_map[mask_all] = gt_values["object_insert_depth"][..., 0][mask_all]
+        depth_override = gt_values["object_insert_depth"][..., 0]
+    if depth_override is not None:
+        target_depth_map = torch.where(mask_all, depth_override.to(target_depth_map.dtype), target_depth_map)
+        if depth_aliased:
+            depth_map = target_depth_map
+            disp_map = 1. / torch.max(1e-10 * torch.ones_like(depth_map), depth_map / acc_map)
 
     x_surface = (rays_o + rays_d * target_depth_map[..., None]).detach()                       # :262-263
 
@@ -259,6 +265,8 @@ def raw2outputs(rays_o, rays_d, z_vals, z_vals_constant, network_query_fn, netwo
         reflected_radiance_map = prefiltered_env_maps[:, 0]
         reflected_coarse_radiance_map = [prefiltered_env_maps[:, 1 + k] for k in range(n_coarse)]
 
+        if not calculate_roughness_from_gt:
+            roughness_map = target_roughness_map        # same tensor in the reference (:324): the mip level sees the edits
         correct = bool(kwargs.get("correct_depth_for_prefiltered_radiance_infer", False))     # :455-462
         n_r = depth_map.shape[0]
         near = _per_ray(kwargs["near"] if correct else 0., n_r, raw.device)
@@ -475,7 +483,7 @@ def render_decomp_path(dataset_test, hwf, K, chunk, render_kwargs, savedir=None,
             vals.append(f32c(img))
         sizes = [v.numel() for v in vals]
         flat = torch.cat([v.reshape(-1) for v in vals])
-        host = torch.empty(flat.shape, dtype=torch.float32, pin_memory=True)
+        host = torch.empty(flat.shape, dtype=torch.float32, device="cpu", pin_memory=True)
         host.copy_(flat, non_blocking=True)
         atlas_h = None
         if savedir is not None:
@@ -485,7 +493,7 @@ def render_decomp_path(dataset_test, hwf, K, chunk, render_kwargs, savedir=None,
             call("ibln_pack_u8", dev, (ctypes.c_void_p * k)(*[ctypes.c_void_p(t.data_ptr()) for t in srcs]),
                  (ctypes.c_int64 * k)(*sizes), (ctypes.c_int * k)(*[p[3] for p in pending]),
                  (ctypes.c_float * k)(*[p[4] for p in pending]), k, ptr(atlas))
-            atlas_h = torch.empty(atlas.shape, dtype=torch.uint8, pin_memory=True)
+            atlas_h = torch.empty(atlas.shape, dtype=torch.uint8, device="cpu", pin_memory=True)
             atlas_h.copy_(atlas, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
         arr, a8 = host.numpy(), (atlas_h.numpy() if atlas_h is not None else None)

@@ -24,7 +24,8 @@ extern "C" {
 #endif
 
 #define IBLN_EINVAL (-1)
-#define IBLN_ABI_VERSION 3   /* 2: ibln_mlp_bwd gained freeze_mode; training-tail / export entry points. 3: ibln_depth_to_normal; word-major relu masks in the stash */
+#define IBLN_ABI_VERSION 4   /* 2: ibln_mlp_bwd gained freeze_mode; training-tail / export entry points. 3: ibln_depth_to_normal; word-major relu masks in the stash.
+                              * 4: diagnostics (probes, debug switches) left the product ABI (iblnerf_b200_diag.h); training-tail additions */
 
 /* packed per-ray output of the compositing kernels: one row of IBLN_MAPS_STRIDE floats per ray */
 #define IBLN_MAPS_STRIDE 24
@@ -246,18 +247,6 @@ int ibln_umma_selftest(const float* a, const float* b, float* d, int n, int k, i
 int ibln_umma_mn_selftest(const float* x, const float* y, float* d, int n, int device, void* stream);
 /* cta_group::2 operand/commit self-test: D[256,256] = A[256,K] * B[256,K]^T on one CTA pair (K in {64..256}). */
 int ibln_umma_pair_selftest(const float* a, const float* b, float* d, int k, int device, void* stream);
-
-/* Diagnostics: write `total_bytes` to `out` from `ctas` CTAs (mode 0/1: bulk TMA stores from shared memory,
- * 1 / 4 in flight; mode 2: coalesced st.global.v4) -- used to measure the achievable stash write bandwidth. */
-int ibln_store_probe(void* out, int64_t total_bytes, int mode, int ctas, int device, void* stream);
-/* Diagnostics: TMEM read bandwidth -- `warps` warps issue `iters` x `depth` tcgen05.ld 32x32b.x32 each;
- * out[0] = elapsed clocks of warp 0. */
-int ibln_tmem_probe(long long* out, int warps, int iters, int depth, int device, void* stream);
-/* Diagnostics (process-global, not thread-safe; tuning tools only): host-side switches of ibln_mlp_bwd
- * (bit 4 skip the dgrad launch, bit 5 skip the wgrad launch), and an optional device buffer (>= 8192 uint64) into
- * which CTAs 0/1 of the MLP kernels append (tag << 48 | clock64) marks of their pipeline phases (NULL = off). */
-int ibln_debug_set(int flags);
-int ibln_debug_timeline(void* device_buf);
 
 #ifdef __cplusplus
 }

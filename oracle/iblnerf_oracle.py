@@ -246,7 +246,8 @@ def shade(rays_d, normal, albedo, rough, irr, depth, near, far, prefiltered, lut
           lut_coefficient="F", correct_depth=True, mip_rough=None):
     """nerf_models/ibl_nerf_renderer.py:412-474 + microfacet.py:8-12.
     albedo [N,3], rough [N] (target roughness), irr [N,1], prefiltered [N,4,3], near/far [N,1].
-    mip_rough: the UNEDITED roughness_map used for the mip level (:459); defaults to rough."""
+    mip_rough: roughness used for the mip level (:459 reads `roughness_map`, which is the same tensor as the target
+    roughness unless that came from the ground truth); defaults to rough."""
     mip_rough = rough if mip_rough is None else mip_rough
     ndv = (-rays_d * normal).sum(-1).clamp(0, 1)
     a, b = lut_bilinear(lut, ndv, rough)
@@ -286,24 +287,72 @@ def srgb(x):
 
 
 # --------------------------------------------------------------------------- orchestration
+def object_masks(mask_img, count):
+    """nerf_models/ibl_nerf_renderer.py:222-227 / 232-237: object i is painted with value 10(i+1)/255."""
+    masks = [torch.logical_and(11 * (i + 1) / 255. > mask_img, mask_img > 9 * (i + 1) / 255.) for i in range(count)]
+    return masks, mask_img > 0
+
+
 def raw2outputs(rays_o, rays_d, z, z_const, query, near, far, lut=None, approximate_radiance=False,
-                eps=0.01, gamma_correct=True, lut_coefficient="F", correct_depth=True, n_coarse=3):
-    """nerf_models/ibl_nerf_renderer.py:153-527 for the kitchen configuration (normal from depth
-    gradient epsilon, sigmoid radiance, reflected ray under no_grad, no edit/insert masks)."""
+                eps=0.01, gamma_correct=True, lut_coefficient="F", correct_depth=True, n_coarse=3, gt_values=None, **edit):
+    """nerf_models/ibl_nerf_renderer.py:153-527 for the kitchen configuration (normal from depth gradient epsilon,
+    sigmoid radiance, reflected ray under no_grad) including the two editing modes of test.py (`edit`: insert_object /
+    edit_intrinsic and their lists, :218-256, 378-410).  The reference performs the edits IN PLACE on tensors that
+    alias depth_map / roughness_map / albedo_map / irradiance_map, so the edited depth also feeds disp_map (:258), the
+    surface point, the mip level (:458-459) and the returned depth_map, and the edited roughness feeds the mip level."""
     pts = rays_o[:, None, :] + rays_d[:, None, :] * z[..., None]
     raw = query(pts, rays_d)
     res = composite(raw, z, rays_d, n_coarse)
+    masks = mask_all = None
+    if edit.get("edit_intrinsic", False):
+        masks, mask_all = object_masks(gt_values["edit_intrinsic_mask"][:, 0], edit["num_edit_objects"])
+        if edit.get("edit_depth", False):
+            res["depth_map"] = torch.where(mask_all, gt_values["edit_depth"][..., 0], res["depth_map"])
+    elif edit.get("insert_object", False):
+        masks, mask_all = object_masks(gt_values["object_insert_mask"][:, 0], edit["num_insert_objects"])
+        res["depth_map"] = torch.where(mask_all, gt_values["object_insert_depth"][..., 0], res["depth_map"])
+    if mask_all is not None:
+        res["disp_map"] = 1. / torch.max(1e-10 * torch.ones_like(res["depth_map"]), res["depth_map"] / res["acc_map"])
     res["target_depth_map"] = res["depth_map"]
     x_surface = (rays_o + rays_d * res["depth_map"][:, None]).detach()
     if approximate_radiance:
         with torch.no_grad():
             normal = normal_eps(rays_o, rays_d, z, query, eps)
+        albedo, rough, irr = res["albedo_map"], res["roughness_map"], res["irradiance_map"]
+        vec = lambda v: torch.tensor(v, dtype=torch.float32)
+        if edit.get("edit_intrinsic", False):
+            if edit.get("edit_normal", False):
+                gt_n = torch.nn.functional.normalize(2 * gt_values["edit_normal"] - 1, dim=-1)
+                normal = torch.where(mask_all[:, None], gt_n, normal)
+            if edit.get("edit_albedo", False):
+                albedo = albedo.clone()
+                if edit.get("edit_albedo_by_img", False):
+                    albedo[mask_all] = gt_values["edit_albedo"][mask_all]
+                else:
+                    for i in range(edit["num_edit_objects"]):
+                        albedo[masks[i]] = vec(edit["editing_target_albedo_list"][3 * i:3 * i + 3])
+            if edit.get("edit_roughness", False):
+                rough = rough.clone()
+                if edit.get("edit_roughness_by_img"):
+                    rough[mask_all] = gt_values["edit_roughness"][mask_all][0]
+                else:
+                    for i, r in enumerate(edit.get("editing_target_roughness_list", [])):
+                        rough[masks[i]] = r
+        elif edit.get("insert_object", False):
+            gt_n = torch.nn.functional.normalize(2 * gt_values["object_insert_normal"] - 1, dim=-1)
+            normal = torch.where(mask_all[:, None], gt_n, normal)
+            albedo, rough, irr = albedo.clone(), rough.clone(), irr.clone()
+            for i in range(edit["num_insert_objects"]):
+                rough[masks[i]] = edit["inserting_target_roughness_list"][i]
+                if edit["inserting_target_irradiance_list"][i] > 0:
+                    irr[masks[i]] = edit["inserting_target_irradiance_list"][i]
+                albedo[masks[i]] = vec(edit["inserting_target_albedo_list"][3 * i:3 * i + 3])
+        res["albedo_map"], res["roughness_map"], res["irradiance_map"] = albedo, rough, irr
         refl = reflect(rays_d, normal)
         with torch.no_grad():
             rpts = x_surface[:, None, :] + refl[:, None, :] * z_const[..., None]
             pre = composite_simple(query(rpts, refl), z_const, refl, n_coarse)
-        sh = shade(rays_d, normal, res["albedo_map"], res["roughness_map"], res["irradiance_map"],
-                   res["depth_map"], near, far, pre, lut, lut_coefficient, correct_depth)
+        sh = shade(rays_d, normal, albedo, rough, irr, res["depth_map"], near, far, pre, lut, lut_coefficient, correct_depth)
         res.update(sh)
         res["target_normal_map"] = normal
         res["reflected_radiance_map"] = pre[:, 0]

@@ -110,3 +110,20 @@ def phase_b_loss(result, targets):
         if key + "0" in result:
             loss = loss + mse(result[key + "0"], targets["rgb"] if tk == "rgb" else targets[tk])
     return loss
+
+
+def edit_insert_inputs(n=48, seed=61):
+    """gt_values / kwargs of the two editing modes of test.py (object_insert.txt, edit_intrinsic.txt): two objects whose
+    mask value is 10(i+1)/255 (ibl_nerf_renderer.py:224-227), a third of the rays in each, the rest unmasked."""
+    g = torch.Generator().manual_seed(seed)
+    mask = torch.zeros(n, 3)
+    mask[: n // 3] = 10 / 255.
+    mask[n // 3: 2 * n // 3] = 20 / 255.
+    gt = {"object_insert_mask": mask, "edit_intrinsic_mask": mask.clone(),
+          "object_insert_depth": 1.0 + 4.0 * torch.rand(n, 3, generator=g), "edit_depth": 1.5 + 3.0 * torch.rand(n, 3, generator=g),
+          "object_insert_normal": torch.rand(n, 3, generator=g), "edit_normal": torch.rand(n, 3, generator=g)}
+    insert = dict(insert_object=True, num_insert_objects=2, inserting_target_roughness_list=[0.15, 0.7],
+                  inserting_target_irradiance_list=[0.8, -1.0], inserting_target_albedo_list=[0.9, 0.2, 0.1, 0.1, 0.5, 0.8])
+    edit = dict(edit_intrinsic=True, num_edit_objects=2, edit_depth=True, edit_normal=True, edit_albedo=True, edit_roughness=True,
+                editing_target_roughness_list=[0.05, 0.9], editing_target_albedo_list=[0.2, 0.7, 0.3, 0.6, 0.6, 0.1])
+    return gt, insert, edit

@@ -142,6 +142,27 @@ def g_shading():
     npz("normal_eps.npz", rays_o=ro, rays_d=rd, z=z, normal=nrm)
 
 
+def g_edit_insert():
+    """raw2outputs in the object-insertion and intrinsic-editing modes (ibl_nerf_renderer.py:218-256, 378-410) over the
+    analytic field: pins the in-place aliasing of depth_map / roughness_map (edited values drive disp_map, the mip level
+    and the returned depth_map)."""
+    n, s = 48, 64
+    lut = fx.load_lut()
+    ro, rd = fx.make_rays(n, seed=62)
+    ro = ro * 0.3
+    z = fx.make_sorted_z(n, s, seed=63)
+    near = torch.full((n, 1), fx.NEAR)
+    far = torch.full((n, 1), fx.FAR)
+    gt, insert, edit = fx.edit_insert_inputs(n)
+    for tag, mode in (("insert", insert), ("edit", edit)):
+        with torch.no_grad():
+            res = raw2outputs(ro, rd, z, z, fx.analytic_query, fx.STUB_NET, brdf_lut=lut, epsilon=0.01, gamma_correct=True,
+                              approximate_radiance=True, lut_coefficient="F", gt_values={k: v.clone() for k, v in gt.items()},
+                              target_normal_map_for_radiance_calculation="normal_map_from_depth_gradient_epsilon",
+                              correct_depth_for_prefiltered_radiance_infer=True, near=near, far=far, **mode)
+        npz("edit_%s.npz" % tag, rays_o=ro, rays_d=rd, z=z, **{k: v for k, v in res.items() if v is not None})
+
+
 def build_nets():
     torch.manual_seed(0)
     coarse = IBLNeRF(**fx.KITCHEN_ARCH)
@@ -232,7 +253,7 @@ def g_depth_to_normal():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["lut", "posenc", "sample_pdf", "composite", "shading", "mlp", "render_rays", "depth_to_normal"]
+    which = sys.argv[1:] or ["lut", "posenc", "sample_pdf", "composite", "shading", "mlp", "render_rays", "depth_to_normal", "edit_insert"]
     for w in which:
         {"lut": dump_lut, "posenc": g_posenc, "sample_pdf": g_sample_pdf, "composite": g_composite,
-         "shading": g_shading, "mlp": g_mlp, "render_rays": g_render_rays, "depth_to_normal": g_depth_to_normal}[w]()
+         "shading": g_shading, "edit_insert": g_edit_insert, "mlp": g_mlp, "render_rays": g_render_rays, "depth_to_normal": g_depth_to_normal}[w]()

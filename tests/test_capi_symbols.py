@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(h, n), "missing export: " + n
     assert set(names) == set(_lib.exported_names()), set(names) ^ set(_lib.exported_names())
     hh = _lib.lib()
-    assert hh.ibln_abi_version() == _lib.ABI_VERSION == 3
+    assert hh.ibln_abi_version() == _lib.ABI_VERSION == 4
     assert hh.ibln_mlp_packed_bytes() == (98 + 92) * 16384 + 4 * 6296      # fwd chunks + consts + transposed (dgrad) chunks
 
 

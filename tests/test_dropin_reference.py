@@ -52,3 +52,33 @@ def test_reference_drivers_bind_to_dropin(tmp_path):
     code = SCRIPT % dict(root=ROOT, ref=REF, tmp=str(tmp_path))
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert "DROPIN_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+
+
+DRY = r'''
+import os, sys
+sys.path.insert(0, %(root)r)
+import torch
+torch.set_default_tensor_type = lambda *a, **k: None      # no CUDA in the authoring container: keep tensors on the CPU
+from ibl_nerf_b200 import launcher, synthetic_dataset, _lib
+synthetic_dataset.write_dataset(%(data)r, n_train=3, n_test=2, size=(64, 80))
+try:
+    launcher.main([%(ref)r, %(mode)r, "--config", "../configs/IBL-NeRF/kitchen/IBL-NeRF.txt", "--datadir", %(data)r,
+                   "--basedir", %(logs)r, "--N_iter", "3", "--N_rand", "64"])
+    raise SystemExit("expected IblnError from the first render (no CPU fallback)")
+except _lib.IblnError as e:
+    import traceback
+    tb = traceback.format_exc()
+    assert "render_decomp" in tb and "stratified_z" in tb, tb
+print("REACHED_RENDER")
+'''
+
+
+@pytest.mark.parametrize("mode", ["train", "test"])
+def test_launcher_main_drives_the_reference_up_to_the_first_render(tmp_path, mode):
+    """launcher.main == the drivers' own __main__ (device, expname from the config name, export_basedir), dataset
+    load, log dir, the reference's create_IBLNeRF with this package's types substituted, sample generator: everything up
+    to the first kernel call runs here; on CPU tensors the product path then refuses (no fallback)."""
+    os.makedirs(tmp_path / "logs" / "IBL-NeRF", exist_ok=True)
+    code = DRY % dict(root=ROOT, ref=REF, mode=mode, data=str(tmp_path / "kitchen"), logs=str(tmp_path / "logs"))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert "REACHED_RENDER" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]

@@ -77,3 +77,37 @@ def test_shade_kernel_vs_oracle_random():
     (out_s[:, 10:13] * cot.to(DEV)).sum().backward()
     for a, b, nm in zip(gl, leaves, ("g_albedo", "g_rough", "g_irr")):
         close(a.grad, b.grad, rtol=2e-3, atol=1e-5, name=nm)
+
+
+@pytest.mark.parametrize("tag", ["insert", "edit"])
+def test_raw2outputs_edit_and_insert_modes_golden(tag):
+    """Object insertion / intrinsic editing (test.py with object_insert.txt / edit_intrinsic.txt) against the reference:
+    the edited depth and roughness reach disp_map, the mip level and the returned depth_map exactly as through the
+    reference's in-place writes on aliased tensors (ibl_nerf_renderer.py:249-258, 324, 395-407, 458-459)."""
+    g = G("edit_%s.npz" % tag, DEV)
+    n = g["z"].shape[0]
+    gt, insert, edit = fx.edit_insert_inputs(n)
+    gt = {k: v.to(DEV) for k, v in gt.items()}
+    lut = fx.load_lut().to(DEV)
+    near = torch.full((n, 1), fx.NEAR, device=DEV)
+    far = torch.full((n, 1), fx.FAR, device=DEV)
+    with torch.no_grad():
+        res = ib.raw2outputs(g["rays_o"], g["rays_d"], g["z"], g["z"], fx.analytic_query, fx.STUB_NET, brdf_lut=lut, epsilon=0.01,
+                             gamma_correct=True, approximate_radiance=True, lut_coefficient="F", gt_values=gt,
+                             target_normal_map_for_radiance_calculation="normal_map_from_depth_gradient_epsilon",
+                             correct_depth_for_prefiltered_radiance_infer=True, near=near, far=far,
+                             **(insert if tag == "insert" else edit))
+    res = {k: v for k, v in res.items() if v is not None}
+    m = (gt["object_insert_mask"][:, 0] > 0).cpu()
+    for k in g:
+        if k in ("rays_o", "rays_d", "z"):
+            continue
+        assert k in res, k
+        a, b = res[k].reshape(g[k].shape).cpu(), g[k].cpu()
+        # masked rays: normal, depth, roughness, albedo are prescribed -> everything but the network-driven reflected
+        # march is well conditioned; unmasked rays keep the finite-difference normal's ~1e-3 conditioning
+        dep = any(t in k for t in ("normal", "n_dot_v", "specular", "diffuse", "color", "reflected", "prefiltered"))
+        close(a[~m], b[~m], rtol=5e-3 if dep else 2e-4, atol=3e-3 if dep else 2e-5, name=k + " (unmasked)")
+        tight = k in ("depth_map", "target_depth_map", "disp_map", "roughness_map", "albedo_map", "irradiance_map",
+                      "target_normal_map", "n_dot_v_map")
+        close(a[m], b[m], rtol=2e-4 if tight else 5e-3, atol=2e-5 if tight else 3e-3, name=k + " (masked)")

@@ -89,6 +89,27 @@ def test_shading_raw2outputs(coef):
     close(cap["main"].grad, g["g_raw"], rtol=1e-4, atol=1e-7, name="g_raw")
 
 
+@pytest.mark.parametrize("tag", ["insert", "edit"])
+def test_edit_and_insert_modes(tag):
+    """The editing modes of test.py (object_insert.txt / edit_intrinsic.txt): masked overwrites that the reference
+    performs in place on aliased tensors -- depth_map, disp_map and the mip level see the edited values."""
+    g = G("edit_%s.npz" % tag)
+    n = g["z"].shape[0]
+    gt, insert, edit = fx.edit_insert_inputs(n)
+    with torch.no_grad():
+        res = orc.raw2outputs(g["rays_o"], g["rays_d"], g["z"], g["z"], lambda p, v: fx.analytic_query(p, v, None),
+                              torch.full((n, 1), fx.NEAR), torch.full((n, 1), fx.FAR), fx.load_lut(), True, gt_values=gt,
+                              **(insert if tag == "insert" else edit))
+    for k in g:
+        if k in ("rays_o", "rays_d", "z"):
+            continue
+        assert k in res, k
+        close(res[k], g[k], rtol=2e-5, atol=2e-6, name=k)
+    m = gt["object_insert_mask"][:, 0] > 0
+    want = (gt["object_insert_depth"] if tag == "insert" else gt["edit_depth"])[:, 0]
+    assert torch.equal(g["depth_map"][m], want[m]) and torch.equal(g["target_depth_map"], g["depth_map"])
+
+
 def _nets():
     """Same construction order / seed as make_golden.build_nets, with the oracle's own parameter table."""
     torch.manual_seed(0)

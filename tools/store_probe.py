@@ -1,4 +1,5 @@
 import sys, os
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__))); import _diag  # noqa: diagnostics build of the library
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from ibl_nerf_b200._lib import call, ptr

@@ -1,5 +1,6 @@
 """Per-step clock64 timeline of CTA pair 0 of the forward kernel (diagnostics hook ibln_debug_timeline)."""
 import sys, os, ctypes
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__))); import _diag  # noqa: diagnostics build of the library
 R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, R); sys.path.insert(0, os.path.join(R, "tests"))
 import torch, fixtures as fx
