@@ -22,10 +22,12 @@ _SIGS = {
     "ibln_merge_sort_z": [c_p, c_p, c_int, c_int, c_int, c_p],
     "ibln_composite_fwd": [c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_p],
     "ibln_composite_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_p],
-    "ibln_composite_simple_fwd": [c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_p],
+    "ibln_composite_simple_fwd": [c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_int, c_p, c_p],
     "ibln_depth_fwd": [c_p, c_p, c_p, c_int, c_int, c_int, c_p, c_p, c_p],
     "ibln_normal_eps_points": [c_p, c_p, c_p, c_int, c_int, c_f, c_p],
-    "ibln_normal_eps_finish": [c_p, c_p, c_int, c_f, c_p, c_p],
+    "ibln_normal_eps_finish": [c_p, c_p, c_int, c_f, c_p, c_p, c_p, c_p, c_int, c_p],
+    "ibln_shade_fwd_maps": [c_p] * 6 + [c_int, c_p, c_int, c_int, c_int, c_int, c_int, c_p, c_p],
+    "ibln_shade_bwd_maps": [c_p] * 6 + [c_int, c_p, c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_p],
     "ibln_shade_fwd": [c_p] * 10 + [c_int, c_p, c_int, c_int, c_int, c_int, c_int, c_p, c_p],
     "ibln_shade_bwd": [c_p] * 10 + [c_int, c_p, c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_p, c_p, c_p, c_p],
     "ibln_encode": [c_p, c_i64, c_int, c_p, c_i64],
@@ -35,11 +37,13 @@ _SIGS = {
     "ibln_mlp_pack_weights": [c_p, c_p],
     "ibln_mlp_fwd": [c_p, c_int, c_p, c_p, c_p, c_p, c_i64, c_int, c_f, c_int, c_p, c_p],
     "ibln_mlp_bwd": [c_p, c_p, c_p, c_i64, c_p, c_p, c_int],
-    "ibln_phase_b_loss": [c_p, c_p, c_p, c_p, c_p, c_p, c_int, c_f, c_p, c_p, c_p],
+    "ibln_image_losses": [c_p] * 7 + [c_int] + [c_f] * 6 + [c_p, c_p, c_p],
     "ibln_sample_rays": [c_p, c_p, c_int, c_int, c_int, c_f, c_f, c_f, c_f, c_p, c_p, c_p, c_p, c_p, c_p, c_int],
     "ibln_pack_u8": [c_p, c_p, c_p, c_p, c_int, c_p],
     "ibln_depth_to_normal": [c_p, c_int, c_int, c_f, c_f, c_f, c_f, c_p, c_p],
     "ibln_adam_step": [c_p, c_p, c_p, c_p, c_i64, c_f, c_f, c_f, c_f, c_int, c_f],
+    "ibln_adam_step_pack": [c_p, c_p, c_p, c_p, c_int, c_f, c_f, c_f, c_f, c_int, c_f, c_p],
+    "ibln_zero": [c_p, c_i64],
     "ibln_umma_selftest": [c_p, c_p, c_p, c_int, c_int, c_int],
     "ibln_umma_mn_selftest": [c_p, c_p, c_p, c_int],
     "ibln_umma_pair_selftest": [c_p, c_p, c_p, c_int],
@@ -65,7 +69,7 @@ _PLAIN = {  # no device/stream tail
 ABI_VERSION = 4      # include/iblnerf_b200.h: IBLN_ABI_VERSION
 _lib = None
 # kernels launched per entry point (for bench.py's gpu_launches); default 1
-KERNELS_PER_CALL = {"ibln_sgemm_wgrad": 2, "ibln_mlp_pack_weights": 3, "ibln_mlp_bwd": 2}
+KERNELS_PER_CALL = {"ibln_sgemm_wgrad": 2, "ibln_mlp_pack_weights": 3, "ibln_mlp_bwd": 2, "ibln_adam_step_pack": 2, "ibln_zero": 0}
 # bench.py sets this to {} to collect per-entry launch counts, CUDA-event pairs and algorithmic FLOPs;
 # PROFILE_EVENTS (None = every entry) limits the CUDA-event bracketing to the named entry points
 PROFILE = None

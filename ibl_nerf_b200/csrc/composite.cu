@@ -184,7 +184,10 @@ composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
         }
       }
     } else {
-      if (lane < 3 + 3 * nc) pre_out[(int64_t)r * (3 + 3 * nc) + lane] = s_out[lane];
+      if (lane < 3 + 3 * nc) {
+        pre_out[(int64_t)r * (3 + 3 * nc) + lane] = s_out[lane];
+        if (maps_srgb != nullptr) maps_srgb[(int64_t)r * (3 + 3 * nc) + lane] = srgbf(s_out[lane]);   // :485-496 gamma
+      }
     }
     __syncwarp();
   }
@@ -472,10 +475,10 @@ extern "C" int ibln_composite_fwd(const float* raw, const float* z, const float*
 }
 
 extern "C" int ibln_composite_simple_fwd(const float* raw, const float* z, const float* dirs, int n, int S, int C, int nc,
-                                         int sigm, float* pre_out, int device, void* stream) {
+                                         int sigm, float* pre_out, float* pre_srgb, int device, void* stream) {
   if (n == 0) return 0;
   if (!pre_out) return IBLN_EINVAL;
-  return launch_fwd<true>(raw, z, dirs, nullptr, n, S, C, nc, sigm, nullptr, nullptr, nullptr, pre_out, device, stream);
+  return launch_fwd<true>(raw, z, dirs, nullptr, n, S, C, nc, sigm, nullptr, nullptr, pre_srgb, pre_out, device, stream);
 }
 
 extern "C" int ibln_composite_bwd(const float* raw, const float* z, const float* rays_d, const float* noise,

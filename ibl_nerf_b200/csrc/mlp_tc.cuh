@@ -125,8 +125,7 @@ __host__ __device__ inline ChunkSrc chunk_src(int chunk) {
   return ChunkSrc{0, 0, 0, 0, 0};
 }
 
-static __global__ void pack_chunks_kernel(PackArgs a, uint8_t* __restrict__ packed) {
-  int chunk = blockIdx.x;
+__device__ __forceinline__ void pack_chunk_body(const PackArgs& a, uint8_t* __restrict__ packed, int chunk) {
   ChunkSrc c = chunk_src(chunk);
   const float* W = a.p[c.param];
   for (int e = threadIdx.x; e < 128 * 8; e += blockDim.x) {
@@ -142,9 +141,9 @@ static __global__ void pack_chunks_kernel(PackArgs a, uint8_t* __restrict__ pack
     *reinterpret_cast<uint4*>(packed + (size_t)chunk * KB_BYTES + swz_offset(row, c16)) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
+static __global__ void pack_chunks_kernel(PackArgs a, uint8_t* __restrict__ packed) { pack_chunk_body(a, packed, blockIdx.x); }
 
-static __global__ void pack_consts_kernel(PackArgs a, float* __restrict__ cst) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void pack_consts_body(const PackArgs& a, float* __restrict__ cst, int i) {
   if (i >= C_TOTAL) return;
   float v = 0.f;
   if (i < C_SR) {
@@ -177,9 +176,16 @@ static __global__ void pack_consts_kernel(PackArgs a, float* __restrict__ cst) {
   }
   cst[i] = v;
 }
+static __global__ void pack_consts_kernel(PackArgs a, float* __restrict__ cst) {
+  pack_consts_body(a, cst, blockIdx.x * blockDim.x + threadIdx.x);
+}
 
 // defined in mlp_tc_bwd.cu: packs the transposed (dgrad) weight chunk stream at packed + PACKED_BWD_OFF
 int launch_pack_bwd(const PackArgs& a, uint8_t* packed, cudaStream_t stream);
+// defined in mlp_tc_bwd.cu: all three sections of the packed image (forward chunk stream, constants, transposed
+// stream) of up to 4 networks whose parameters live back to back in one flat fp32 buffer (state-dict order), ONE launch
+struct PackFlat { const float* flat[4]; uint8_t* packed[4]; };
+int launch_pack_flat(const PackFlat& pf, int n_nets, cudaStream_t stream);
 
 // Diagnostics exist only in the tuning build (-DIBLN_DIAGNOSTICS -> libiblnerf_b200_diag.so, include/iblnerf_b200_diag.h);
 // in the product library the switches are compile-time zero and the timeline pointer is always NULL.

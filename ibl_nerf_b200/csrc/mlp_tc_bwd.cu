@@ -53,8 +53,7 @@ __host__ __device__ inline BChunkSrc bchunk_src(int chunk) {
   return BChunkSrc{0, 0, 0, 0};
 }
 
-static __global__ void pack_bwd_chunks_kernel(PackArgs a, uint8_t* __restrict__ out) {
-  int chunk = blockIdx.x;
+__device__ __forceinline__ void pack_bwd_chunk_body(const PackArgs& a, uint8_t* __restrict__ out, int chunk) {
   BChunkSrc c = bchunk_src(chunk);
   const float* W = a.p[c.param];
   for (int e = threadIdx.x; e < 128 * 8; e += blockDim.x) {
@@ -70,6 +69,8 @@ static __global__ void pack_bwd_chunks_kernel(PackArgs a, uint8_t* __restrict__ 
     *reinterpret_cast<uint4*>(out + (size_t)chunk * KB_BYTES + swz_offset(n, c16)) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
+
+static __global__ void pack_bwd_chunks_kernel(PackArgs a, uint8_t* __restrict__ out) { pack_bwd_chunk_body(a, out, blockIdx.x); }
 
 int launch_pack_bwd(const PackArgs& a, uint8_t* packed, cudaStream_t stream) {
   pack_bwd_chunks_kernel<<<N_CHUNKS_BWD, 256, 0, stream>>>(a, packed + PACKED_BWD_OFF);
@@ -89,6 +90,28 @@ __host__ __device__ inline FlatOff flat_offsets() {
 // indices into the 23 Linear layers: 0..7 positions, 8 views, 9 feature, 10 sigma, 11 albedo_f, 12 albedo,
 // 13 rough, 14 irr_f, 15 irr, 16 rad, 17..19 add_f, 20..22 add
 constexpr int FLAT_TOTAL = 798994;
+
+// Re-pack straight from the optimizer's flat parameter buffer (training.FlatParameters): blockIdx.y = network,
+// blockIdx.x walks the forward chunks, then the constant section, then the transposed (dgrad) chunks.
+constexpr int PACK_CONST_BLOCKS = (C_TOTAL + 255) / 256;
+static __global__ void __launch_bounds__(256) pack_flat_kernel(PackFlat pf) {
+  const float* base = pf.flat[blockIdx.y];
+  uint8_t* out = pf.packed[blockIdx.y];
+  PackArgs a;
+  const FlatOff fo = flat_offsets();
+#pragma unroll
+  for (int i = 0; i < 23; ++i) { a.p[2 * i] = base + fo.w[i]; a.p[2 * i + 1] = base + fo.b[i]; }
+  int b = blockIdx.x;
+  if (b < N_CHUNKS) { pack_chunk_body(a, out, b); return; }
+  b -= N_CHUNKS;
+  if (b < PACK_CONST_BLOCKS) { pack_consts_body(a, reinterpret_cast<float*>(out + PACKED_CONST_OFF), b * 256 + (int)threadIdx.x); return; }
+  pack_bwd_chunk_body(a, out + PACKED_BWD_OFF, b - PACK_CONST_BLOCKS);
+}
+
+int launch_pack_flat(const PackFlat& pf, int n_nets, cudaStream_t stream) {
+  pack_flat_kernel<<<dim3(N_CHUNKS + PACK_CONST_BLOCKS + N_CHUNKS_BWD, n_nets), 256, 0, stream>>>(pf);
+  return (int)cudaGetLastError();
+}
 
 // ---------------------------------------------------------------- dgrad kernel
 struct DgradParams {
@@ -917,4 +940,23 @@ extern "C" int ibln_umma_mn_selftest(const float* x, const float* y, float* d, i
   IBLN_CUDA(cudaFuncSetAttribute(umma_mn_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   umma_mn_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(x, y, d, n);
   IBLN_RETURN_LAST();
+}
+
+// Adam over the flat parameter buffer of n_nets networks + the bf16 re-pack of all of them: 2 launches per step
+// instead of 1 + 3 per network (ibln_adam_step + ibln_mlp_pack_weights).
+extern "C" int ibln_adam_step_pack(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int n_nets, float lr,
+                                   float beta1, float beta2, float eps, int step, float grad_scale,
+                                   void* const* packed_host, int device, void* stream) {
+  if (n_nets < 1 || n_nets > 4 || !packed_host) return IBLN_EINVAL;
+  int rc = ibln_adam_step(param, grad, exp_avg, exp_avg_sq, (int64_t)n_nets * FLAT_TOTAL, lr, beta1, beta2, eps, step, grad_scale,
+                          device, stream);
+  if (rc != 0) return rc;
+  DeviceGuard guard(device);
+  PackFlat pf;
+  for (int i = 0; i < 4; ++i) {
+    pf.flat[i] = i < n_nets ? param + (size_t)i * FLAT_TOTAL : nullptr;
+    pf.packed[i] = i < n_nets ? (uint8_t*)packed_host[i] : nullptr;
+    if (i < n_nets && (!pf.packed[i] || (reinterpret_cast<uintptr_t>(pf.packed[i]) & 15))) return IBLN_EINVAL;
+  }
+  return launch_pack_flat(pf, n_nets, (cudaStream_t)stream);
 }

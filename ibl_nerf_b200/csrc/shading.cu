@@ -35,10 +35,17 @@ __global__ void normal_eps_points_kernel(const float* __restrict__ o, const floa
 }
 
 __global__ void normal_eps_finish_kernel(const float* __restrict__ d, const float* __restrict__ depths4, int n, float eps,
-                                         float* __restrict__ normal, float* __restrict__ refl) {
+                                         float* __restrict__ normal, float* __restrict__ refl,
+                                         const float* __restrict__ o, const float* __restrict__ depth, int depth_ld,
+                                         float* __restrict__ x_surface) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
   float dd[3] = {d[3 * r], d[3 * r + 1], d[3 * r + 2]}, right[3], up[3];
+  if (x_surface != nullptr) {      // x_surface = rays_o + rays_d * depth   (ibl_nerf_renderer.py:262)
+    const float t = depth[(size_t)r * depth_ld];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) x_surface[3 * r + c] = __fadd_rn(o[3 * r + c], __fmul_rn(dd[c], t));
+  }
   eps_frame(dd, right, up);
   float ddx = depths4[r] - depths4[n + r];
   float ddy = depths4[2 * n + r] - depths4[3 * n + r];
@@ -100,13 +107,16 @@ struct ShadeMid {
   LutFetch lf;
 };
 
+// ld3 / ld1: row stride (floats) of albedo and of the per-ray scalars rough / irr / mip_rough / depth: 3 / 1 for
+// separate tensors, IBLN_MAPS_STRIDE for columns of the packed compositing output.
 __device__ __forceinline__ ShadeIn load_in(const float* rays_d, const float* normal, const float* albedo, const float* rough,
                                            const float* irr, const float* mip_rough, const float* depth,
-                                           const float* nearp, const float* farp, int r) {
+                                           const float* nearp, const float* farp, int r, int ld3, int ld1) {
   ShadeIn s;
 #pragma unroll
-  for (int c = 0; c < 3; ++c) { s.d[c] = rays_d[3 * r + c]; s.n[c] = normal[3 * r + c]; s.alb[c] = albedo[3 * r + c]; }
-  s.rough = rough[r]; s.irr = irr[r]; s.mip_rough = mip_rough[r]; s.depth = depth[r]; s.nearv = nearp[r]; s.farv = farp[r];
+  for (int c = 0; c < 3; ++c) { s.d[c] = rays_d[3 * r + c]; s.n[c] = normal[3 * r + c]; s.alb[c] = albedo[(size_t)ld3 * r + c]; }
+  s.rough = rough[(size_t)ld1 * r]; s.irr = irr[(size_t)ld1 * r]; s.mip_rough = mip_rough[(size_t)ld1 * r];
+  s.depth = depth[(size_t)ld1 * r]; s.nearv = nearp[r]; s.farv = farp[r];
   return s;
 }
 
@@ -155,10 +165,10 @@ __global__ void shade_fwd_kernel(const float* __restrict__ rays_d, const float* 
                                  const float* __restrict__ depth, const float* __restrict__ nearp,
                                  const float* __restrict__ farp, const float* __restrict__ pref, int n_pref,
                                  const float* __restrict__ lut, int H, int W, int lut_coef, int correct_depth, int n,
-                                 float* __restrict__ out, float* __restrict__ out_srgb) {
+                                 float* __restrict__ out, float* __restrict__ out_srgb, int ld3, int ld1) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
-  ShadeIn in = load_in(rays_d, normal, albedo, rough, irr, mip_rough, depth, nearp, farp, r);
+  ShadeIn in = load_in(rays_d, normal, albedo, rough, irr, mip_rough, depth, nearp, farp, r, ld3, ld1);
   ShadeMid m = shade_core(in, pref + (size_t)r * n_pref * 3, n_pref, lut, H, W, lut_coef, correct_depth);
   float o[IBLN_SHADE_STRIDE];
   o[IBLN_SH_NDV] = m.ndv;
@@ -188,10 +198,10 @@ __global__ void shade_bwd_kernel(const float* __restrict__ rays_d, const float* 
                                  const float* __restrict__ lut, int H, int W, int lut_coef, int correct_depth, int n,
                                  const float* __restrict__ g_out, const float* __restrict__ g_srgb,
                                  float* __restrict__ g_albedo, float* __restrict__ g_rough, float* __restrict__ g_irr,
-                                 float* __restrict__ g_mip) {
+                                 float* __restrict__ g_mip, int ld3, int ld1, float* __restrict__ g_maps) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
-  ShadeIn in = load_in(rays_d, normal, albedo, rough, irr, mip_rough, depth, nearp, farp, r);
+  ShadeIn in = load_in(rays_d, normal, albedo, rough, irr, mip_rough, depth, nearp, farp, r, ld3, ld1);
   const float* P = pref + (size_t)r * n_pref * 3;
   ShadeMid m = shade_core(in, P, n_pref, lut, H, W, lut_coef, correct_depth);
   float G[IBLN_SHADE_STRIDE];
@@ -242,6 +252,20 @@ __global__ void shade_bwd_kernel(const float* __restrict__ rays_d, const float* 
   } else {
     gMip = gLvl;
   }
+  if (g_maps != nullptr) {
+    // packed form: one row of d loss / d maps (linear compositing outputs); roughness_map feeds both the LUT / Fresnel
+    // terms and the mip level (ibl_nerf_renderer.py:324, 459), the depth is detached (:458)
+    float row[IBLN_MAPS_STRIDE];
+#pragma unroll
+    for (int c = 0; c < IBLN_MAPS_STRIDE; ++c) row[c] = 0.f;
+    row[IBLN_MAP_ROUGH] = gRho + gMip; row[IBLN_MAP_IRR] = gI;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) row[IBLN_MAP_ALBEDO + c] = gAlb[c];
+    float4* dst = reinterpret_cast<float4*>(g_maps + (size_t)r * IBLN_MAPS_STRIDE);
+#pragma unroll
+    for (int q = 0; q < IBLN_MAPS_STRIDE / 4; ++q) dst[q] = make_float4(row[4 * q], row[4 * q + 1], row[4 * q + 2], row[4 * q + 3]);
+    return;
+  }
 #pragma unroll
   for (int c = 0; c < 3; ++c) g_albedo[3 * r + c] = gAlb[c];
   g_rough[r] = gRho; g_irr[r] = gI; g_mip[r] = gMip;
@@ -262,11 +286,13 @@ extern "C" int ibln_normal_eps_points(const float* rays_o, const float* rays_d, 
 }
 
 extern "C" int ibln_normal_eps_finish(const float* rays_d, const float* depths4, int n, float eps, float* normal,
-                                      float* refl, int device, void* stream) {
+                                      float* refl, const float* rays_o, const float* depth, int depth_ld,
+                                      float* x_surface, int device, void* stream) {
   if (n == 0) return 0;
-  if (n < 0 || !rays_d || !depths4 || !normal) return IBLN_EINVAL;
+  if (n < 0 || !rays_d || !depths4 || !normal || (x_surface && (!rays_o || !depth || depth_ld < 1))) return IBLN_EINVAL;
   DeviceGuard g(device);
-  normal_eps_finish_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rays_d, depths4, n, eps, normal, refl);
+  normal_eps_finish_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rays_d, depths4, n, eps, normal, refl, rays_o,
+                                                                             depth, depth_ld, x_surface);
   IBLN_RETURN_LAST();
 }
 
@@ -283,7 +309,37 @@ extern "C" int ibln_shade_fwd(const float* rays_d, const float* normal, const fl
   DeviceGuard g(device);
   shade_fwd_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rays_d, normal, albedo, rough, irr, mip_rough, depth,
                                                                      nearp, farp, prefiltered, n_pref, lut, lut_h, lut_w,
-                                                                     lut_coef, correct_depth, n, out, out_srgb);
+                                                                     lut_coef, correct_depth, n, out, out_srgb, 3, 1);
+  IBLN_RETURN_LAST();
+}
+
+extern "C" int ibln_shade_fwd_maps(const float* rays_d, const float* normal, const float* maps, const float* nearp,
+                                   const float* farp, const float* prefiltered, int n_pref, const float* lut, int lut_h,
+                                   int lut_w, int lut_coef, int correct_depth, int n, float* out, float* out_srgb, int device,
+                                   void* stream) {
+  if (n == 0) return 0;
+  if (n < 0 || n_pref < 1 || lut_h < 2 || lut_w < 2 || !rays_d || !normal || !maps || !nearp || !farp || !prefiltered || !lut ||
+      !(lut_coef == 0 || lut_coef == 1) || !out) return IBLN_EINVAL;
+  DeviceGuard g(device);
+  shade_fwd_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      rays_d, normal, maps + IBLN_MAP_ALBEDO, maps + IBLN_MAP_ROUGH, maps + IBLN_MAP_IRR, maps + IBLN_MAP_ROUGH,
+      maps + IBLN_MAP_DEPTH, nearp, farp, prefiltered, n_pref, lut, lut_h, lut_w, lut_coef, correct_depth, n, out, out_srgb,
+      IBLN_MAPS_STRIDE, IBLN_MAPS_STRIDE);
+  IBLN_RETURN_LAST();
+}
+
+extern "C" int ibln_shade_bwd_maps(const float* rays_d, const float* normal, const float* maps, const float* nearp,
+                                   const float* farp, const float* prefiltered, int n_pref, const float* lut, int lut_h,
+                                   int lut_w, int lut_coef, int correct_depth, int n, const float* g_out,
+                                   const float* g_out_srgb, float* g_maps, int device, void* stream) {
+  if (n == 0) return 0;
+  if (n < 0 || n_pref < 1 || lut_h < 2 || lut_w < 2 || !rays_d || !normal || !maps || !nearp || !farp || !prefiltered || !lut ||
+      !(lut_coef == 0 || lut_coef == 1) || !g_maps) return IBLN_EINVAL;
+  DeviceGuard g(device);
+  shade_bwd_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      rays_d, normal, maps + IBLN_MAP_ALBEDO, maps + IBLN_MAP_ROUGH, maps + IBLN_MAP_IRR, maps + IBLN_MAP_ROUGH,
+      maps + IBLN_MAP_DEPTH, nearp, farp, prefiltered, n_pref, lut, lut_h, lut_w, lut_coef, correct_depth, n, g_out, g_out_srgb,
+      nullptr, nullptr, nullptr, nullptr, IBLN_MAPS_STRIDE, IBLN_MAPS_STRIDE, g_maps);
   IBLN_RETURN_LAST();
 }
 
@@ -299,6 +355,6 @@ extern "C" int ibln_shade_bwd(const float* rays_d, const float* normal, const fl
   shade_bwd_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rays_d, normal, albedo, rough, irr, mip_rough, depth,
                                                                      nearp, farp, prefiltered, n_pref, lut, lut_h, lut_w,
                                                                      lut_coef, correct_depth, n, g_out, g_out_srgb,
-                                                                     g_albedo, g_rough, g_irr, g_mip_rough);
+                                                                     g_albedo, g_rough, g_irr, g_mip_rough, 3, 1, nullptr);
   IBLN_RETURN_LAST();
 }

@@ -1,51 +1,74 @@
 // Training-step tail kernels: the phase-gated image losses of src/train.py and the Adam update of
-// both networks, each as ONE launch over flat buffers instead of ~60 small ATen launches + ~100 per-tensor updates.
+// both networks, each as ONE launch over flat buffers instead of ~60 small ATen launches + ~100 per-tensor updates;
+// ray generation / target gather, export packing, and the ABI bookkeeping entry points.
 #include "common.cuh"
 
 namespace ibln {
 
-// loss += scale * sum over the used terms of mean((pred - target)^2)           (img2mse, nerf_renderer_helper.py:8)
-// terms: radiance_map (maps cols 9..11) vs rgb, radiance_map_k (cols 12+3k..) vs rgb_k, color_map (shade cols
-// 10..12) vs rgb  -- train.py:322-432 with the shipped betas.  Also writes d loss / d maps, d loss / d shade.
+// The phase-gated image losses of train.py:299-441 for ONE pass (fine or coarse) on the packed, gamma-corrected kernel
+// outputs, forward and backward in one launch.  With mse = mean over all elements (img2mse, nerf_renderer_helper.py:8):
+//   *loss += scale * [ w_rad   * ( mse(radiance_map, rgb) + sum_k mse(radiance_map_k, rgb_k) )     train.py:326-334, 420-423
+//                    + w_color * mse(color_map, rgb)                                               :323, 437-438 (full-IBL phase)
+//                    + w_alb   * mse(albedo_map, prior_albedo)                                     :401-403, 444-446 (prior phase)
+//                    + w_irr   * mse(irradiance_map, irr_target) ]                                 :410-412, 447 (fine pass only)
+// maps cols: irradiance 5, albedo 6..8, radiance 9..11, coarse radiance k 12+3k..; shade cols: colour 10..12.
+struct LossWeights { float rad, color, alb, irr, irr_target, scale; };
 constexpr int LOSS_THREADS = 256;
 __global__ void __launch_bounds__(LOSS_THREADS)
-phase_b_loss_kernel(const float* __restrict__ maps, const float* __restrict__ shade, const float* __restrict__ rgb,
-                    const float* __restrict__ rgb1, const float* __restrict__ rgb2, const float* __restrict__ rgb3, int n,
-                    float scale, float* __restrict__ loss, float* __restrict__ g_maps, float* __restrict__ g_shade) {
+image_losses_kernel(const float* __restrict__ maps, const float* __restrict__ shade, const float* __restrict__ rgb,
+                    const float* __restrict__ rgb1, const float* __restrict__ rgb2, const float* __restrict__ rgb3,
+                    const float* __restrict__ prior_albedo, int n, LossWeights w, float* __restrict__ loss,
+                    float* __restrict__ g_maps, float* __restrict__ g_shade) {
   const int r = blockIdx.x * LOSS_THREADS + threadIdx.x;
   float acc = 0.f;
   if (r < n) {
-    const float inv = scale / (3.0f * (float)n);
+    const float inv3 = w.scale / (3.0f * (float)n), inv1 = w.scale / (float)n;
     const float* m = maps + (size_t)r * 24;
-    float* gm = g_maps + (size_t)r * 24;
+    float g[24];
+#pragma unroll
+    for (int j = 0; j < 24; ++j) g[j] = 0.f;
     const float* tg[4] = {rgb, rgb1, rgb2, rgb3};
 #pragma unroll
-    for (int j = 0; j < 9; ++j) gm[j] = 0.f;
-#pragma unroll
     for (int k = 0; k < 4; ++k) {
+      if (tg[k] == nullptr || w.rad == 0.f) continue;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        float d = 0.f;
-        if (tg[k] != nullptr) d = m[9 + 3 * k + c] - tg[k][(size_t)r * 3 + c];
-        acc += d * d;
-        gm[9 + 3 * k + c] = 2.0f * inv * d;
+        const float d = m[9 + 3 * k + c] - tg[k][(size_t)r * 3 + c];
+        acc += w.rad * inv3 * d * d;
+        g[9 + 3 * k + c] = 2.0f * w.rad * inv3 * d;
       }
     }
+    if (prior_albedo != nullptr && w.alb != 0.f) {
 #pragma unroll
-    for (int j = 21; j < 24; ++j) gm[j] = 0.f;
+      for (int c = 0; c < 3; ++c) {
+        const float d = m[6 + c] - prior_albedo[(size_t)r * 3 + c];
+        acc += w.alb * inv3 * d * d;
+        g[6 + c] = 2.0f * w.alb * inv3 * d;
+      }
+    }
+    if (w.irr != 0.f) {
+      const float d = m[5] - w.irr_target;
+      acc += w.irr * inv1 * d * d;
+      g[5] = 2.0f * w.irr * inv1 * d;
+    }
+    float4* gm = reinterpret_cast<float4*>(g_maps + (size_t)r * 24);
+#pragma unroll
+    for (int q = 0; q < 6; ++q) gm[q] = make_float4(g[4 * q], g[4 * q + 1], g[4 * q + 2], g[4 * q + 3]);
     if (shade != nullptr) {
       const float* s = shade + (size_t)r * 16;
-      float* gs = g_shade + (size_t)r * 16;
+      float gs[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) gs[j] = 0.f;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const float d = s[10 + c] - rgb[(size_t)r * 3 + c];
-        acc += d * d;
-        gs[10 + c] = 2.0f * inv * d;
+        acc += w.color * inv3 * d * d;
+        gs[10 + c] = 2.0f * w.color * inv3 * d;
       }
+      float4* gp = reinterpret_cast<float4*>(g_shade + (size_t)r * 16);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) gp[q] = make_float4(gs[4 * q], gs[4 * q + 1], gs[4 * q + 2], gs[4 * q + 3]);
     }
-    acc *= inv;
   }
   __shared__ float part[LOSS_THREADS / 32];
   acc = warp_sum(acc);
@@ -95,15 +118,26 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
 
 using namespace ibln;
 
-extern "C" int ibln_phase_b_loss(const float* maps_srgb, const float* shade_srgb, const float* rgb, const float* rgb_1,
-                                 const float* rgb_2, const float* rgb_3, int n, float scale, float* loss, float* g_maps,
-                                 float* g_shade, int device, void* stream) {
+extern "C" int ibln_image_losses(const float* maps_srgb, const float* shade_srgb, const float* rgb, const float* rgb_1,
+                                 const float* rgb_2, const float* rgb_3, const float* prior_albedo, int n, float w_radiance,
+                                 float w_color, float w_prior_albedo, float w_irradiance_reg, float irradiance_target,
+                                 float scale, float* loss, float* g_maps, float* g_shade, int device, void* stream) {
   if (n == 0) return 0;
   if (n < 0 || !maps_srgb || !rgb || !loss || !g_maps || (shade_srgb && !g_shade)) return IBLN_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(g_maps) | reinterpret_cast<uintptr_t>(g_shade)) & 15) return IBLN_EINVAL;
   DeviceGuard g(device);
-  phase_b_loss_kernel<<<(n + LOSS_THREADS - 1) / LOSS_THREADS, LOSS_THREADS, 0, (cudaStream_t)stream>>>(
-      maps_srgb, shade_srgb, rgb, rgb_1, rgb_2, rgb_3, n, scale, loss, g_maps, g_shade);
+  LossWeights w = {w_radiance, w_color, w_prior_albedo, w_irradiance_reg, irradiance_target, scale};
+  image_losses_kernel<<<(n + LOSS_THREADS - 1) / LOSS_THREADS, LOSS_THREADS, 0, (cudaStream_t)stream>>>(
+      maps_srgb, shade_srgb, rgb, rgb_1, rgb_2, rgb_3, prior_albedo, n, w, loss, g_maps, g_shade);
   IBLN_RETURN_LAST();
+}
+
+extern "C" int ibln_zero(void* buf, int64_t bytes, int device, void* stream) {
+  if (bytes == 0) return 0;
+  if (!buf || bytes < 0) return IBLN_EINVAL;
+  DeviceGuard g(device);
+  IBLN_CUDA(cudaMemsetAsync(buf, 0, (size_t)bytes, (cudaStream_t)stream));
+  return 0;
 }
 
 extern "C" int ibln_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,

@@ -145,6 +145,23 @@ class IBLNeRF(nn.Module):
             self._pack_gen += 1
         return self._packed
 
+    def _pack_key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.ordered_params())
+
+    def packed_buffer(self):
+        """The device buffer of the packed image (allocated on first use), for producers that write it themselves
+        (ibln_adam_step_pack re-packs straight from the optimizer's flat parameter buffer)."""
+        dev = self.ordered_params()[0].device
+        if self._packed is None or self._packed.device != dev:
+            self._packed = torch.empty(_lib.lib().ibln_mlp_packed_bytes(), dtype=torch.uint8, device=dev)
+            self._packed_key = None
+        return self._packed
+
+    def mark_packed(self):
+        """packed_buffer() now holds the image of the CURRENT parameter values."""
+        self._packed_key = self._pack_key()
+        self._pack_gen += 1
+
     def invalidate_packed(self):
         """Force a re-pack on the next query (parameters were updated in place outside torch, e.g. ibln_adam_step)."""
         self._packed_key = None

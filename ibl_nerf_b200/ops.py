@@ -115,13 +115,15 @@ def composite(raw, z, rays_d, noise=None, n_coarse=3, radiance_sigmoid=True, wan
     return _Composite.apply(raw, z, rays_d, noise, n_coarse, radiance_sigmoid, want_srgb)
 
 
-def composite_simple(raw, z, dirs, n_coarse=3, radiance_sigmoid=True):
-    """raw2outputs_simple (no grad): [N,1+n_coarse,3]."""
+def composite_simple(raw, z, dirs, n_coarse=3, radiance_sigmoid=True, want_srgb=False):
+    """raw2outputs_simple (no grad): [N,1+n_coarse,3]; with want_srgb also its gamma-corrected copy (same launch)."""
     raw, z, dirs = f32c(raw.detach()), f32c(z), f32c(dirs)
     n, s, c = raw.shape
     out = _new(raw, n, 1 + n_coarse, 3)
-    call("ibln_composite_simple_fwd", raw.device, ptr(raw), ptr(z), ptr(dirs), n, s, c, n_coarse, int(radiance_sigmoid), ptr(out))
-    return out
+    out_srgb = _new(raw, n, 1 + n_coarse, 3) if want_srgb else None
+    call("ibln_composite_simple_fwd", raw.device, ptr(raw), ptr(z), ptr(dirs), n, s, c, n_coarse, int(radiance_sigmoid), ptr(out),
+         ptr(out_srgb))
+    return (out, out_srgb) if want_srgb else out
 
 
 def depth_composite(sigma, z, rays_d, want_weights=False, want_visibility=False):
@@ -149,7 +151,7 @@ def normal_eps_finish(rays_d, depths4, eps):
     rays_d, depths4 = f32c(rays_d), f32c(depths4)
     n = rays_d.shape[0]
     normal, refl = _new(rays_d, n, 3), _new(rays_d, n, 3)
-    call("ibln_normal_eps_finish", rays_d.device, ptr(rays_d), ptr(depths4), n, float(eps), ptr(normal), ptr(refl))
+    call("ibln_normal_eps_finish", rays_d.device, ptr(rays_d), ptr(depths4), n, float(eps), ptr(normal), ptr(refl), None, None, 1, None)
     return normal, refl
 
 

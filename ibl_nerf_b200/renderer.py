@@ -261,7 +261,10 @@ def raw2outputs(rays_o, rays_d, z_vals, z_vals_constant, network_query_fn, netwo
             else:
                 reflected_pts = x_surface[..., None, :] + reflected_dirs[..., None, :] * z_vals_constant[..., :, None]
                 reflected_ray_raw = network_query_fn(reflected_pts, reflected_dirs, network_fn)
-            prefiltered_env_maps = ops.composite_simple(reflected_ray_raw, z_vals_constant, reflected_dirs, n_coarse, is_radiance_sigmoid)
+            prefiltered_env_maps = ops.composite_simple(reflected_ray_raw, z_vals_constant, reflected_dirs, n_coarse, is_radiance_sigmoid,
+                                                        want_srgb=fused_gamma)
+            if fused_gamma:
+                prefiltered_env_maps, prefiltered_srgb = prefiltered_env_maps
         reflected_radiance_map = prefiltered_env_maps[:, 0]
         reflected_coarse_radiance_map = [prefiltered_env_maps[:, 1 + k] for k in range(n_coarse)]
 
@@ -295,11 +298,11 @@ def raw2outputs(rays_o, rays_d, z_vals, z_vals_constant, network_query_fn, netwo
         for k in range(n_coarse):
             results["radiance_map_%d" % (k + 1)] = ms[:, ops.MAP_COARSE + 3 * k:ops.MAP_COARSE + 3 * k + 3]
         for k in range(len(reflected_coarse_radiance_map)):
-            results["reflected_coarse_radiance_map_%d" % (k + 1)] = rgb_to_srgb(reflected_coarse_radiance_map[k])
+            results["reflected_coarse_radiance_map_%d" % (k + 1)] = prefiltered_srgb[:, 1 + k]
         results["irradiance_map"] = output_f(target_irradiance_map) if "irradiance" in overridden else ms[:, ops.MAP_IRR:ops.MAP_IRR + 1]
         results["min_irradiance_map"] = None
         results["max_irradiance_map"] = None
-        results["reflected_radiance_map"] = output_f(reflected_radiance_map)
+        results["reflected_radiance_map"] = None if reflected_radiance_map is None else prefiltered_srgb[:, 0]
         results["prefiltered_reflected_map"] = sh(ops.SH_PRE)
         results["albedo_map"] = albedo_f(target_albedo_map) if "albedo" in overridden else ms[:, ops.MAP_ALBEDO:ops.MAP_ALBEDO + 3]
         results["specular_map"] = sh(ops.SH_SPEC)

@@ -101,7 +101,8 @@ int ibln_composite_bwd(const float* raw, const float* z, const float* rays_d, co
 /* raw2outputs_simple (reflected ray, no grad): ibl_nerf_renderer.py:38-68.
  * pre_out [N,1+n_coarse,3] = radiance, coarse radiance 1..n_coarse. */
 int ibln_composite_simple_fwd(const float* raw, const float* z, const float* dirs, int n_rays, int n_samples,
-                              int n_ch, int n_coarse, int radiance_sigmoid, float* pre_out, int device, void* stream);
+                              int n_ch, int n_coarse, int radiance_sigmoid, float* pre_out, float* pre_srgb /* nullable:
+                              pow(x+1e-12, 1/2.2) of pre_out, :485-496 */, int device, void* stream);
 
 /* Depth-only compositing: raw2outputs_depth (:121-150) and raw2depth (normal_from_depth.py:164-169).
  * sigma [reps*N, S] (row m uses z / rays_d of ray m % N), depth [reps*N]; weights [reps*N,S] and
@@ -117,9 +118,12 @@ int ibln_normal_eps_points(const float* rays_o, const float* rays_d, const float
                            float eps, float* pts_out, int device, void* stream);
 
 /* Tail of the estimator: normal_from_depth.py:177-183 plus the reflection of :439.
- * depths4 [4,N] (right,left,up,down); normal [N,3]; refl [N,3] nullable. */
+ * depths4 [4,N] (right,left,up,down); normal [N,3]; refl [N,3] nullable.  Optionally also the surface point of
+ * ibl_nerf_renderer.py:262: x_surface [N,3] = rays_o + rays_d * depth[r * depth_ld]  (x_surface nullable; rays_o / depth
+ * are only read when it is given; depth_ld = 1 for a dense vector, IBLN_MAPS_STRIDE for column 0 of the packed maps). */
 int ibln_normal_eps_finish(const float* rays_d, const float* depths4, int n_rays, float eps,
-                           float* normal, float* refl, int device, void* stream);
+                           float* normal, float* refl, const float* rays_o, const float* depth, int depth_ld,
+                           float* x_surface, int device, void* stream);
 
 /* Split-sum shading forward: ibl_nerf_renderer.py:412-438,455-474 + microfacet.py:8-12.
  * rays_d,normal,albedo [N,3]; rough,irr,mip_rough,depth,near,far [N]; prefiltered [N,n_pref,3];
@@ -137,6 +141,18 @@ int ibln_shade_bwd(const float* rays_d, const float* normal, const float* albedo
                    const float* prefiltered, int n_pref, const float* lut, int lut_h, int lut_w,
                    int lut_coef, int correct_depth, int n_rays, const float* g_out, const float* g_out_srgb,
                    float* g_albedo, float* g_rough, float* g_irr, float* g_mip_rough, int device, void* stream);
+
+/* The same two kernels reading albedo / roughness / irradiance / depth straight from the packed compositing output
+ * `maps` [N,24] (no column copies; mip_rough = roughness_map, depth = depth_map as in the shipped configuration), and
+ * the backward writing one full row of d loss / d maps per ray: g_maps [N,24] = 0 except roughness (LUT / Fresnel / mip
+ * level terms summed), irradiance and albedo columns. */
+int ibln_shade_fwd_maps(const float* rays_d, const float* normal, const float* maps, const float* near, const float* far,
+                        const float* prefiltered, int n_pref, const float* lut, int lut_h, int lut_w, int lut_coef,
+                        int correct_depth, int n_rays, float* out, float* out_srgb, int device, void* stream);
+int ibln_shade_bwd_maps(const float* rays_d, const float* normal, const float* maps, const float* near, const float* far,
+                        const float* prefiltered, int n_pref, const float* lut, int lut_h, int lut_w, int lut_coef,
+                        int correct_depth, int n_rays, const float* g_out, const float* g_out_srgb, float* g_maps,
+                        int device, void* stream);
 
 /* ---- (2)+(3) positional encoding and the intrinsic-component MLP ----------------------------- */
 
@@ -197,22 +213,35 @@ int ibln_mlp_bwd(const void* packed, const void* saved, const float* g_out, int6
 
 /* ---- training-step tail ------------------------------------------------------ */
 
-/* Phase-B image losses of src/train.py:322-432 (shipped betas = 1) on the packed gamma-corrected outputs of
- * ibln_composite_fwd / ibln_shade_fwd, forward and backward in one launch:
- *   *loss += scale * [ mse(radiance_map, rgb) + sum_k mse(radiance_map_k, rgb_k) + mse(color_map, rgb) ]
- * with mse = mean over N*3 elements (img2mse, nerf_renderer_helper.py:8).  maps_srgb [N,24] (radiance cols 9..11,
- * coarse radiance k cols 12+3k..), shade_srgb [N,16] nullable (color cols 10..12; null = radiance-only phase),
- * rgb_k [N,3] nullable (term skipped).  g_maps [N,24], g_shade [N,16] receive d loss / d input (all columns
- * written).  *loss must be zeroed by the caller. */
-int ibln_phase_b_loss(const float* maps_srgb, const float* shade_srgb, const float* rgb, const float* rgb_1,
-                      const float* rgb_2, const float* rgb_3, int n, float scale, float* loss, float* g_maps,
-                      float* g_shade, int device, void* stream);
+/* Phase-gated image losses of src/train.py:299-441 for ONE pass (fine or coarse) on the packed gamma-corrected outputs
+ * of ibln_composite_fwd / ibln_shade_fwd, forward and backward in one launch.  mse = mean over all elements (img2mse,
+ * nerf_renderer_helper.py:8):
+ *   *loss += scale * [ w_radiance (mse(radiance_map, rgb) + sum_k mse(radiance_map_k, rgb_k))      train.py:326-334, 420-423
+ *                    + w_color mse(color_map, rgb)                                                 :323, 437-438
+ *                    + w_prior_albedo mse(albedo_map, prior_albedo)                                :401-403, 444-446
+ *                    + w_irradiance_reg mse(irradiance_map, irradiance_target) ]                   :410-412, 447
+ * maps_srgb [N,24] (irradiance col 5, albedo 6..8, radiance 9..11, coarse radiance k 12+3k..), shade_srgb [N,16] nullable
+ * (colour cols 10..12; null = radiance-only phase), rgb_k / prior_albedo [N,3] nullable (term skipped).  g_maps [N,24],
+ * g_shade [N,16] receive d loss / d input (all columns written; 16-byte aligned).  *loss must be zeroed by the caller. */
+int ibln_image_losses(const float* maps_srgb, const float* shade_srgb, const float* rgb, const float* rgb_1,
+                      const float* rgb_2, const float* rgb_3, const float* prior_albedo, int n, float w_radiance,
+                      float w_color, float w_prior_albedo, float w_irradiance_reg, float irradiance_target,
+                      float scale, float* loss, float* g_maps, float* g_shade, int device, void* stream);
 
 /* torch.optim.Adam step (amsgrad off, no weight decay; src/train.py:479-498) over one flat fp32 buffer:
  * step = 1-based iteration count (bias correction), grad_scale multiplies the gradient first (e.g. 1/world).
  * All four buffers 16-byte aligned, n elements. */
 int ibln_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                    float beta1, float beta2, float eps, int step, float grad_scale, int device, void* stream);
+
+/* The same update over a flat buffer that holds n_nets (<= 4) networks back to back (798 994 floats each, state-dict
+ * order: training.FlatParameters), followed by the bf16 re-pack (ibln_mlp_pack_weights) of every network straight from that
+ * buffer into packed_host[i] (HOST array of device pointers): 2 launches per optimisation step. */
+int ibln_adam_step_pack(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int n_nets, float lr,
+                        float beta1, float beta2, float eps, int step, float grad_scale, void* const* packed_host,
+                        int device, void* stream);
+/* cudaMemsetAsync(buf, 0, bytes) on the given stream (gradient / loss accumulators of the fused training step). */
+int ibln_zero(void* buf, int64_t bytes, int device, void* stream);
 
 /* Ray generation + target gather for one training batch: get_rays_few
  * (nerf_renderer_helper.py:14-23) for pixels (u[i], v[i]) of a camera (intrinsics fx, fy, cx, cy; c2w [3,4]

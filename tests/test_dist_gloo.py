@@ -46,7 +46,18 @@ def _worker(rank, world, port, q):
     ok_flat = ok_flat and all(bool((p.grad == tot).all()) and p.grad.data_ptr() >= flat.grad.data_ptr()
                               for net in nets for p in net.parameters())
     ok_flat = ok_flat and nets[1]._grad_sink.data_ptr() == flat.grad.data_ptr() + 4 * 798994
-    q.put((rank, ok_cover, ok_grad and ok_flat))
+    # (4) the final gather of the tile-sharded render: every map of this rank's row tile packed into one buffer, ONE
+    # all_gather, unpacked to full-size maps (ragged last tile: 1001 rays over 2 ranks)
+    g = torch.Generator().manual_seed(3)
+    full = {"color_map": torch.rand(n, 3, generator=g), "depth_map": torch.rand(n, generator=g), "weights": torch.rand(n, 5, generator=g)}
+    mine = {k: v[lo:hi].clone() for k, v in full.items()}
+    calls = []
+    orig = dist.all_gather_into_tensor
+    dist.all_gather_into_tensor = lambda *a, **k: (calls.append(1), orig(*a, **k))[1]
+    got = training.gather_maps(mine, sorted(full), n, world)
+    dist.all_gather_into_tensor = orig
+    ok_gather = len(calls) == 1 and all(torch.equal(got[k], full[k]) for k in full)
+    q.put((rank, ok_cover, ok_grad and ok_flat and ok_gather))
     dist.destroy_process_group()
 
 

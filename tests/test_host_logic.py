@@ -54,3 +54,37 @@ def test_step_program_chunk_table_is_consistent():
     steps = [(256, 1, 0, 0)] + [(256, 0, 4, 0)] * 4 + [(256, 1, 4, 0), (256, 0, 4, 0), (256, 0, 4, 0), (256, 0, 4, 0),
                                                        (256, 0, 4, 0), (256, 0, 4, 1), (256, 0, 4, 0), (128, 0, 4, 0)]
     assert sum((a + k + l) * (n // 128) for n, a, k, l in steps) == 98
+
+
+def test_train_step_schedule_follows_the_reference_driver():
+    """lr decay and phase switches of src/train.py:275-283, 286-297, 483-498 (kitchen: lrate_decay 500, phase boundaries at
+    10 000 / 100 000 iterations)."""
+    import torch
+    from ibl_nerf_b200 import training
+    ts = training.TrainStep("cpu", torch.zeros(3, 4, 4), precision="fp32", lrate_decay=500)
+    # replay the reference loop: set_lr runs after optimizer.step() with the not-yet-incremented global_step
+    lr, global_step, used = 5e-4, 0, []
+    for _ in range(6):
+        used.append(lr)
+        if global_step > 0:
+            lr = 5e-4 * (0.1 ** (global_step / (500 * 1000)))
+        global_step += 1
+    assert [ts.lr_for_step(g) for g in range(6)] == used
+    assert abs(ts.lr_for_step(500001) - 5e-5) < 1e-12
+    assert [training.TrainStep.phase_for_iteration(i) for i in (1, 9999, 10000, 99999, 100000)] == \
+        ["radiance", "radiance", "full", "full", "prior"]
+    ts.set_phase("prior")
+    assert ts.coarse.freeze_radiance and ts.fine.freeze_roughness and ts.approx
+    ts.set_phase("radiance")
+    assert not ts.coarse.freeze_radiance and not ts.approx
+
+
+def test_pack_maps_round_trip():
+    import torch
+    from ibl_nerf_b200 import training
+    g = torch.Generator().manual_seed(0)
+    res = {"a": torch.rand(7, 3, generator=g), "b": torch.rand(7, generator=g), "c": torch.rand(7, 4, 3, generator=g)}
+    buf, layout = training.pack_maps(res, ["a", "b", "c"], 9)
+    assert buf.shape == (9, 3 + 1 + 12)
+    out = training.unpack_maps(buf, layout, 7)
+    assert all(torch.equal(out[k], res[k]) for k in res)
