@@ -2,21 +2,29 @@
 """bench.py -- IBL-NeRF kitchen-config training step throughput (rays/s) on N B200s.
 
     python bench.py --gpus N --steps K --warmup W            # B200-native path (this repo)
-    python bench.py --impl reference --gpus N ...            # reference algorithm on the host CPU cores (oracle port)
+    python bench.py --impl reference --gpus N ...            # the reference's CPU implementation on the host cores
 
 step = one training iteration of src/train.py for the kitchen config in the full-IBL phase (BASELINE.json configs[1]):
-render_decomp (64 coarse + 128 fine samples, epsilon normals, reflected ray, split-sum shading) -> phase-B losses ->
-backward -> (NCCL gradient all-reduce) -> Adam, on N_rand = 4096 synthetic rays per GPU with random-init weights.
-Prints ONE JSON line (rank 0).
+render (64 coarse + 128 fine samples, epsilon normals, reflected ray, split-sum shading) -> image losses -> backward ->
+(NCCL gradient all-reduce) -> Adam + weight re-pack, on N_rand = 4096 synthetic rays per GPU with random-init weights.
+Prints ONE JSON line (rank 0).  Besides the headline (`value`, `e2e`, `roofline`, `cpu_baseline`) the line carries, each
+measured outside the headline's timed region with its own clock sample:
+  phases     the radiance-only and prior/freeze phases of the shipped schedule (same step, other loss gates)
+  strong     BASELINE configs[3]: one step over 65 536 rays in total, sharded over the N ranks (strong scaling)
+  render     BASELINE configs[2]: 8 full 480x640 test renders (all maps), image rows sharded over the N ranks + one gather
+  micro      BASELINE configs[4] (N = 1): composite fwd / bwd and sample_pdf vs the HBM roofline at S = 64 / 192 / 512
+  dp_parity  (N > 1) correctness of the sharded paths against rank 0 computing the whole batch / image on one GPU
 """
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
 import sys
 import tempfile
 import time
+import types
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -32,6 +40,9 @@ WORKLOAD = ("IBL-NeRF kitchen full-IBL training step (render_decomp + phase-B lo
 N_RAND = 4096
 FLOP_FULL, FLOP_SIGMA = 1591552, 982528          # algorithmic FLOP / point (unpadded)
 FLOP_PER_RAY_STEP = 2432139264                   # full-IBL training step
+FLOP_PER_RAY_RADIANCE = 1222311936               # radiance-only training step
+FLOP_PER_RAY_RENDER = 1617264640                 # full-IBL render (no grad)
+REF_SRC = os.path.join(ROOT, "baseline", "_ref", "src")
 
 
 def synth_rays(n, seed, device="cpu", pin=False):
@@ -39,7 +50,7 @@ def synth_rays(n, seed, device="cpu", pin=False):
     o = torch.rand(n, 3, generator=g) * 2 - 1
     d = torch.randn(n, 3, generator=g)
     d = d / d.norm(dim=-1, keepdim=True) * (1.0 + 0.3 * torch.rand(n, 1, generator=g))
-    tg = {k: torch.rand(n, 3, generator=g) for k in ("rgb", "rgb_1", "rgb_2", "rgb_3")}
+    tg = {k: torch.rand(n, 3, generator=g) for k in ("rgb", "rgb_1", "rgb_2", "rgb_3", "prior_albedo")}
     if pin:
         o, d = o.pin_memory(), d.pin_memory()
         tg = {k: v.pin_memory() for k, v in tg.items()}
@@ -47,7 +58,7 @@ def synth_rays(n, seed, device="cpu", pin=False):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 20 ms DURING the timed regions (resident + end-to-end)."""
+    """nvidia-smi clocks / throttle reasons sampled every 20 ms DURING a timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -83,22 +94,76 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+# ------------------------------------------------------------------------------------------------ CPU baselines
+_REF = {}
+
+
+def reference_modules():
+    """The reference's own modules from baseline/_ref (tools/install_reference.py), imageio / matplotlib stubbed as in
+    tests/golden/make_golden.py; None when the checkout did not travel with the repo."""
+    if "m" in _REF:
+        return _REF["m"]
+    m = None
+    if os.path.isdir(os.path.join(REF_SRC, "nerf_models")):
+        try:
+            for name in ("imageio", "matplotlib", "matplotlib.pyplot"):
+                try:
+                    __import__(name)
+                except ImportError:
+                    sys.modules.setdefault(name, types.ModuleType(name))
+            sys.path.insert(0, REF_SRC)
+            from nerf_models.ibl_nerf_renderer import render_rays
+            from nerf_models.ibl_nerf import IBLNeRF, run_network
+            from nerf_models.positional_embedder import get_embedder
+            torch.autograd.set_detect_anomaly(False)      # nerf_renderer_helper.py:2 turns it on at import; off for timing
+            m = dict(render_rays=render_rays, IBLNeRF=IBLNeRF, run_network=run_network, get_embedder=get_embedder)
+        except Exception as e:          # a reported baseline must never take the bench line down
+            m = None
+            _REF["error"] = "%s: %s" % (type(e).__name__, str(e)[:200])
+        finally:
+            if REF_SRC in sys.path:
+                sys.path.remove(REF_SRC)
+    _REF["m"] = m
+    return m
+
+
+def cpu_reference_kind():
+    return "reference" if reference_modules() is not None else "port"
+
+
 def cpu_reference_step(n_rays, threads):
-    """One fwd+bwd of the reference algorithm (oracle port, plain torch CPU fp32) on n_rays rays; returns seconds."""
+    """One fwd+bwd of the path on n_rays rays on the host cores; returns seconds.  The reference's own PyTorch
+    implementation (src/nerf_models, unmodified, from baseline/_ref) when present, else the oracle port."""
     import fixtures as fx
-    from oracle import iblnerf_oracle as orc
     torch.set_num_threads(threads)
-    torch.manual_seed(0)
-    nets = []
-    for _ in range(2):
-        p = {}
-        for name, o, i in orc.PARAM_SHAPES_INIT_ORDER:
-            lin = torch.nn.Linear(i, o)
-            p[name + ".weight"], p[name + ".bias"] = lin.weight, lin.bias
-        nets.append(p)
     o, d, tg = synth_rays(n_rays, 1)
     rays = torch.cat([o, d, torch.full((n_rays, 1), 0.5), torch.full((n_rays, 1), 8.0), d / d.norm(dim=-1, keepdim=True)], -1)
     lut = fx.load_lut()
+    m = reference_modules()
+    torch.manual_seed(0)
+    if m is not None:
+        arch = dict(D=8, W=256, input_ch=63, input_ch_views=27, skips=[4], coarse_radiance_number=3,
+                    is_color_independent_to_direction=False)
+        coarse, fine = m["IBLNeRF"](**arch), m["IBLNeRF"](**arch)
+        e10, e4 = m["get_embedder"](10, 0)[0], m["get_embedder"](4, 0)[0]
+        q = lambda p, v, f: m["run_network"](p, v, f, e10, e4, 65536)
+        kw = dict(network_fn=coarse, network_fine=fine, network_query_fn=q, N_samples=64, N_importance=128, perturb=1.0,
+                  raw_noise_std=0., brdf_lut=lut, epsilon=0.01, gamma_correct=True, lut_coefficient="F",
+                  target_normal_map_for_radiance_calculation="normal_map_from_depth_gradient_epsilon",
+                  correct_depth_for_prefiltered_radiance_infer=True, use_viewdirs=True, white_bkgd=False, lindisp=False)
+        t0 = time.perf_counter()
+        res = m["render_rays"](rays, approximate_radiance=True, **kw)
+        loss = fx.phase_b_loss(res, tg)
+        loss.backward()
+        return time.perf_counter() - t0
+    from oracle import iblnerf_oracle as orc
+    nets = []
+    for _ in range(2):
+        p = {}
+        for name, oo, ii in orc.PARAM_SHAPES_INIT_ORDER:
+            lin = torch.nn.Linear(ii, oo)
+            p[name + ".weight"], p[name + ".bias"] = lin.weight, lin.bias
+        nets.append(p)
     t0 = time.perf_counter()
     res = orc.render_rays(rays, nets[0], nets[1], lut, perturb=1.0, approximate_radiance=True)
     loss = fx.phase_b_loss(res, tg)
@@ -106,11 +171,16 @@ def cpu_reference_step(n_rays, threads):
     return time.perf_counter() - t0
 
 
+def cpu_sample_text(kind):
+    return ("/root/reference src/nerf_models (render_rays + train.py loss + backward, unmodified, baseline/_ref; torch CPU fp32, "
+            "anomaly mode off)" if kind == "reference" else "oracle/iblnerf_oracle.py (torch CPU fp32)")
+
+
 def eager_cuda_reference(n_rays, steps=2):
-    """The same reference algorithm (oracle port) in PyTorch EAGER mode on cuda:0 -- what a user of the reference gets
-    on this GPU without this package ("the oracle in eager CUDA fp32 as the reference-on-B200
-    bar").  A reported baseline like cpu_baseline: fp32 matmuls (parity setting) and TF32 matmuls (the setting of the
-    reference authors' Ampere GPUs, torch 1.11 default).  Returns {"fp32": rays/s, "tf32": rays/s}."""
+    """The same algorithm (oracle port) in PyTorch EAGER mode on cuda:0 -- what a user of the reference gets on this
+    GPU without this package ("the oracle in eager CUDA fp32 as the reference-on-B200 bar").
+    A reported baseline like cpu_baseline: fp32 matmuls (parity setting) and TF32 matmuls (the setting of the reference
+    authors' Ampere GPUs, torch 1.11 default).  Returns {"fp32": rays/s, "tf32": rays/s}."""
     import fixtures as fx
     from oracle import iblnerf_oracle as orc
     dev = torch.device("cuda:0")
@@ -153,10 +223,11 @@ def eager_cuda_reference(n_rays, steps=2):
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's own algorithm on the box's host cores (rank 0 only)."""
+    """--impl reference: the reference's own CPU implementation of the path on the box's host cores (rank 0 only)."""
     if rank != 0:
         return
     threads = os.cpu_count() or 1
+    kind = cpu_reference_kind()
     sample = 1024                       # BASELINE.json configs[0]: N_rand = 1024 on the CPU reference path
     for _ in range(max(1, min(args.warmup, 1))):
         cpu_reference_step(256, threads)
@@ -170,10 +241,194 @@ def run_reference(args, rank, world):
             # the product arm's workload (same string); each reference step is a bounded sample of it
             "config": {"workload": WORKLOAD % args.n_rand, "n_rand_per_gpu": args.n_rand,
                        "sample": "each step = fwd+bwd of %d of the %d rays (the reference algorithm scales linearly in rays)" % (sample, args.n_rand)},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": "%d rays x %d steps, oracle/iblnerf_oracle.py (torch CPU fp32)" % (sample, steps)},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind,
+                             "sample": "%d rays x %d steps, %s" % (sample, steps, cpu_sample_text(kind))},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ sub-records
+def camera_poses(dev, n=8):
+    poses = []
+    for i in range(n):
+        a = 2 * math.pi * i / n
+        c2w = torch.eye(4)[:3].clone()
+        c2w[0, 0], c2w[0, 2], c2w[2, 0], c2w[2, 2] = math.cos(a), math.sin(a), -math.sin(a), math.cos(a)
+        c2w[:, 3] = torch.tensor([2 * math.sin(a), 0., 2 * math.cos(a)])
+        poses.append(c2w.to(dev))
+    return poses
+
+
+def pinhole(H, W, fov_deg=60.0):
+    import numpy as np
+    focal = .5 * W / math.tan(.5 * math.radians(fov_deg))
+    return np.array([[focal, 0, .5 * W], [0, focal, .5 * H], [0, 0, 1]], np.float32)
+
+
+def render_record(ts, dev, rank, world, local, barrier, H=480, W=640, n_poses=8):
+    """BASELINE.json configs[2]: full-image test render (perturb = 0, all output maps), image rows sharded over the ranks,
+    one packed all_gather per image (its time is inside the measurement and reported separately)."""
+    from ibl_nerf_b200 import training
+    K = pinhole(H, W)
+    poses = camera_poses(dev, n_poses)
+    kw = dict(ts.kw, perturb=0.)
+    gather_ms = []
+
+    def render_all(timed_gather=False):
+        out = None
+        for c2w in poses:
+            if timed_gather and world > 1:
+                orig = dist.all_gather_into_tensor
+
+                def timed(*a, **k):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(); r = orig(*a, **k); e1.record()
+                    gather_ms.append((e0, e1))
+                    return r
+                dist.all_gather_into_tensor = timed
+                try:
+                    out = training.render_image_sharded(H, W, K, c2w, kw, chunk=1 << 16)
+                finally:
+                    dist.all_gather_into_tensor = orig
+            else:
+                out = training.render_image_sharded(H, W, K, c2w, kw, chunk=1 << 16)
+        return out
+    render_all()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = render_all(timed_gather=True)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if sampler else None
+    rays = n_poses * H * W
+    return {"config": "BASELINE configs[2]: %d synthetic poses, %dx%d, fov 60, perturb 0, all %d output maps, rows sharded over %d rank(s)"
+                      % (n_poses, H, W, len(out), world),
+            "metric": "render_rays_per_sec", "value": rays / ms.item() * 1e3, "unit": UNIT, "ms_per_image": ms.item() / n_poses,
+            "gather_ms_per_image": (sum(a.elapsed_time(b) for a, b in gather_ms) / n_poses) if gather_ms else 0.0,
+            "collectives_per_image": (len(gather_ms) / n_poses) if world > 1 else 0,
+            "tflops": rays * FLOP_PER_RAY_RENDER / ms.item() / 1e9, "clocks": clocks}
+
+
+def micro_record(dev, local, hbm_peak):
+    """BASELINE.json configs[4] (subset that fits a default run): raw2outputs compositing fwd / bwd and sample_pdf as
+    stand-alone kernels against the HBM roofline.  32 Mi samples per slab (2.4 GB of raw >> L2), CUDA events, algorithmic
+    bytes of SURVEY.md 8d (80 / 152 B per sample + per-ray terms; sample_pdf 4 (2 S - 3 + 2 N_importance) B per ray)."""
+    from ibl_nerf_b200._lib import call, ptr
+
+    def timeit(fn, iters=5, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+    sampler = ClockSampler(local)
+    rows = []
+    for S in (64, 192, 512):
+        n = (1 << 25) // S
+        raw = torch.randn(n, S, 18, device=dev)
+        z = torch.sort(torch.rand(n, S, device=dev) * 7.5 + 0.5, -1)[0]
+        rd = torch.randn(n, 3, device=dev)
+        w = torch.empty(n, S, device=dev); maps = torch.empty(n, 24, device=dev)
+        ms = timeit(lambda: call("ibln_composite_fwd", dev, ptr(raw), ptr(z), ptr(rd), None, n, S, 18, 3, 1, ptr(w), ptr(maps), None))
+        gb = n * (S * 80 + 92) / 1e9
+        rows.append(dict(kernel="composite_fwd", S=S, rays=n, ms=ms, gbs=gb / ms * 1e3, frac=gb / ms * 1e3 / hbm_peak, gsamples_s=n * S / ms / 1e6))
+        g_raw = torch.empty_like(raw); gm = torch.randn(n, 24, device=dev)
+        ms = timeit(lambda: call("ibln_composite_bwd", dev, ptr(raw), ptr(z), ptr(rd), None, ptr(w), ptr(gm), None, n, S, 18, 3, 1, ptr(g_raw)))
+        gb = n * (S * 152 + 108) / 1e9
+        rows.append(dict(kernel="composite_bwd", S=S, rays=n, ms=ms, gbs=gb / ms * 1e3, frac=gb / ms * 1e3 / hbm_peak, gsamples_s=n * S / ms / 1e6))
+        del raw, g_raw, w, z, gm
+        nb, ns = S - 1, (2 * S if S > 64 else 128)
+        n2 = 1 << 20
+        bins = torch.sort(torch.rand(n2, nb, device=dev), -1)[0]; wt = torch.rand(n2, nb - 1, device=dev)
+        u = torch.rand(n2, ns, device=dev, generator=torch.Generator(device=dev).manual_seed(2)); out = torch.empty(n2, ns, device=dev)
+        ms = timeit(lambda: call("ibln_sample_pdf", dev, ptr(bins), nb, ptr(wt), nb - 1, ptr(u), n2, nb, ns, ptr(out)))
+        gb = n2 * 4 * (nb + nb - 1 + 2 * ns) / 1e9
+        rows.append(dict(kernel="sample_pdf", S=S, bins=nb, samples=ns, rays=n2, ms=ms, gbs=gb / ms * 1e3, frac=gb / ms * 1e3 / hbm_peak,
+                         grays_s=n2 / ms / 1e6))
+        del bins, wt, u, out
+        torch.cuda.empty_cache()
+    return {"config": "BASELINE configs[4] subset: 32 Mi samples per compositing slab, 1 Mi rays for sample_pdf; frac = algorithmic GB/s / hbm_gbs",
+            "hbm_peak_gbs": hbm_peak, "rows": [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items()} for r in rows],
+            "clocks": sampler.stop()}
+
+
+def dp_parity(dev, rank, world, lut):
+    """Correctness of the N > 1 paths against ONE GPU computing the whole problem (src/train.py:479-481: one global-mean
+    loss), outside every timed region:
+      grad_fp32  exact-fp32 kernels: all-reduced gradient of the rank-sharded batch vs rank 0's gradient of the
+                 concatenated batch, rel. L2 over all parameters (bar 1e-3)
+      grad_bf16  the same through the fused tensor-core step (flat gradient buffer, overlapped all-reduce; bar 2e-2)
+      render     render_image_sharded (row tiles + one packed all_gather) vs the unsharded render, every map bit-equal"""
+    from ibl_nerf_b200 import training
+    from ibl_nerf_b200.renderer import render_decomp
+    out = {}
+    per = 128
+    n = per * world
+    o, d, tg = synth_rays(n, 4242, dev)
+    lo, hi = rank * per, (rank + 1) * per
+
+    def rel(a, b):
+        return ((a - b).double().norm() / (b.double().norm() + 1e-30)).item()
+    for tag, prec, bar in (("grad_fp32", "fp32", 1e-3), ("grad_bf16", "bf16", 2e-2)):
+        ts = training.TrainStep(dev, lut, precision=prec, seed=7)
+        ts.kw["perturb"] = 0.0                       # deterministic z / u: a ray's samples do not depend on its batch
+        if prec == "fp32":
+            def grads(ro, rd, t, reduce):
+                for p in ts.params:
+                    p.grad = None
+                res = render_decomp(0, 0, None, chunk=1 << 20, rays=(ro, rd), gt_values=t, approximate_radiance=True, **ts.kw)
+                training.phase_loss(res, t, "full").backward()
+                if reduce:
+                    ts.allreduce_grads()
+                return torch.cat([p.grad.reshape(-1) for p in ts.params])
+            g_shard = grads(o[lo:hi], d[lo:hi], {k: v[lo:hi] for k, v in tg.items()}, True)
+            g_full = grads(o, d, tg, False) if rank == 0 else None
+        else:
+            def grads(ro, rd, t, reduce):
+                world_saved = ts.world
+                ts.world = world if reduce else 1
+                ts.lr0 = 0.0                          # keep the weights: exp_avg after the step is 0.1 * mean gradient
+                ts.flat.exp_avg.zero_(); ts.flat.exp_avg_sq.zero_(); ts.flat.step_count = 0; ts.global_step = 0
+                ts.step(ro, rd, t)
+                ts.world = world_saved
+                return ts.flat.exp_avg.clone() * 10.0
+            g_shard = grads(o[lo:hi], d[lo:hi], {k: v[lo:hi] for k, v in tg.items()}, True)
+            g_full = grads(o, d, tg, False) if rank == 0 else None
+        err = torch.tensor([rel(g_shard, g_full) if rank == 0 else 0.0], device=dev)
+        dist.broadcast(err, 0)
+        out[tag] = {"rel_l2": err.item(), "bar": bar, "ok": bool(err.item() <= bar)}
+        del ts
+    # sharded render vs unsharded, 96 x 128 pixels
+    H, W = 96, 128
+    ts = training.TrainStep(dev, lut, precision="bf16", seed=7)
+    kw = dict(ts.kw, perturb=0.)
+    K, c2w = pinhole(H, W), camera_poses(dev, 8)[1]
+    shard = training.render_image_sharded(H, W, K, c2w, kw, chunk=1 << 16)
+    bad = []
+    if rank == 0:
+        from ibl_nerf_b200.helper import get_rays
+        ro, rd = get_rays(H, W, K, c2w)
+        with torch.no_grad():
+            full = render_decomp(H, W, K, chunk=1 << 16, rays=(ro.reshape(-1, 3), rd.reshape(-1, 3)), approximate_radiance=True, **kw)
+        for k in sorted(full):
+            a, b = shard[k].reshape(full[k].shape), full[k]
+            if not (torch.equal(torch.isnan(a), torch.isnan(b)) and torch.equal(a.nan_to_num(), b.nan_to_num())):
+                bad.append(k)
+    flag = torch.tensor([float(len(bad))], device=dev)
+    dist.broadcast(flag, 0)
+    out["render"] = {"maps": len(shard), "mismatching_maps": bad if rank == 0 else int(flag.item()), "ok": flag.item() == 0}
+    out["ok"] = all(v["ok"] for v in out.values())
+    return out
 
 
 def main():
@@ -183,11 +438,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n-rand", type=int, default=N_RAND)
+    ap.add_argument("--n-rand-total", type=int, default=65536, help="total rays per step of the strong-scaling sub-record")
     ap.add_argument("--precision", default=None, choices=[None, "bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the PyTorch-eager-on-GPU run of the oracle (N=1 only)")
+    ap.add_argument("--skip", default="", help="comma list of sub-records to skip: phases,strong,render,micro,dp_parity")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    skip = set(x for x in args.skip.split(",") if x)
 
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -215,7 +473,14 @@ def main():
     ts = training.TrainStep(dev, lut, precision=args.precision)
     o_d, d_d, tg_d = synth_rays(n, 100 + rank, dev)
     o_h, d_h, tg_h = synth_rays(n, 100 + rank, "cpu", pin=True)
+    step_keys = ("rgb", "rgb_1", "rgb_2", "rgb_3")                 # what the full-IBL phase reads (train.py:228, 329-331)
+    tg_h = {k: tg_h[k] for k in step_keys}
     h2d = sum(t.numel() * 4 for t in (o_h, d_h, *tg_h.values()))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
 
     def barrier():
         if world > 1:
@@ -304,54 +569,108 @@ def main():
     prof_all = _lib.PROFILE
     _lib.PROFILE = None
 
+    def sub_timed(fn, steps, warm=2):
+        """A sub-record's own timed region (+ clock sample on rank 0): ms per call, max over ranks."""
+        for _ in range(warm):
+            fn()
+        s = ClockSampler(local) if rank == 0 else None
+        ms = timed(fn, steps) / steps
+        return ms, (s.stop() if s else None)
+
+    extra = {}
+    if "phases" not in skip:
+        # the other two phases of the shipped schedule (configs/IBL-NeRF/common.txt:8-10), same rays, same optimizer state
+        ph = {}
+        for phase, flop in (("radiance", FLOP_PER_RAY_RADIANCE), ("prior", None)):
+            ts.set_phase(phase)
+            ms, ck = sub_timed(step_resident, max(3, args.steps // 2))
+            ph[phase] = {"ms_per_step": ms, "value": world * n / (ms * 1e-3), "unit": UNIT, "clocks": ck}
+            if flop:
+                ph[phase]["step_tflops"] = world * n * flop / (ms * 1e-3) / 1e12
+        ts.set_phase("full")
+        ph["note"] = ("radiance = iterations < N_iter_ignore_approximated_radiance (approximate_radiance False); prior = iterations >= "
+                      "N_iter_ignore_prior (albedo-prior + irradiance-regulariser losses, freeze_radiance + freeze_roughness: only the "
+                      "albedo / irradiance heads train)")
+        extra["phases"] = ph
+    if "strong" not in skip:
+        nt = args.n_rand_total
+        per = nt // world
+        o_s, d_s, tg_s = synth_rays(per, 500 + rank, dev)
+        ms, ck = sub_timed(lambda: ts.step(o_s, d_s, tg_s), 3, warm=2)
+        extra["strong"] = {"config": "BASELINE configs[3]: N_rand = %d rays per step in total, %d per GPU (micro-batches of %d), "
+                                     "NCCL gradient all-reduce" % (nt, per, ts.micro_batch),
+                           "n_rand_total": per * world, "ms_per_step": ms, "value": per * world / (ms * 1e-3), "unit": UNIT,
+                           "scaling": "strong", "clocks": ck}
+        del o_s, d_s, tg_s
+        ts._bufs.clear()
+        torch.cuda.empty_cache()
+    if "render" not in skip:
+        extra["render"] = render_record(ts, dev, rank, world, local, barrier)
+    if "micro" not in skip and world == 1:
+        ts._bufs.clear()
+        torch.cuda.empty_cache()
+        extra["micro"] = micro_record(dev, local, peaks.get("hbm_gbs", 6650.0))
+    if "dp_parity" not in skip and world > 1:
+        try:
+            extra["dp_parity"] = dp_parity(dev, rank, world, lut)
+        except Exception as e:
+            extra["dp_parity"] = {"ok": False, "error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+
     if rank == 0:
         torch.cuda.synchronize()
         launches = sum(v["launches"] for v in prof.values())
         mlp = prof.get("ibln_mlp_fwd")
         roof = None
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
         if mlp and mlp["events"]:
             dur_ms = sum(a.elapsed_time(b) for a, b in mlp["events"])
             peak = peaks.get("bf16_tflops_sustained", 1400.0)
             ach = mlp["flops"] / (dur_ms * 1e-3) / 1e12
+            traffic, traffic_src = None, "not measured in this run (ncu cannot run inside bench.py)"
+            try:        # per-launch dram bytes of the same kernel from the committed ncu --set full capture
+                t = json.load(open(os.path.join(ROOT, "profiles", "r2_mlp_fwd_traffic.json")))
+                traffic, traffic_src = t["dram_bytes_per_launch_mean"], "profiles/r2_mlp_fwd_traffic.json (%s), not measured in this run" % t["source"]
+            except Exception:
+                pass
             roof = {"bound": "tensor", "kernel": "mlp_fwd_kernel (fused encode + MLP, tcgen05)", "achieved": ach, "peak": peak,
-                    "unit": "TFLOP/s", "frac": ach / peak,
-                    # dram__bytes_read+write per launch, mean over the 6 launches of one step (profiles/r1_final_ncu_full.md);
-                    # 99.5 % of it is the activation stash written by the two gradient launches
-                    "traffic": 1.228e9, "traffic_unit": "B/launch",
+                    "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic, "traffic_unit": "B/launch", "traffic_source": traffic_src,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)",
                     "launches": len(mlp["events"]), "share_of_step": dur_ms / ms_total}
+        own = sum(v["launches"] for k, v in prof.items())
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16" if (args.precision or ib.mlp.default_precision()) == "bf16" else "f32",
                 "data": "synthetic rays (seeded), random-init weights of the kitchen architecture",
                 "config": {"workload": WORKLOAD % n,
-                           "n_rand_per_gpu": n, "parallelism": "ray-sharded dp%d, NCCL grad all-reduce" % world,
+                           "n_rand_per_gpu": n, "parallelism": "ray-sharded dp%d, NCCL grad all-reduce (per network, overlapped with the backward)" % world,
+                           "route": "fused kernel chain (training.TrainStep, no autograd graph)" if ts.fused else "render_decomp + autograd",
                            "l2": "per-step working set >> 126 MB L2 (no explicit flush)",
                            "step_tflops": world * n * FLOP_PER_RAY_STEP / (ms_step * 1e-3) / 1e12},
                 "clocks": clocks,
                 "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
                 "gpu_launches": launches,
+                "gpu_launches_note": "kernels of libiblnerf_b200.so launched in the timed region (%d per step); besides them each step "
+                                     "runs 2 torch.rand launches and 1 memset" % (own // max(args.steps, 1)),
                 "kernel_launches_by_entry": {k: v["launches"] for k, v in sorted(prof.items())},
                 "ms_per_step_by_entry": {k: round(sum(a.elapsed_time(b) for a, b in v["events"]) / 2, 4)
                                          for k, v in sorted(prof_all.items())},
                 "roofline": roof}
+        line["glue_ms_per_step"] = round(ms_step - sum(line["ms_per_step_by_entry"].values()), 4)
         if mlp and mlp["events"] and len(mlp["events"]) % args.steps == 0:
             per = len(mlp["events"]) // args.steps
             line["mlp_fwd_launch_ms"] = [round(sum(mlp["events"][i * per + j][0].elapsed_time(mlp["events"][i * per + j][1])
                                                    for i in range(args.steps)) / args.steps, 4) for j in range(per)]
+        line.update(extra)
         if not args.no_cpu_baseline and world == 1:     # reported at N=1 only
             threads = os.cpu_count() or 1
             sample = 1024
+            kind = cpu_reference_kind()
             cpu_reference_step(64, threads)
             secs = [cpu_reference_step(sample, threads) for _ in range(2)]
             sec = sum(secs) / len(secs)
-            line["cpu_baseline"] = {"value": sample / sec, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": "2 steps of %d rays (fwd+bwd, %.1f s), oracle/iblnerf_oracle.py, torch CPU fp32" % (sample, sum(secs))}
+            line["cpu_baseline"] = {"value": sample / sec, "unit": UNIT, "cores": threads, "kind": kind,
+                                    "sample": "2 steps of %d rays (fwd+bwd, %.1f s), %s" % (sample, sum(secs), cpu_sample_text(kind))}
+            if kind == "port" and "error" in _REF:
+                line["cpu_baseline"]["reference_import_error"] = _REF["error"]
         if not args.no_eager_baseline and world == 1:
             try:
                 eg = eager_cuda_reference(n)
