@@ -58,35 +58,60 @@ def synth_rays(n, seed, device="cpu", pin=False):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 20 ms DURING a timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """ONE nvidia-smi process per bench run samples SM clocks / throttle reasons every 20 ms with a timestamp; each timed
+    region reports the samples that fall inside its own [start, stop] wall-clock window (nvidia-smi needs ~0.2 s to
+    start, which is longer than some of the regions, so it is started once, up front)."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    _proc = None
+    _file = None
+
+    @classmethod
+    def start_global(cls, index):
+        if cls._proc is not None:
+            return
+        cls._file = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            cls._proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + cls.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "20"], stdout=cls._file, stderr=subprocess.DEVNULL)
+        except Exception:
+            cls._proc = False
+
+    @classmethod
+    def stop_global(cls):
+        if cls._proc:
+            cls._proc.terminate()
+            try:
+                cls._proc.wait(timeout=5)
+            except Exception:
+                cls._proc.kill()
+        if cls._file is not None:
+            try:
+                os.unlink(cls._file.name)
+            except OSError:
+                pass
+        cls._proc, cls._file = None, None
 
     def __init__(self, index):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                       "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
-        except Exception:
-            self.p = None
+        ClockSampler.start_global(index)
+        self.t0 = time.time()
 
     def stop(self):
-        if self.p is None:
+        import datetime
+        t1 = time.time()
+        if not ClockSampler._proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        rows = [r.strip().split(", ") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
-        os.unlink(self.f.name)
+        time.sleep(0.03)                 # let the sample that covers the end of the window reach the file
         sm, mx, reasons = [], None, set()
-        for r in rows:
+        for row in open(ClockSampler._file.name).read().strip().splitlines():
+            r = [x.strip() for x in row.split(",")]
             try:
-                sm.append(float(r[0])); mx = float(r[1])
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                    if v.strip().lower().startswith("active"):
+                ts = datetime.datetime.strptime(r[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                if ts < self.t0 - 0.02 or ts > t1 + 0.02:
+                    continue
+                sm.append(float(r[1])); mx = float(r[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
                         reasons.add(name)
             except Exception:
                 pass
@@ -468,6 +493,8 @@ def main():
             os.environ["NCCL_DEBUG"] = "WARN"       # the version banner goes to stdout, which carries the ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     _lib.lib()
+    if rank == 0:
+        ClockSampler.start_global(local)
     n = args.n_rand
     lut = fx.load_lut().to(dev)
     ts = training.TrainStep(dev, lut, precision=args.precision)
@@ -681,6 +708,7 @@ def main():
                 line["eager_cuda_baseline"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
             torch.cuda.empty_cache()
         print(json.dumps(line), flush=True)
+    ClockSampler.stop_global()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
