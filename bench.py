@@ -467,8 +467,6 @@ def main():
     ap.add_argument("--precision", default=None, choices=[None, "bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the PyTorch-eager-on-GPU run of the oracle (N=1 only)")
-    ap.add_argument("--graph", action="store_true", help="experiment: replay the fused step as CUDA graphs (no per-kernel events, so "
-                                                         "the line then carries no live roofline)")
     ap.add_argument("--skip", default="", help="comma list of sub-records to skip: phases,strong,render,micro,dp_parity")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -499,7 +497,7 @@ def main():
         ClockSampler.start_global(local)
     n = args.n_rand
     lut = fx.load_lut().to(dev)
-    ts = training.TrainStep(dev, lut, precision=args.precision, graph=args.graph)
+    ts = training.TrainStep(dev, lut, precision=args.precision)
     o_d, d_d, tg_d = synth_rays(n, 100 + rank, dev)
     o_h, d_h, tg_h = synth_rays(n, 100 + rank, "cpu", pin=True)
     step_keys = ("rgb", "rgb_1", "rgb_2", "rgb_3")                 # what the full-IBL phase reads (train.py:228, 329-331)
@@ -568,12 +566,11 @@ def main():
     # evaluations) is far larger than the 126 MB L2, so no explicit flush is needed between iterations.
     # inside the timed region only the dominant kernel's launches are bracketed by CUDA events (roofline); every
     # entry point still counts its launches
-    if not args.graph:
-        _lib.PROFILE = {}
-        _lib.PROFILE_EVENTS = {"ibln_mlp_fwd"}
+    _lib.PROFILE = {}
+    _lib.PROFILE_EVENTS = {"ibln_mlp_fwd"}
     sampler = ClockSampler(local) if rank == 0 else None
     ms_total = timed(step_resident, args.steps)
-    prof = _lib.PROFILE or {}
+    prof = _lib.PROFILE
     _lib.PROFILE = None
     _lib.PROFILE_EVENTS = None
     ms_step = ms_total / args.steps

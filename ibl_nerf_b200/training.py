@@ -227,10 +227,6 @@ class _StepBuffers:
             self.depths4 = f(4 * n)
             self.refl_raw = f(n * 64, 18)
         self.near, self.far = f(n), f(n)
-        # static inputs + captured graphs of the CUDA-graph route (TrainStep(graph=True))
-        self.in_o, self.in_d = f(n, 3), f(n, 3)
-        self.in_tg = {k: f(n, 3) for k in ("rgb", "rgb_1", "rgb_2", "rgb_3", "prior_albedo")}
-        self.graphs = {}
 
 
 class TrainStep:
@@ -242,7 +238,7 @@ class TrainStep:
 
     def __init__(self, device, lut, near=0.5, far=8.0, lr=5e-4, seed=0, precision=None, approximate_radiance=True,
                  chunk=1 << 20, micro_batch=8192, phase=None, lrate_decay=500, betas=None, prior_irradiance_mean=0.5,
-                 fused=True, overlap_allreduce=True, graph=False):
+                 fused=True, overlap_allreduce=True):
         torch.manual_seed(seed)
         self.device = torch.device(device)
         self.coarse = IBLNeRF(**KITCHEN_ARCH).to(device)
@@ -272,10 +268,6 @@ class TrainStep:
         self.micro_batch = micro_batch      # rays per forward/backward pass (bounds the activation stash: ~1.7 GB per 1024 rays)
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.overlap_allreduce = overlap_allreduce
-        # graph=True: the fused chain of a single-micro-batch step is captured once per (rays, phase) into two CUDA graphs
-        # (everything up to the fine network's backward | the coarse network's backward; the gradient all-reduce of the
-        # fine network starts between them) and replayed; Adam stays outside (its step count / lr are host scalars)
-        self.graph = bool(graph) and self.fused
         self._bufs = {}
         self._pending = []
         self.set_phase(phase or ("full" if approximate_radiance else "radiance"))
@@ -411,10 +403,8 @@ class TrainStep:
         same two torch.rand calls, in the same order, as the autograd route (t_rand then u)."""
         dev = self.device
         f32c = _lib.f32c
-        mb = self.micro_batch
-        if self.graph and n_total <= mb and _lib.PROFILE is None:
-            return self._step_graphed(rays_o, rays_d, targets, n_total)
         self.flat.zero_grad()
+        mb = self.micro_batch
         for lo in range(0, n_total, mb):
             hi = min(n_total, lo + mb)
             n = hi - lo
@@ -423,70 +413,27 @@ class TrainStep:
             o, d = f32c(rays_o if whole else rays_o[lo:hi]), f32c(rays_d if whole else rays_d[lo:hi])
             tg = {k: f32c(v if whole else v[lo:hi]) for k, v in targets.items()}
             b = self._buffers(n)
-            self._chain_a(b, o, d, tg, n, n / n_total)
+            c, f = b.coarse, b.fine
+            perturb = self.kw["perturb"] > 0.
+            if perturb:
+                torch.rand(n, 64, out=b.t_rand)
+            call("ibln_stratified_z", dev, ptr(b.near), ptr(b.far), ptr(b.t_rand) if perturb else None, n, 64, 0, ptr(c.z))
+            self._forward_pass(self.coarse, c, b, o, d, n)
+            if perturb:
+                torch.rand(n, 128, out=b.u)
+            else:
+                b.u.copy_(torch.linspace(0., 1., 128, device=dev).expand(n, 128))
+            call("ibln_hierarchical_sample", dev, ptr(c.z), ptr(c.weights), ptr(b.u), n, 64, 128, ptr(b.z_samples), ptr(f.z))
+            self._forward_pass(self.fine, f, b, o, d, n)
+            scale = n / n_total
+            self._loss_pass(f, tg, n, scale, True)
+            self._loss_pass(c, tg, n, scale, False)
+            self._backward_pass(self.fine, 1, f, b, d, n)
             if last:
                 self._grad_ready(1)
-            self._chain_b(b, d, n)
+            self._backward_pass(self.coarse, 0, c, b, d, n)
             if last:
                 self._grad_ready(0)
-        self._finish_allreduce()
-        self.flat.adam_step(self.lr, grad_scale=1.0 / self.world)
-        return self.flat.loss[0]
-
-    def _chain_a(self, b, o, d, tg, n, scale):
-        """stratified z -> coarse pass -> hierarchical samples -> fine pass -> losses -> backward of the fine network."""
-        dev = self.device
-        c, f = b.coarse, b.fine
-        perturb = self.kw["perturb"] > 0.
-        if perturb:
-            torch.rand(n, 64, out=b.t_rand)
-        call("ibln_stratified_z", dev, ptr(b.near), ptr(b.far), ptr(b.t_rand) if perturb else None, n, 64, 0, ptr(c.z))
-        self._forward_pass(self.coarse, c, b, o, d, n)
-        if perturb:
-            torch.rand(n, 128, out=b.u)
-        else:
-            b.u.copy_(torch.linspace(0., 1., 128, device=dev).expand(n, 128))
-        call("ibln_hierarchical_sample", dev, ptr(c.z), ptr(c.weights), ptr(b.u), n, 64, 128, ptr(b.z_samples), ptr(f.z))
-        self._forward_pass(self.fine, f, b, o, d, n)
-        self._loss_pass(f, tg, n, scale, True)
-        self._loss_pass(c, tg, n, scale, False)
-        self._backward_pass(self.fine, 1, f, b, d, n)
-
-    def _chain_b(self, b, d, n):
-        self._backward_pass(self.coarse, 0, b.coarse, b, d, n)
-
-    def input_buffers(self, n):
-        """Static device inputs of the graph route: (rays_o [n,3], rays_d [n,3], {target name: [n,3]}).  Filling them
-        directly (e.g. with the H2D copy of the batch) and passing them to step() avoids a device-to-device copy."""
-        b = self._buffers(n)
-        return b.in_o, b.in_d, b.in_tg
-
-    def _step_graphed(self, rays_o, rays_d, targets, n):
-        b = self._buffers(n)
-        for dst, src in [(b.in_o, rays_o), (b.in_d, rays_d)] + [(b.in_tg[k], v) for k, v in targets.items() if k in b.in_tg]:
-            if src.data_ptr() != dst.data_ptr():
-                dst.copy_(src, non_blocking=True)
-        key = (self.phase, self.kw["perturb"] > 0.)
-        g = b.graphs.get(key)
-        if g is None:
-            for net in (self.coarse, self.fine):
-                net.packed_weights()                  # current before capture: the graphs read these buffers in place
-            # one eager pass first (kernel attributes, lazy initialisation), then capture
-            self.flat.zero_grad()
-            self._chain_a(b, b.in_o, b.in_d, b.in_tg, n, 1.0)
-            self._chain_b(b, b.in_d, n)
-            torch.cuda.synchronize(self.device)
-            ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-            with torch.cuda.graph(ga):
-                self.flat.zero_grad()
-                self._chain_a(b, b.in_o, b.in_d, b.in_tg, n, 1.0)
-            with torch.cuda.graph(gb, pool=ga.pool()):
-                self._chain_b(b, b.in_d, n)
-            g = b.graphs[key] = (ga, gb)
-        g[0].replay()
-        self._grad_ready(1)
-        g[1].replay()
-        self._grad_ready(0)
         self._finish_allreduce()
         self.flat.adam_step(self.lr, grad_scale=1.0 / self.world)
         return self.flat.loss[0]
@@ -561,9 +508,7 @@ def render_image_sharded(H, W, K, c2w, render_kwargs, chunk=1 << 16, approximate
     with torch.no_grad():
         res = render_decomp(H, W, K, chunk=chunk, rays=(rays_o[lo:hi], rays_d[lo:hi]),
                             approximate_radiance=approximate_radiance, **render_kwargs)
-    # the output MAPS are gathered; the per-sample compositing weights ([rays, 64 / 192]: 3/4 of all bytes, read by no
-    # caller of the test render, ibl_nerf_renderer.py:870-900) stay on their rank unless asked for by name
-    keys = keys or sorted(k for k in res.keys() if k not in ("weights", "weights0"))
+    keys = keys or sorted(res.keys())
     if world == 1:
         return {k: res[k] for k in keys}
     return gather_maps(res, keys, H * W, world)
