@@ -13,7 +13,8 @@ the per-step learning-rate decay -> bf16 weight re-pack.  The three phases of th
 Two routes compute the same step (tests/test_gpu_train.py compares them):
   * fused (default on the tensor-core path): every kernel is called directly on preallocated buffers, the backward is
     the hand-ordered chain loss -> shade_bwd -> composite_bwd -> mlp_bwd.  No autograd graph, no ATen kernels besides
-    the two torch.rand draws, CUDA-graph capturable;
+    the two torch.rand draws (replaying it from captured CUDA graphs was measured on the same box: 10.83 vs 10.91 ms,
+    i.e. the step is bound by its kernels, not by launch gaps -- not kept);
   * autograd: render_decomp (the drop-in API of the reference) + torch autograd, used by the exact fp32 mode and as the
     cross-check.
 Rays are independent, so the batch is sharded across ranks with replicated weights; the only collective is the
@@ -508,7 +509,9 @@ def render_image_sharded(H, W, K, c2w, render_kwargs, chunk=1 << 16, approximate
     with torch.no_grad():
         res = render_decomp(H, W, K, chunk=chunk, rays=(rays_o[lo:hi], rays_d[lo:hi]),
                             approximate_radiance=approximate_radiance, **render_kwargs)
-    keys = keys or sorted(res.keys())
+    # the output MAPS are gathered; the per-sample compositing weights ([rays, 64 / 192]: 3/4 of all bytes, read by no
+    # caller of the test render, ibl_nerf_renderer.py:870-900) stay on their rank unless asked for by name
+    keys = keys or sorted(k for k in res.keys() if k not in ("weights", "weights0"))
     if world == 1:
         return {k: res[k] for k in keys}
     return gather_maps(res, keys, H * W, world)
