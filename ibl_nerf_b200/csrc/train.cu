@@ -160,7 +160,7 @@ extern "C" int ibln_adam_step(float* param, const float* grad, float* exp_avg, f
 // for N random pixels of one image + NerfDataset.get_info pixel gathers (dataset_interface.py:178-197) of the
 // target image and its prefiltered copies.
 namespace ibln {
-struct GatherArgs { const float* img[8]; float* out[8]; int ch[8]; int n_img; };
+struct GatherArgs { const float* img[12]; float* out[12]; int ch[12]; int n_img; };
 __global__ void __launch_bounds__(256)
 sample_rays_kernel(const int* __restrict__ u, const int* __restrict__ v, int n, int H, int W, float fx, float fy, float cx,
                    float cy, const float* __restrict__ c2w /* [3,4] row-major */, float* __restrict__ rays_o,
@@ -191,7 +191,7 @@ extern "C" int ibln_sample_rays(const int* u, const int* v, int n, int height, i
                                 const float* c2w, float* rays_o, float* rays_d, const float* const* images,
                                 float* const* outputs, const int* channels, int n_images, int device, void* stream) {
   if (n == 0) return 0;
-  if (n < 0 || !u || !v || !c2w || !rays_o || !rays_d || n_images < 0 || n_images > 8 || height < 1 || width < 1) return IBLN_EINVAL;
+  if (n < 0 || !u || !v || !c2w || !rays_o || !rays_d || n_images < 0 || n_images > 12 || height < 1 || width < 1) return IBLN_EINVAL;
   if (n_images > 0 && (!images || !outputs || !channels)) return IBLN_EINVAL;
   ibln::GatherArgs ga;
   ga.n_img = n_images;

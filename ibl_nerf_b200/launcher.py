@@ -50,6 +50,10 @@ def main(argv=None):
     os.chdir(src)                                    # the reference uses paths relative to src/ (../data, ../configs)
     sys.argv = [argv[1] + ".py"] + argv[2:]
     mod = importlib.import_module(argv[1])
+    if os.environ.get("IBLN_DEVICE_SAMPLER", "1") != "0" and hasattr(mod, "sample_generator_single_image"):
+        # the driver star-imported the host-numpy generator (train.py:23): rebind it to the device one
+        from . import sampling
+        mod.sample_generator_single_image = sampling.sample_generator_single_image
     args = prepare_args(mod, mod.recursive_config_parser().parse_args())
     getattr(mod, argv[1])(args)
 

@@ -246,7 +246,7 @@ int ibln_zero(void* buf, int64_t bytes, int device, void* stream);
 /* Ray generation + target gather for one training batch: get_rays_few
  * (nerf_renderer_helper.py:14-23) for pixels (u[i], v[i]) of a camera (intrinsics fx, fy, cx, cy; c2w [3,4]
  * row-major, device) -> rays_o, rays_d [N,3], and NerfDataset.get_info pixel gathers
- * (dataset_interface.py:178-197): outputs[k][i,:] = images[k][v[i], u[i], :] for n_images (<= 8) device images
+ * (dataset_interface.py:178-197): outputs[k][i,:] = images[k][v[i], u[i], :] for n_images (<= 12) device images
  * [H,W,channels[k]].  images / outputs / channels are HOST arrays (of device pointers / ints). */
 int ibln_sample_rays(const int* u, const int* v, int n, int height, int width, float fx, float fy, float cx, float cy,
                      const float* c2w, float* rays_o, float* rays_d, const float* const* images,

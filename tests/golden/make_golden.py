@@ -239,6 +239,25 @@ def g_render_rays():
     npz("render_rays_test.npz", rays=rays, **{k: v for k, v in res.items()})
 
 
+def g_rays_few():
+    """get_rays_few (nerf_renderer_helper.py:14-23) exactly as sample_generator_single_image calls it
+    (utils/generator_utils.py:108-142): numpy pixel draws -> torch.Tensor uv -> rays of one posed pinhole view."""
+    from nerf_models.nerf_renderer_helper import get_rays_few, get_rays
+    import math
+    H, W, n = 96, 128, 512
+    focal = .5 * W / math.tan(.5 * math.radians(60))
+    K = np.array([[focal, 0, .5 * W], [0, focal, .5 * H], [0, 0, 1]]).astype(np.float32)
+    a = 0.7
+    c2w = torch.tensor([[math.cos(a), 0.1, math.sin(a), 1.5], [0., 1., 0.2, -0.3], [-math.sin(a), 0.05, math.cos(a), 2.0], [0., 0., 0., 1.]])
+    rs = np.random.RandomState(0)
+    u, v = rs.randint(0, W, n), rs.randint(0, H, n)
+    uv_t = torch.Tensor(np.stack([u, v], 1))
+    ro, rd = get_rays_few(uv_t, K, c2w[:3, :4])
+    fo, fd = get_rays(H, W, K, c2w[:3, :4])
+    npz("rays_few.npz", u=u.astype(np.int32), v=v.astype(np.int32), K=K, c2w=c2w, rays_o=ro.contiguous(), rays_d=rd,
+        full_rays_d_corner=fd[[0, 0, H - 1, H - 1], [0, W - 1, 0, W - 1]])
+
+
 def g_depth_to_normal():
     from utils.depth_to_normal_utils import depth_to_normal_image_space      # utils/depth_to_normal_utils.py:26-46
     g = torch.Generator().manual_seed(33)
@@ -253,7 +272,7 @@ def g_depth_to_normal():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["lut", "posenc", "sample_pdf", "composite", "shading", "mlp", "render_rays", "depth_to_normal", "edit_insert"]
+    which = sys.argv[1:] or ["lut", "posenc", "sample_pdf", "composite", "shading", "mlp", "render_rays", "depth_to_normal", "edit_insert", "rays_few"]
     for w in which:
         {"lut": dump_lut, "posenc": g_posenc, "sample_pdf": g_sample_pdf, "composite": g_composite,
-         "shading": g_shading, "edit_insert": g_edit_insert, "mlp": g_mlp, "render_rays": g_render_rays, "depth_to_normal": g_depth_to_normal}[w]()
+         "shading": g_shading, "edit_insert": g_edit_insert, "rays_few": g_rays_few, "mlp": g_mlp, "render_rays": g_render_rays, "depth_to_normal": g_depth_to_normal}[w]()

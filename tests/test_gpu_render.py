@@ -154,6 +154,69 @@ def test_full_size_mlp_properties():
     assert torch.isfinite(a).all()
 
 
+def test_full_size_mlp_vs_rounding_point_oracle_on_a_subsample():
+    """BASELINE config size (4096 rays x 192 samples = 786 432 points through the tensor-core kernels), compared with
+    the oracle MLP that has the kernel's rounding points (bf16 weights / hidden activations, fp32 accumulation and heads)
+    on a random 2 % of the RAYS (82 rays, all of their 192 samples: ~15.7 k points on the CPU), for the stash
+    (gradient), inference, sigma-only and epsilon-shifted programs."""
+    from test_gpu_mlp import bf16_oracle
+    coarse, _ = build_nets(DEV, structured=True, precision="bf16")
+    n, s = 4096, 192
+    ro, rd = fx.make_rays(n, seed=19)
+    z = fx.make_sorted_z(n, s, seed=19)
+    pick = torch.randperm(n, generator=torch.Generator().manual_seed(2))[: n // 50]
+    pts = ro[pick][:, None] + rd[pick][:, None] * z[pick][..., None]
+    want_full = bf16_oracle(coarse, pts, rd[pick])
+    scale = want_full.abs().max().item()
+    g = [t.to(DEV) for t in (ro, rd, z)]
+    with torch.no_grad():
+        inf = coarse.query_rays(*g)
+        sig = coarse.query_rays(*g, sigma_only=True)
+        eps4 = coarse.query_eps_sigma(*g, 0.01)
+    stash = coarse.query_rays(*g)                              # grad enabled: the stash instantiation
+    assert stash.requires_grad and torch.equal(stash.detach(), inf)
+    close(inf[pick.to(DEV)], want_full, rtol=2e-2, atol=2e-3 * scale, name="full program, 4096 x 192")
+    close(sig[pick.to(DEV)], want_full[..., :1], rtol=2e-2, atol=2e-3 * scale, name="sigma-only program")
+    eps_pts = ib.ops.normal_eps_points(g[0][pick.to(DEV)], g[1][pick.to(DEV)], g[2][pick.to(DEV)], 0.01)       # [4 * 82, 192, 3]
+    want_eps = bf16_oracle(coarse, eps_pts.cpu(), None)[..., 0].reshape(4, len(pick), s)
+    got_eps = eps4.reshape(4, n, s)[:, pick.to(DEV)]
+    close(got_eps, want_eps, rtol=2e-2, atol=2e-3 * scale, name="epsilon-shifted sigma program")
+
+
+def test_full_size_image_sharded_render_equals_unsharded():
+    """BASELINE configs[2] size: one 480 x 640 view rendered as 4 row tiles (the per-rank work of render_image_sharded at
+    world = 4, executed one after the other on this GPU) and packed / unpacked like the final gather == the unsharded
+    render, bit for bit, for every output map."""
+    import math
+    import numpy as np
+    from ibl_nerf_b200 import training
+    from ibl_nerf_b200.helper import get_rays
+    H, W, world = 480, 640, 4
+    coarse, fine = build_nets(DEV, structured=True, precision="bf16")
+    kw = training.kitchen_render_kwargs(coarse, fine, fx.load_lut().to(DEV), fx.NEAR, fx.FAR, perturb=0.)
+    focal = .5 * W / math.tan(.5 * math.radians(60))
+    K = np.array([[focal, 0, .5 * W], [0, focal, .5 * H], [0, 0, 1]], np.float32)
+    c2w = torch.tensor([[0.8, 0., 0.6, 1.2], [0., 1., 0., 0.], [-0.6, 0., 0.8, 1.6]], device=DEV)
+    ro, rd = get_rays(H, W, K, c2w)
+    ro, rd = ro.reshape(-1, 3), rd.reshape(-1, 3)
+    with torch.no_grad():
+        full = ib.render_decomp(H, W, K, chunk=1 << 16, rays=(ro, rd), approximate_radiance=True, **kw)
+        keys = sorted(k for k in full if k not in ("weights", "weights0"))
+        per = (H * W + world - 1) // world
+        bufs = []
+        for r in range(world):
+            lo, hi = training.shard_rows(H * W, r, world)
+            res = ib.render_decomp(H, W, K, chunk=1 << 16, rays=(ro[lo:hi], rd[lo:hi]), approximate_radiance=True, **kw)
+            buf, layout = training.pack_maps(res, keys, per)
+            bufs.append(buf)
+        got = training.unpack_maps(torch.cat(bufs, 0), layout, H * W)
+    assert len(keys) >= 40
+    for k in keys:
+        a, b = got[k].reshape(full[k].shape), full[k]
+        assert torch.equal(torch.isnan(a), torch.isnan(b)) and torch.equal(a.nan_to_num(), b.nan_to_num()), k
+    assert torch.isfinite(full["color_map"]).all() and full["color_map"].std() > 1e-3
+
+
 def test_render_decomp_path_export(tmp_path):
     """Export path (ibl_nerf_renderer.py:819-910): returned float stacks == the maps of render_decomp, PNG files ==
     to8b of them (uint8 atlas kernel + batched D2H + threaded PNG writers)."""

@@ -211,3 +211,53 @@ def test_fused_step_micro_batches_equal_one_batch():
     assert abs(out[0][0] - out[1][0]) <= 1e-4 * abs(out[0][0]), out
     rel = ((out[0][1] - out[1][1]).double().norm() / out[0][1].double().norm()).item()
     assert rel < 2e-3, rel
+
+
+def test_sample_rays_kernel_matches_reference_golden():
+    """ibln_sample_rays against the REFERENCE's get_rays_few output (tests/golden/rays_few.npz, written by
+    make_golden.py from nerf_renderer_helper.py:14-23 with the pixel draws of generator_utils.py:108-109)."""
+    from ibl_nerf_b200 import helper
+    from util import G
+    g = G("rays_few.npz", DEV)
+    ro, rd, _ = helper.sample_training_rays(g["u"], g["v"], g["K"].cpu().numpy(), g["c2w"][:3, :4], {})
+    assert torch.equal(ro, g["rays_o"])
+    close(rd, g["rays_d"], rtol=1e-6, atol=1e-7, name="rays_d")
+
+
+def test_device_sample_generator_yields_the_reference_tuple():
+    """sampling.sample_generator_single_image (device RNG + one gather kernel) on a stand-in dataset with the attributes
+    NerfDataset exposes: the yield tuple, keys, shapes and values follow generator_utils.py:108-158 /
+    dataset_interface.py:178-197 for the pixels it drew."""
+    import math
+    import types
+    import numpy as np
+    from ibl_nerf_b200 import helper, sampling
+    H, W, n_img = 64, 80, 3
+    g = torch.Generator().manual_seed(8)
+    r = lambda *s: torch.rand(*s, generator=g).to(DEV)
+    ds = types.SimpleNamespace(
+        height=H, width=W, coarse_radiance_number=3, images=r(n_img, H, W, 3), prefiltered_images=[r(n_img, H, W, 3) for _ in range(3)],
+        load_albedo=True, albedos=r(n_img, H, W, 3), load_normal=True, normals=r(n_img, H, W, 3), load_roughness=True,
+        roughness=r(n_img, H, W, 1), load_depth=True, depths=r(n_img, H, W, 1), load_irradiance=True, irradiances=r(n_img, H, W, 3),
+        load_priors=True, prior_albedos=r(n_img, H, W, 3), prior_irradiances=r(n_img, H, W, 3),
+        poses=torch.eye(4).repeat(n_img, 1, 1).to(DEV) + 0.1 * r(n_img, 4, 4))
+    focal = .5 * W / math.tan(.5 * math.radians(60))
+    ds.get_focal_matrix = lambda: np.array([[focal, 0, .5 * W], [0, focal, .5 * H], [0, 0, 1]], np.float32)
+    ds.__len__ = lambda: n_img
+    ds = type("DS", (), dict(vars(ds), __len__=lambda self: n_img))()
+    info, ro, rd, u, v = sampling.sample_batch(ds, 1, 2048, sampling.crop_window(H, W, 0, 10, 0.5))
+    assert int(u.min()) >= 20 and int(u.max()) < 60 and int(v.min()) >= 16 and int(v.max()) < 48      # centre crop
+    ul, vl = u.long(), v.long()
+    want = {"rgb": ds.images[1][vl, ul], "rgb_2": ds.prefiltered_images[1][1][vl, ul], "albedo": ds.albedos[1][vl, ul],
+            "normal": ds.normals[1][vl, ul], "roughness": ds.roughness[1][vl, ul], "depth": ds.depths[1][vl, ul],
+            "irradiance": ds.irradiances[1][vl, ul], "prior_albedo": ds.prior_albedos[1][vl, ul],
+            "prior_irradiance": ds.prior_irradiances[1][vl, ul, 0]}
+    assert set(info) == set(want) | {"rgb_1", "rgb_3"}
+    for k, w_ in want.items():
+        assert info[k].shape == w_.shape and torch.equal(info[k], w_), k
+    wo, wd = helper.get_rays_few(torch.stack([u, v], 1).float().cpu(), ds.get_focal_matrix(), ds.poses[1][:3, :4].cpu())
+    assert torch.equal(ro.cpu(), wo.contiguous())
+    close(rd, wd, rtol=1e-6, atol=1e-7, name="rays_d")
+    gen = sampling.sample_generator_single_image(ds, batch_size=256, precrop_iters=0)
+    out = next(gen)
+    assert len(out) == 6 and out[1].shape == (256, 3) and out[3] == {} and out[4] is None and out[0]["rgb"].shape == (256, 3)

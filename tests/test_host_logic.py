@@ -88,3 +88,25 @@ def test_pack_maps_round_trip():
     assert buf.shape == (9, 3 + 1 + 12)
     out = training.unpack_maps(buf, layout, 7)
     assert all(torch.equal(out[k], res[k]) for k in res)
+
+
+def test_host_ray_helpers_match_reference_golden():
+    """helper.get_rays_few / get_rays (host mirror of nerf_renderer_helper.py:14-45) against outputs of the reference."""
+    import numpy as np
+    import torch
+    from ibl_nerf_b200 import helper
+    from util import G
+    g = G("rays_few.npz")
+    uv = torch.stack([g["u"], g["v"]], 1).float()
+    ro, rd = helper.get_rays_few(uv, g["K"].numpy(), g["c2w"][:3, :4])
+    assert torch.equal(ro.contiguous(), g["rays_o"]) and torch.equal(rd, g["rays_d"])
+    fo, fd = helper.get_rays(96, 128, g["K"].numpy(), g["c2w"][:3, :4])
+    assert torch.equal(fd[[0, 0, 95, 95], [0, 127, 0, 127]], g["full_rays_d_corner"])
+
+
+def test_sample_generator_crop_window():
+    """generator_utils.py:86-108."""
+    from ibl_nerf_b200 import sampling
+    assert sampling.crop_window(480, 640, 0, 500, 0.5) == (160, 480, 120, 360)
+    assert sampling.crop_window(480, 640, 500, 500, 0.5) == (0, 640, 0, 480)
+    assert sampling.crop_window(480, 640, 10, 0, 0.5, "patch") == (1, 639, 1, 479)
