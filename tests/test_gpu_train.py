@@ -242,9 +242,8 @@ def test_device_sample_generator_yields_the_reference_tuple():
         load_priors=True, prior_albedos=r(n_img, H, W, 3), prior_irradiances=r(n_img, H, W, 3),
         poses=torch.eye(4).repeat(n_img, 1, 1).to(DEV) + 0.1 * r(n_img, 4, 4))
     focal = .5 * W / math.tan(.5 * math.radians(60))
-    ds.get_focal_matrix = lambda: np.array([[focal, 0, .5 * W], [0, focal, .5 * H], [0, 0, 1]], np.float32)
-    ds.__len__ = lambda: n_img
-    ds = type("DS", (), dict(vars(ds), __len__=lambda self: n_img))()
+    Kmat = np.array([[focal, 0, .5 * W], [0, focal, .5 * H], [0, 0, 1]], np.float32)
+    ds = type("DS", (), dict(vars(ds), __len__=lambda self: n_img, get_focal_matrix=lambda self: Kmat))()
     info, ro, rd, u, v = sampling.sample_batch(ds, 1, 2048, sampling.crop_window(H, W, 0, 10, 0.5))
     assert int(u.min()) >= 20 and int(u.max()) < 60 and int(v.min()) >= 16 and int(v.max()) < 48      # centre crop
     ul, vl = u.long(), v.long()
