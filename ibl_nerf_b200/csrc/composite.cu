@@ -397,6 +397,158 @@ composite_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
   }
 }
 
+// Backward, RAY-RESIDENT variant for the reference layout (C = 18, 3 coarse heads, sigmoid heads) and S % 32 == 0,
+// S <= 256 (the shipped 64 / 192 and the sweep's 128 / 256).  The streaming kernel above re-reads every row from L2 /
+// DRAM in its reverse pass and evaluates every head sigmoid twice; ncu's instruction mix puts it at the MUFU pipe
+// (68 ex2 / rcp per sample: 2 x 17 sigmoids + the alpha exponential) rather than at HBM.  Here the ray's whole
+// [S,18] tile stays in shared memory: pass 1 overwrites each head channel with its ACTIVATION y = sigmoid(x), pass 2
+// (reverse) needs only y and y (1 - y) -- no second global read, no second MUFU pass -- and builds g_raw in place.
+// While pass 2 walks the rows backwards, every row it has streamed out is immediately refilled with the same row of
+// the warp's NEXT ray (cp.async), so the loads of ray r+1 overlap the arithmetic of ray r.
+__global__ void __launch_bounds__(256)
+composite_bwd_resident_kernel(const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays_d,
+                              const float* __restrict__ noise, const float* __restrict__ g_weights,
+                              const float* __restrict__ g_maps, const float* __restrict__ g_srgb, int n, int S,
+                              float* __restrict__ g_raw) {
+  constexpr int C = 18, rowf = ROW * C;           // 576 floats = 144 float4 per row
+  extern __shared__ __align__(16) float sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nrows = S / ROW;
+  float* tile = sm + (size_t)warp * ((size_t)S * C + 3 * S + 32);
+  float* s_alpha = tile + (size_t)S * C;
+  float* s_T = s_alpha + S;
+  float* s_dist = s_T + S;
+  float* s_g = s_dist + S;
+  const int nwarps = blockDim.x >> 5;
+  const int stride = gridDim.x * nwarps;
+  int r = blockIdx.x * nwarps + warp;
+  if (r >= n) return;
+  auto load_row = [&](int64_t rr, int k) {       // row k of ray rr -> tile row k (one commit group)
+    const float* src = raw + ((int64_t)rr * S + (int64_t)k * ROW) * C;
+    float* dst = tile + (size_t)k * rowf;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      const int e = lane + 32 * j;
+      if (j < 4 || e < 144) cp_async16(dst + 4 * e, src + 4 * e);
+    }
+    cp_async_commit();
+  };
+  for (int k = 0; k < nrows; ++k) load_row(r, k);
+  for (; r < n; r += stride) {
+    const float dx = rays_d[3 * r], dy = rays_d[3 * r + 1], dz = rays_d[3 * r + 2];
+    const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
+    const float* zr = z + (int64_t)r * S;
+    cp_async_wait<0>();                            // (rows were issued during the previous ray's reverse pass)
+    __syncwarp();
+    float carry = 1.0f, a_depth = 0.f, a_acc = 0.f, a_irr = 0.f;
+    float a_col[15];
+#pragma unroll
+    for (int c = 0; c < 15; ++c) a_col[c] = 0.f;
+    // ---- pass 1: alpha / T per sample, head activations written back in place, per-ray sums
+    for (int k = 0; k < nrows; ++k) {
+      const int i = k * ROW + lane;
+      const float zi = zr[i];
+      float dist = (i < S - 1) ? (zr[i + 1] - zi) : 1e10f;
+      dist *= dnorm;
+      float* px = tile + (size_t)i * C;
+      float sig = px[0];
+      if (noise != nullptr) sig += noise[(int64_t)r * S + i];
+      RayAlpha ra = row_alpha(sig, dist, true, carry, lane);
+      s_alpha[i] = ra.alpha; s_T[i] = ra.T; s_dist[i] = (sig > 0.f) ? dist : 0.f;
+      a_depth += ra.w * zi; a_acc += ra.w;
+      float y[17];
+#pragma unroll
+      for (int c = 0; c < 17; ++c) { y[c] = sigmoidf_fast(px[1 + c]); px[1 + c] = y[c]; }
+      a_irr += ra.w * y[4];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) a_col[c] += ra.w * y[c];
+#pragma unroll
+      for (int c = 0; c < 12; ++c) a_col[3 + c] += ra.w * y[5 + c];
+    }
+    // ---- combined per-ray gradients wrt the LINEAR maps (same expressions as the streaming kernel)
+    a_depth = warp_sum(a_depth); a_acc = warp_sum(a_acc);
+    if (g_srgb != nullptr) {
+      a_irr = warp_sum(a_irr);
+#pragma unroll
+      for (int c = 0; c < 15; ++c) a_col[c] = warp_sum(a_col[c]);
+    }
+    if (lane < IBLN_MAPS_STRIDE) {
+      float g = g_maps ? g_maps[(int64_t)r * IBLN_MAPS_STRIDE + lane] : 0.f;
+      if (g_srgb != nullptr) {
+        const float gs = g_srgb[(int64_t)r * IBLN_MAPS_STRIDE + lane];
+        const bool colour = (lane == IBLN_MAP_IRR) || (lane >= IBLN_MAP_ALBEDO && lane < IBLN_MAP_COARSE + 9);
+        if (colour) {
+          float lin = (lane == IBLN_MAP_IRR) ? a_irr : 0.f;
+#pragma unroll
+          for (int c = 0; c < 15; ++c) if (lane == IBLN_MAP_ALBEDO + c) lin = a_col[c];
+          g += gs * dsrgbf(lin);
+        } else {
+          g += gs;
+        }
+      }
+      s_g[lane] = g;
+    }
+    __syncwarp();
+    float gdepth = s_g[IBLN_MAP_DEPTH], gacc = s_g[IBLN_MAP_ACC];
+    const float gdisp = s_g[IBLN_MAP_DISP];
+    if (gdisp != 0.f) {
+      const float q = a_depth / a_acc;
+      if (q > 1e-10f) {
+        const float iq2 = 1.0f / (q * q);
+        gdepth += gdisp * (-iq2 / a_acc);
+        gacc += gdisp * (iq2 * a_depth / (a_acc * a_acc));
+      }
+    }
+    float suffix = s_g[IBLN_MAP_TEND] * carry;
+    float gm[17];                                  // d loss / d (linear map) of the 17 head channels, raw-channel order
+#pragma unroll
+    for (int c = 0; c < 3; ++c) gm[c] = s_g[IBLN_MAP_ALBEDO + c];
+    gm[3] = s_g[IBLN_MAP_ROUGH]; gm[4] = s_g[IBLN_MAP_IRR];
+#pragma unroll
+    for (int c = 0; c < 12; ++c) gm[5 + c] = s_g[IBLN_MAP_RAD + c];
+    const int rn = r + stride;
+    // ---- pass 2 (reverse): g_raw rows built in place, streamed out, row refilled with the next ray
+    for (int k = nrows - 1; k >= 0; --k) {
+      const int i = k * ROW + lane;
+      const float zi = zr[i];
+      float* px = tile + (size_t)i * C;
+      const float alpha = s_alpha[i], T = s_T[i], w = alpha * T;
+      float gw = (g_weights ? g_weights[(int64_t)r * S + i] : 0.f) + gdepth * zi + gacc;
+      float go[18];
+#pragma unroll
+      for (int c = 0; c < 17; ++c) {
+        const float y = px[1 + c];
+        if (c >= 5 && c < 8) gw += gm[c] * y;     // radiance composites with LIVE weights (:305-306)
+        go[1 + c] = w * gm[c] * y * (1.f - y);
+      }
+      const float tv = gw * w;
+      float p = tv;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float v = __shfl_down_sync(FULL, p, o);
+        if (lane + o < 32) p += v;
+      }
+      const float excl = p - tv + suffix;
+      suffix += __shfl_sync(FULL, p, 0);
+      const float om = (1.0f - alpha) + 1e-10f;
+      const float galpha = gw * T - excl / om;
+      go[0] = galpha * s_dist[i] * (1.0f - alpha);
+#pragma unroll
+      for (int c = 0; c < 18; ++c) px[c] = go[c];
+      __syncwarp();
+      float4* dst = reinterpret_cast<float4*>(g_raw + ((int64_t)r * S + (int64_t)k * ROW) * C);
+      const float4* srow = reinterpret_cast<const float4*>(tile + (size_t)k * rowf);
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        const int e = lane + 32 * j;
+        if (j < 4 || e < 144) __stcs(dst + e, srow[e]);
+      }
+      __syncwarp();                                // the row has been read out: refill it
+      if (rn < n) load_row(rn, k);
+    }
+  }
+}
+
 // sigma-only depth compositing (normal estimator / raw2outputs_depth): no tile staging needed.
 __global__ void __launch_bounds__(CP_WARPS * 32)
 depth_fwd_kernel(const float* __restrict__ sigma, const float* __restrict__ z, const float* __restrict__ rays_d,
@@ -487,6 +639,21 @@ extern "C" int ibln_composite_bwd(const float* raw, const float* z, const float*
   if (n == 0) return 0;
   if (n < 0 || S < 1 || C < 9 + 3 * nc || C > MAXCH || nc < 0 || nc > 3 || !raw || !z || !rays_d || !g_raw) return IBLN_EINVAL;
   DeviceGuard g(device);
+  if (C == 18 && nc == 3 && sigm == 1 && S % 32 == 0 && S <= 256 && (reinterpret_cast<uintptr_t>(raw) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(g_raw) & 15) == 0) {
+    // ray-resident kernel: [S,18] tile + 3 S floats per warp (5.4 KB at S = 64, 16.1 KB at S = 192)
+    const size_t pw = ((size_t)S * 18 + 3 * (size_t)S + 32) * sizeof(float);
+    int warps = 8;
+    while (warps > 2 && warps * pw > 100 * 1024) warps >>= 1;
+    const size_t smem = warps * pw;
+    int per_sm = (int)((220 * 1024) / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 8) per_sm = 8;
+    IBLN_CUDA(cudaFuncSetAttribute(composite_bwd_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    composite_bwd_resident_kernel<<<comp_grid(n, device, per_sm, warps), warps * 32, smem, (cudaStream_t)stream>>>(
+        raw, z, rays_d, noise, g_weights, g_maps, g_maps_srgb, n, S, g_raw);
+    IBLN_RETURN_LAST();
+  }
   int Sp = (S + 31) & ~31;
   int warps = 8;
   size_t per_warp = (2 * (size_t)ROW * C + 3 * (size_t)Sp + 32) * sizeof(float);
