@@ -65,6 +65,21 @@ __device__ __forceinline__ void row_load_async(float* dst, const float* __restri
   cp_async_commit();
 }
 
+// The 18 channels the kernels read of one staged sample.  FIXED layout (C = 18): 9 float2 loads -- with the 72-byte
+// sample stride the 16 lanes of a half-warp hit 16 distinct 8-byte bank pairs, so each access is conflict-free, while
+// scalar accesses at stride 18 are 2-way bank-conflicted (ncu: 6.7 shared-memory wavefronts per sample in the backward).
+template <bool FIXED>
+__device__ __forceinline__ void load_sample(float (&x)[18], const float* px, int C) {
+  if (FIXED) {
+    const float2* p2 = reinterpret_cast<const float2*>(px);
+#pragma unroll
+    for (int q = 0; q < 9; ++q) { const float2 v = p2[q]; x[2 * q] = v.x; x[2 * q + 1] = v.y; }
+  } else {
+#pragma unroll
+    for (int c = 0; c < 18; ++c) x[c] = c < C ? px[c] : 0.f;
+  }
+}
+
 // FIXED: the reference's channel layout (C = 18, 3 coarse heads, sigmoid radiance) at compile time; FULL: S % 32 == 0
 // (complete rows: no validity predicates, unrolled row copies) -- see composite_bwd_kernel.
 template <bool SIMPLE, bool FIXED, bool FULL>
@@ -128,7 +143,9 @@ composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
       const float zi = valid ? zr[i] : 0.f;
       float dist = (valid && i < S - 1) ? (zr[i + 1] - zi) : 1e10f;
       dist *= dnorm;
-      const float* px = cur + (size_t)(valid ? lane : 0) * C;
+      const float* pxp = cur + (size_t)(valid ? lane : 0) * C;
+      float px[18];
+      load_sample<FIXED>(px, pxp, C);
       float sig = px[0];
       if (noise != nullptr && valid) sig += noise[(int64_t)r * S + i];
       RayAlpha ra = row_alpha(sig, dist, valid, carry, lane);
@@ -266,7 +283,9 @@ composite_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
       const int i = k * ROW + lane;
       const bool valid = FULL ? true : (i < S);
       const float zi = valid ? zr[i] : 0.f;
-      float* px = cur + (size_t)(valid ? lane : 0) * C;
+      float* pxp = cur + (size_t)(valid ? lane : 0) * C;
+      float px[18];
+      load_sample<FIXED>(px, pxp, C);
 
       if (t < nrows) {
         // ---- pass 1
@@ -373,9 +392,15 @@ composite_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
           const float om = (1.0f - alpha) + 1e-10f;
           const float galpha = gw * T - excl / om;
           go[0] = galpha * s_dist[i] * (1.0f - alpha);   // d alpha/d sigma = dist * exp(-sigma dist), 0 where sigma <= 0
+          if (FIXED) {
+            float2* p2 = reinterpret_cast<float2*>(pxp);
 #pragma unroll
-          for (int c = 0; c < 18; ++c) if (c < C) px[c] = go[c];
-          for (int c = 18; c < C; ++c) px[c] = 0.f;
+            for (int q = 0; q < 9; ++q) p2[q] = make_float2(go[2 * q], go[2 * q + 1]);
+          } else {
+#pragma unroll
+            for (int c = 0; c < 18; ++c) if (c < C) pxp[c] = go[c];
+            for (int c = 18; c < C; ++c) pxp[c] = 0.f;
+          }
         }
         __syncwarp();
         const int n_float = FULL ? ROW * C : min(ROW, S - k * ROW) * C;
@@ -398,13 +423,16 @@ composite_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
 }
 
 // Backward, RAY-RESIDENT variant for the reference layout (C = 18, 3 coarse heads, sigmoid heads) and S % 32 == 0,
-// S <= 256 (the shipped 64 / 192 and the sweep's 128 / 256).  The streaming kernel above re-reads every row from L2 /
+// S <= RESIDENT_MAX_S (the coarse pass's 64 samples; at 192 samples the 16 KB tile per warp leaves 12 warps per SM and
+// the streaming kernel is faster: 0.76 vs 0.54 of the HBM copy peak, measured).
+// The streaming kernel above re-reads every row from L2 /
 // DRAM in its reverse pass and evaluates every head sigmoid twice; ncu's instruction mix puts it at the MUFU pipe
 // (68 ex2 / rcp per sample: 2 x 17 sigmoids + the alpha exponential) rather than at HBM.  Here the ray's whole
 // [S,18] tile stays in shared memory: pass 1 overwrites each head channel with its ACTIVATION y = sigmoid(x), pass 2
 // (reverse) needs only y and y (1 - y) -- no second global read, no second MUFU pass -- and builds g_raw in place.
 // While pass 2 walks the rows backwards, every row it has streamed out is immediately refilled with the same row of
 // the warp's NEXT ray (cp.async), so the loads of ray r+1 overlap the arithmetic of ray r.
+constexpr int RESIDENT_MAX_S = 128;
 __global__ void __launch_bounds__(256)
 composite_bwd_resident_kernel(const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays_d,
                               const float* __restrict__ noise, const float* __restrict__ g_weights,
@@ -450,15 +478,23 @@ composite_bwd_resident_kernel(const float* __restrict__ raw, const float* __rest
       const float zi = zr[i];
       float dist = (i < S - 1) ? (zr[i + 1] - zi) : 1e10f;
       dist *= dnorm;
-      float* px = tile + (size_t)i * C;
-      float sig = px[0];
+      // a sample's 18 channels as 9 float2: with the 72-byte sample stride the 16 lanes of a half-warp hit 16 distinct
+      // 8-byte bank pairs, so each access is conflict-free (scalar accesses at stride 18 are 2-way conflicted)
+      float2* px2 = reinterpret_cast<float2*>(tile + (size_t)i * C);
+      float x[18];
+#pragma unroll
+      for (int q = 0; q < 9; ++q) { const float2 v = px2[q]; x[2 * q] = v.x; x[2 * q + 1] = v.y; }
+      float sig = x[0];
       if (noise != nullptr) sig += noise[(int64_t)r * S + i];
       RayAlpha ra = row_alpha(sig, dist, true, carry, lane);
       s_alpha[i] = ra.alpha; s_T[i] = ra.T; s_dist[i] = (sig > 0.f) ? dist : 0.f;
       a_depth += ra.w * zi; a_acc += ra.w;
       float y[17];
 #pragma unroll
-      for (int c = 0; c < 17; ++c) { y[c] = sigmoidf_fast(px[1 + c]); px[1 + c] = y[c]; }
+      for (int c = 0; c < 17; ++c) y[c] = sigmoidf_fast(x[1 + c]);
+      px2[0] = make_float2(x[0], y[0]);
+#pragma unroll
+      for (int q = 1; q < 9; ++q) px2[q] = make_float2(y[2 * q - 1], y[2 * q]);
       a_irr += ra.w * y[4];
 #pragma unroll
       for (int c = 0; c < 3; ++c) a_col[c] += ra.w * y[c];
@@ -511,13 +547,15 @@ composite_bwd_resident_kernel(const float* __restrict__ raw, const float* __rest
     for (int k = nrows - 1; k >= 0; --k) {
       const int i = k * ROW + lane;
       const float zi = zr[i];
-      float* px = tile + (size_t)i * C;
+      float2* px2 = reinterpret_cast<float2*>(tile + (size_t)i * C);
       const float alpha = s_alpha[i], T = s_T[i], w = alpha * T;
       float gw = (g_weights ? g_weights[(int64_t)r * S + i] : 0.f) + gdepth * zi + gacc;
-      float go[18];
+      float yy[18], go[18];
+#pragma unroll
+      for (int q = 0; q < 9; ++q) { const float2 v = px2[q]; yy[2 * q] = v.x; yy[2 * q + 1] = v.y; }
 #pragma unroll
       for (int c = 0; c < 17; ++c) {
-        const float y = px[1 + c];
+        const float y = yy[1 + c];
         if (c >= 5 && c < 8) gw += gm[c] * y;     // radiance composites with LIVE weights (:305-306)
         go[1 + c] = w * gm[c] * y * (1.f - y);
       }
@@ -534,7 +572,7 @@ composite_bwd_resident_kernel(const float* __restrict__ raw, const float* __rest
       const float galpha = gw * T - excl / om;
       go[0] = galpha * s_dist[i] * (1.0f - alpha);
 #pragma unroll
-      for (int c = 0; c < 18; ++c) px[c] = go[c];
+      for (int q = 0; q < 9; ++q) px2[q] = make_float2(go[2 * q], go[2 * q + 1]);
       __syncwarp();
       float4* dst = reinterpret_cast<float4*>(g_raw + ((int64_t)r * S + (int64_t)k * ROW) * C);
       const float4* srow = reinterpret_cast<const float4*>(tile + (size_t)k * rowf);
@@ -639,7 +677,7 @@ extern "C" int ibln_composite_bwd(const float* raw, const float* z, const float*
   if (n == 0) return 0;
   if (n < 0 || S < 1 || C < 9 + 3 * nc || C > MAXCH || nc < 0 || nc > 3 || !raw || !z || !rays_d || !g_raw) return IBLN_EINVAL;
   DeviceGuard g(device);
-  if (C == 18 && nc == 3 && sigm == 1 && S % 32 == 0 && S <= 256 && (reinterpret_cast<uintptr_t>(raw) & 15) == 0 &&
+  if (C == 18 && nc == 3 && sigm == 1 && S % 32 == 0 && S <= RESIDENT_MAX_S && (reinterpret_cast<uintptr_t>(raw) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(g_raw) & 15) == 0) {
     // ray-resident kernel: [S,18] tile + 3 S floats per warp (5.4 KB at S = 64, 16.1 KB at S = 192)
     const size_t pw = ((size_t)S * 18 + 3 * (size_t)S + 32) * sizeof(float);
