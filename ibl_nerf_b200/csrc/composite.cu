@@ -143,9 +143,9 @@ composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
       const float zi = valid ? zr[i] : 0.f;
       float dist = (valid && i < S - 1) ? (zr[i + 1] - zi) : 1e10f;
       dist *= dnorm;
-      const float* pxp = cur + (size_t)(valid ? lane : 0) * C;
-      float px[18];
-      load_sample<FIXED>(px, pxp, C);
+      // (scalar channel reads here: preloading the sample as float2 pairs, which pays off in the backward kernels, made
+      // the forward 15-20 % slower -- it is bound by load latency, not by the shared-memory pipe)
+      const float* px = cur + (size_t)(valid ? lane : 0) * C;
       float sig = px[0];
       if (noise != nullptr && valid) sig += noise[(int64_t)r * S + i];
       RayAlpha ra = row_alpha(sig, dist, valid, carry, lane);
