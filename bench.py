@@ -668,7 +668,7 @@ def main():
                 "dtype": "bf16" if (args.precision or ib.mlp.default_precision()) == "bf16" else "f32",
                 "data": "synthetic rays (seeded), random-init weights of the kitchen architecture",
                 "config": {"workload": WORKLOAD % n,
-                           "n_rand_per_gpu": n, "parallelism": "ray-sharded dp%d, NCCL grad all-reduce (per network, overlapped with the backward)" % world,
+                           "n_rand_per_gpu": n, "parallelism": "ray-sharded dp%d; gradient all-reduce: %s" % (world, ts.allreduce_mode),
                            "route": "fused kernel chain (training.TrainStep, no autograd graph)" if ts.fused else "render_decomp + autograd",
                            "l2": "per-step working set >> 126 MB L2 (no explicit flush)",
                            "step_tflops": world * n * FLOP_PER_RAY_STEP / (ms_step * 1e-3) / 1e12},

@@ -43,6 +43,8 @@ _SIGS = {
     "ibln_depth_to_normal": [c_p, c_int, c_int, c_f, c_f, c_f, c_f, c_p, c_p],
     "ibln_adam_step": [c_p, c_p, c_p, c_p, c_i64, c_f, c_f, c_f, c_f, c_int, c_f],
     "ibln_adam_step_pack": [c_p, c_p, c_p, c_p, c_int, c_f, c_f, c_f, c_f, c_int, c_f, c_p],
+    "ibln_adam_allreduce_step": [c_p, c_p, c_p, c_int, c_p, c_p, c_i64, c_f, c_f, c_f, c_f, c_int, c_f],
+    "ibln_adam_allreduce_step_pack": [c_p, c_p, c_p, c_int, c_p, c_p, c_int, c_f, c_f, c_f, c_f, c_int, c_f, c_p],
     "ibln_zero": [c_p, c_i64],
     "ibln_umma_selftest": [c_p, c_p, c_p, c_int, c_int, c_int],
     "ibln_umma_mn_selftest": [c_p, c_p, c_p, c_int],
@@ -69,7 +71,7 @@ _PLAIN = {  # no device/stream tail
 ABI_VERSION = 4      # include/iblnerf_b200.h: IBLN_ABI_VERSION
 _lib = None
 # kernels launched per entry point (for bench.py's gpu_launches); default 1
-KERNELS_PER_CALL = {"ibln_sgemm_wgrad": 2, "ibln_mlp_pack_weights": 3, "ibln_mlp_bwd": 2, "ibln_adam_step_pack": 2, "ibln_zero": 0}
+KERNELS_PER_CALL = {"ibln_sgemm_wgrad": 2, "ibln_mlp_pack_weights": 3, "ibln_mlp_bwd": 2, "ibln_adam_step_pack": 2, "ibln_adam_allreduce_step_pack": 2, "ibln_zero": 0}
 # bench.py sets this to {} to collect per-entry launch counts, CUDA-event pairs and algorithmic FLOPs;
 # PROFILE_EVENTS (None = every entry) limits the CUDA-event bracketing to the named entry points
 PROFILE = None

@@ -960,3 +960,23 @@ extern "C" int ibln_adam_step_pack(float* param, const float* grad, float* exp_a
   }
   return launch_pack_flat(pf, n_nets, (cudaStream_t)stream);
 }
+
+// The data-parallel form of the above: the gradient all-reduce is fused into the Adam kernel (ibln_adam_allreduce_step:
+// NVSwitch multimem.ld_reduce on the symmetric gradient buffer, or P2P loads), then the same single re-pack launch.
+extern "C" int ibln_adam_allreduce_step_pack(float* param, const float* grad_multicast, const float* const* peer_grads_host,
+                                             int world, float* exp_avg, float* exp_avg_sq, int n_nets, float lr, float beta1,
+                                             float beta2, float eps, int step, float grad_scale, void* const* packed_host,
+                                             int device, void* stream) {
+  if (n_nets < 1 || n_nets > 4 || !packed_host) return IBLN_EINVAL;
+  int rc = ibln_adam_allreduce_step(param, grad_multicast, peer_grads_host, world, exp_avg, exp_avg_sq, (int64_t)n_nets * FLAT_TOTAL,
+                                    lr, beta1, beta2, eps, step, grad_scale, device, stream);
+  if (rc != 0) return rc;
+  DeviceGuard guard(device);
+  PackFlat pf;
+  for (int i = 0; i < 4; ++i) {
+    pf.flat[i] = i < n_nets ? param + (size_t)i * FLAT_TOTAL : nullptr;
+    pf.packed[i] = i < n_nets ? (uint8_t*)packed_host[i] : nullptr;
+    if (i < n_nets && (!pf.packed[i] || (reinterpret_cast<uintptr_t>(pf.packed[i]) & 15))) return IBLN_EINVAL;
+  }
+  return launch_pack_flat(pf, n_nets, (cudaStream_t)stream);
+}

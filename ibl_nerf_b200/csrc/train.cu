@@ -114,9 +114,80 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   }
 }
 
+// Gradient all-reduce FUSED into the optimizer (data-parallel training, one process per GPU): the flat gradient buffer
+// of every rank lives in symmetric memory (torch.distributed._symmetric_memory: the same virtual layout on all ranks,
+// mapped into every peer and bound to one NVSwitch multicast object).  Each rank then runs this ONE kernel:
+//   MC = true : g = multimem.ld_reduce.add.v4.f32 [multicast address]  -- the switch sums the ranks' values in flight
+//               (NVLS), the GPU receives the reduced gradient once, 16 bytes per load
+//   MC = false: g = sum over the ranks' peer-mapped pointers (plain P2P loads over NVLink), for fabrics without multicast
+// and applies Adam to its replica -- no NCCL launch, no reduced-gradient round trip through HBM.  The caller brackets it
+// with the symmetric-memory barrier (all gradients written / all ranks done reading).
+struct PeerGrads { const float* p[8]; int world; };
+template <bool MC>
+__global__ void __launch_bounds__(256)
+adam_allreduce_kernel(float* __restrict__ p, const float* g_mc, PeerGrads peers, float* __restrict__ m, float* __restrict__ v,
+                      int64_t n, float step_size, float b1, float b2, float eps, float inv_sqrt_bc2, float grad_scale) {
+  const int64_t i4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i4 >= n) return;
+  float4 gg;
+  if (MC) {
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(gg.x), "=f"(gg.y), "=f"(gg.z), "=f"(gg.w) : "l"(g_mc + i4) : "memory");
+  } else {
+    gg = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < peers.world; ++r) {
+      float4 t;
+      asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "l"(peers.p[r] + i4) : "memory");
+      gg.x += t.x; gg.y += t.y; gg.z += t.z; gg.w += t.w;
+    }
+  }
+  float4 pp = *reinterpret_cast<float4*>(p + i4);
+  float4 mm = *reinterpret_cast<float4*>(m + i4), vv = *reinterpret_cast<float4*>(v + i4);
+  float* P = &pp.x; float* G = &gg.x; float* M = &mm.x; float* V = &vv.x;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float gr = G[k] * grad_scale;
+    M[k] = __fmaf_rn(b1, M[k], (1.0f - b1) * gr);
+    V[k] = __fmaf_rn(b2, V[k], (1.0f - b2) * gr * gr);
+    const float denom = sqrtf(V[k]) * inv_sqrt_bc2 + eps;
+    P[k] -= step_size * (M[k] / denom);
+  }
+  *reinterpret_cast<float4*>(p + i4) = pp;
+  *reinterpret_cast<float4*>(m + i4) = mm;
+  *reinterpret_cast<float4*>(v + i4) = vv;
+}
+
 }  // namespace ibln
 
 using namespace ibln;
+
+extern "C" int ibln_adam_allreduce_step(float* param, const float* grad_multicast, const float* const* peer_grads_host, int world,
+                                        float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2,
+                                        float eps, int step, float grad_scale, int device, void* stream) {
+  if (n == 0) return 0;
+  if (n < 0 || (n & 3) || !param || !exp_avg || !exp_avg_sq || step < 1 || world < 1 || world > 8) return IBLN_EINVAL;
+  if (!grad_multicast && !peer_grads_host) return IBLN_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad_multicast) | reinterpret_cast<uintptr_t>(exp_avg) |
+       reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15) return IBLN_EINVAL;
+  DeviceGuard g(device);
+  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+  const float step_size = (float)((double)lr / bc1), inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+  const unsigned blocks = (unsigned)((n / 4 + 255) / 256);
+  PeerGrads peers;
+  peers.world = world;
+  for (int r = 0; r < 8; ++r) {
+    peers.p[r] = (peer_grads_host && r < world) ? peer_grads_host[r] : nullptr;
+    if (!grad_multicast && r < world && (!peers.p[r] || (reinterpret_cast<uintptr_t>(peers.p[r]) & 15))) return IBLN_EINVAL;
+  }
+  if (grad_multicast)
+    adam_allreduce_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(param, grad_multicast, peers, exp_avg, exp_avg_sq, n, step_size,
+                                                                          beta1, beta2, eps, inv_sqrt_bc2, grad_scale);
+  else
+    adam_allreduce_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(param, nullptr, peers, exp_avg, exp_avg_sq, n, step_size,
+                                                                           beta1, beta2, eps, inv_sqrt_bc2, grad_scale);
+  IBLN_RETURN_LAST();
+}
 
 extern "C" int ibln_image_losses(const float* maps_srgb, const float* shade_srgb, const float* rgb, const float* rgb_1,
                                  const float* rgb_2, const float* rgb_3, const float* prior_albedo, int n, float w_radiance,

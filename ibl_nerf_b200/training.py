@@ -146,6 +146,42 @@ def phase_b_loss_fused(result, targets):
     return phase_loss_fused(result, targets, "full")
 
 
+class SymmetricGradients:
+    """The flat gradient buffer of every rank in symmetric memory (torch.distributed._symmetric_memory: same layout on
+    all ranks, peer-mapped, bound to an NVSwitch multicast object when the fabric has one), so the gradient all-reduce can be
+    FUSED into the Adam kernel (ibln_adam_allreduce_step: multimem.ld_reduce through the switch, or P2P loads).
+    `create` is collective; it returns None on every rank unless it worked on all of them."""
+
+    def __init__(self, buf, handle, world):
+        self.buf, self.handle, self.world = buf, handle, world
+        self.multicast = int(handle.multicast_ptr) if handle.has_multicast_support(buf.device.type, buf.device.index) else 0
+        self.peers = [int(x) for x in handle.buffer_ptrs]
+        self.mode = "multimem" if self.multicast else "p2p"
+
+    @staticmethod
+    def create(n_floats, device, world):
+        import os
+        ok, buf, handle = 1, None, None
+        if os.environ.get("IBLN_FUSED_ALLREDUCE", "1") == "0" or world > 8:
+            ok = 0
+        else:
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                buf = symm_mem.empty(n_floats, dtype=torch.float32, device=device)
+                handle = symm_mem.rendezvous(buf, dist.group.WORLD)
+                buf.zero_()
+            except Exception:
+                ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            return None
+        return SymmetricGradients(buf, handle, world)
+
+    def barrier(self, channel):
+        self.handle.barrier(channel=channel)
+
+
 class FlatParameters:
     """All parameters of the given IBLNeRF modules re-homed into ONE flat fp32 buffer (state-dict order, network
     after network) with a matching flat gradient buffer: the tensor-core backward accumulates straight into it
@@ -154,12 +190,14 @@ class FlatParameters:
     so state_dict() and any torch optimizer still work.  The loss accumulator of the fused step lives in the same
     allocation right behind the gradients, so one memset clears both."""
 
-    def __init__(self, nets):
+    def __init__(self, nets, symmetric=None):
         dev = next(nets[0].parameters()).device
         self.nets = list(nets)
         self.n = FLAT_PARAMS * len(self.nets)
         self.param = torch.empty(self.n, dtype=torch.float32, device=dev)
-        self._grad_and_loss = torch.zeros(self.n + 4, dtype=torch.float32, device=dev)
+        self.symmetric = symmetric         # SymmetricGradients or None
+        self._grad_and_loss = symmetric.buf if symmetric is not None else torch.zeros(self.n + 4, dtype=torch.float32, device=dev)
+        assert self._grad_and_loss.numel() == self.n + 4
         self.grad = self._grad_and_loss[:self.n]
         self.loss = self._grad_and_loss[self.n:self.n + 1]
         self.exp_avg = torch.zeros(self.n, dtype=torch.float32, device=dev)
@@ -184,13 +222,23 @@ class FlatParameters:
     def zero_grad(self):
         call("ibln_zero", self.param.device, ptr(self._grad_and_loss), self._grad_and_loss.numel() * 4)
 
-    def adam_step(self, lr, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0):
-        """Adam over both networks + re-pack of their bf16 weight images (2 launches)."""
+    def adam_step(self, lr, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0, fused_allreduce=False):
+        """Adam over both networks + re-pack of their bf16 weight images (2 launches).  fused_allreduce: the gradient is
+        the sum over all ranks' symmetric buffers, read inside the Adam kernel (no separate collective)."""
         self.step_count += 1
         packed = [net.packed_buffer() for net in self.nets]
         arr = (ctypes.c_void_p * len(packed))(*[ctypes.c_void_p(t.data_ptr()) for t in packed])
-        call("ibln_adam_step_pack", self.param.device, ptr(self.param), ptr(self.grad), ptr(self.exp_avg), ptr(self.exp_avg_sq),
-             len(self.nets), float(lr), float(betas[0]), float(betas[1]), float(eps), self.step_count, float(grad_scale), arr)
+        if fused_allreduce:
+            sym = self.symmetric
+            peers = (ctypes.c_void_p * sym.world)(*[ctypes.c_void_p(x) for x in sym.peers])
+            sym.barrier(0)          # every rank's backward has finished writing its gradients (and they are visible)
+            call("ibln_adam_allreduce_step_pack", self.param.device, ptr(self.param),
+                 ctypes.c_void_p(sym.multicast) if sym.multicast else None, peers, sym.world, ptr(self.exp_avg), ptr(self.exp_avg_sq),
+                 len(self.nets), float(lr), float(betas[0]), float(betas[1]), float(eps), self.step_count, float(grad_scale), arr)
+            sym.barrier(1)          # every rank has read my gradients: the next step may clear them
+        else:
+            call("ibln_adam_step_pack", self.param.device, ptr(self.param), ptr(self.grad), ptr(self.exp_avg), ptr(self.exp_avg_sq),
+                 len(self.nets), float(lr), float(betas[0]), float(betas[1]), float(eps), self.step_count, float(grad_scale), arr)
         for net in self.nets:
             net.mark_packed()
 
@@ -254,8 +302,12 @@ class TrainStep:
         # tensor-core path: flat parameter / gradient buffers + fused loss and Adam kernels; exact fp32 path: torch
         self.fused_tail = (precision or mlp_default_precision()) == "bf16" and self.device.type == "cuda"
         self.fused = bool(fused) and self.fused_tail
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
         if self.fused_tail:
-            self.flat = FlatParameters([self.coarse, self.fine])
+            # N > 1: gradients in symmetric memory -> the all-reduce is fused into the Adam kernel (NVSwitch multimem or P2P);
+            # if symmetric memory is unavailable, NCCL all-reduces per network, overlapped with the backward
+            sym = SymmetricGradients.create(2 * FLAT_PARAMS + 4, self.device, self.world) if (self.world > 1 and self.fused) else None
+            self.flat = FlatParameters([self.coarse, self.fine], symmetric=sym)
             self.opt = None
         else:
             self.flat = None
@@ -267,7 +319,6 @@ class TrainStep:
         self.kw = kitchen_render_kwargs(self.coarse, self.fine, lut, near, far)
         self.chunk = chunk
         self.micro_batch = micro_batch      # rays per forward/backward pass (bounds the activation stash: ~1.7 GB per 1024 rays)
-        self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.overlap_allreduce = overlap_allreduce
         self._bufs = {}
         self._pending = []
@@ -436,15 +487,27 @@ class TrainStep:
             if last:
                 self._grad_ready(0)
         self._finish_allreduce()
-        self.flat.adam_step(self.lr, grad_scale=1.0 / self.world)
+        self.flat.adam_step(self.lr, grad_scale=1.0 / self.world, fused_allreduce=self._fused_allreduce())
         return self.flat.loss[0]
 
     # ------------------------------------------------------------------ collectives
-    def _grad_ready(self, idx):
-        """The backward of network `idx` has been enqueued: start its gradient all-reduce.  NCCL runs it on its own
-        stream behind an event of the compute stream, so the fine network's half overlaps the coarse network's
-        backward; the compute stream only waits for it right before Adam."""
+    def _fused_allreduce(self):
+        return self.world > 1 and self.flat is not None and self.flat.symmetric is not None
+
+    @property
+    def allreduce_mode(self):
         if self.world == 1:
+            return "none"
+        if self._fused_allreduce():
+            return "fused into the Adam kernel (%s over symmetric memory)" % self.flat.symmetric.mode
+        return "NCCL all-reduce per network, overlapped with the backward" if (self.fused and self.overlap_allreduce) else "NCCL all-reduce"
+
+    def _grad_ready(self, idx):
+        """The backward of network `idx` has been enqueued: start its gradient all-reduce (NCCL route only; with symmetric
+        gradients the reduction happens inside the Adam kernel).  NCCL runs it on its own stream behind an event of the
+        compute stream, so the fine network's half overlaps the coarse network's backward; the compute stream only
+        waits for it right before Adam."""
+        if self.world == 1 or self._fused_allreduce():
             return
         if self.overlap_allreduce:
             self._pending.append(dist.all_reduce(self.flat.net_grad(idx), op=dist.ReduceOp.SUM, async_op=True))

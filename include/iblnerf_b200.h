@@ -240,6 +240,20 @@ int ibln_adam_step(float* param, const float* grad, float* exp_avg, float* exp_a
 int ibln_adam_step_pack(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int n_nets, float lr,
                         float beta1, float beta2, float eps, int step, float grad_scale, void* const* packed_host,
                         int device, void* stream);
+/* Data-parallel training: gradient all-reduce FUSED into the Adam kernel over NVLink / NVSwitch peer memory.
+ * Every rank keeps its flat gradient buffer in symmetric memory (torch.distributed._symmetric_memory); this ONE kernel reads
+ * the sum over all ranks -- grad_multicast: the buffer's NVSwitch multicast address, read with multimem.ld_reduce.add.v4.f32
+ * (the switch adds the ranks' values in flight); or, when grad_multicast is NULL, peer_grads_host: HOST array of `world`
+ * peer-mapped device pointers (own buffer included) summed with P2P loads -- scales it by grad_scale (1/world) and applies
+ * Adam to this rank's replica.  n % 4 == 0, world <= 8.  The caller brackets it with the symmetric-memory barrier
+ * (all gradients written before / all ranks done reading after).  Replaces ncclAllReduce + ibln_adam_step. */
+int ibln_adam_allreduce_step(float* param, const float* grad_multicast, const float* const* peer_grads_host, int world,
+                             float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2, float eps,
+                             int step, float grad_scale, int device, void* stream);
+/* ... followed by the bf16 re-pack of the n_nets networks that live back to back in `param` (see ibln_adam_step_pack). */
+int ibln_adam_allreduce_step_pack(float* param, const float* grad_multicast, const float* const* peer_grads_host, int world,
+                                  float* exp_avg, float* exp_avg_sq, int n_nets, float lr, float beta1, float beta2,
+                                  float eps, int step, float grad_scale, void* const* packed_host, int device, void* stream);
 /* cudaMemsetAsync(buf, 0, bytes) on the given stream (gradient / loss accumulators of the fused training step). */
 int ibln_zero(void* buf, int64_t bytes, int device, void* stream);
 
