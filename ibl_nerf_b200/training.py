@@ -154,14 +154,14 @@ class SymmetricGradients:
 
     def __init__(self, buf, handle, world):
         self.buf, self.handle, self.world = buf, handle, world
-        self.multicast = int(handle.multicast_ptr) if handle.has_multicast_support(buf.device.type, buf.device.index) else 0
+        self.multicast = int(handle.multicast_ptr or 0)        # 0 when the fabric has no multicast object (then: P2P loads)
         self.peers = [int(x) for x in handle.buffer_ptrs]
         self.mode = "multimem" if self.multicast else "p2p"
 
     @staticmethod
     def create(n_floats, device, world):
         import os
-        ok, buf, handle = 1, None, None
+        ok, sym = 1, None
         if os.environ.get("IBLN_FUSED_ALLREDUCE", "1") == "0" or world > 8:
             ok = 0
         else:
@@ -170,13 +170,14 @@ class SymmetricGradients:
                 buf = symm_mem.empty(n_floats, dtype=torch.float32, device=device)
                 handle = symm_mem.rendezvous(buf, dist.group.WORLD)
                 buf.zero_()
+                sym = SymmetricGradients(buf, handle, world)
+                if os.environ.get("IBLN_FUSED_ALLREDUCE") == "p2p":
+                    sym.multicast, sym.mode = 0, "p2p"
             except Exception:
                 ok = 0
         flag = torch.tensor([ok], dtype=torch.int32, device=device)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if int(flag.item()) == 0:
-            return None
-        return SymmetricGradients(buf, handle, world)
+        return sym if int(flag.item()) == 1 else None
 
     def barrier(self, channel):
         self.handle.barrier(channel=channel)
