@@ -440,15 +440,18 @@ def dp_parity(dev, rank, world, lut):
     K, c2w = pinhole(H, W), camera_poses(dev, 8)[1]
     shard = training.render_image_sharded(H, W, K, c2w, kw, chunk=1 << 16)
     bad = []
-    if rank == 0:
-        from ibl_nerf_b200.helper import get_rays
-        ro, rd = get_rays(H, W, K, c2w)
-        with torch.no_grad():
-            full = render_decomp(H, W, K, chunk=1 << 16, rays=(ro.reshape(-1, 3), rd.reshape(-1, 3)), approximate_radiance=True, **kw)
-        for k in sorted(full):
-            a, b = shard[k].reshape(full[k].shape), full[k]
-            if not (torch.equal(torch.isnan(a), torch.isnan(b)) and torch.equal(a.nan_to_num(), b.nan_to_num())):
-                bad.append(k)
+    if rank == 0:          # (no collective inside this block: an exception here must not desynchronise the ranks)
+        try:
+            from ibl_nerf_b200.helper import get_rays
+            ro, rd = get_rays(H, W, K, c2w)
+            with torch.no_grad():
+                full = render_decomp(H, W, K, chunk=1 << 16, rays=(ro.reshape(-1, 3), rd.reshape(-1, 3)), approximate_radiance=True, **kw)
+            for k in sorted(shard):
+                a, b = shard[k].reshape(full[k].shape), full[k]
+                if not (torch.equal(torch.isnan(a), torch.isnan(b)) and torch.equal(a.nan_to_num(), b.nan_to_num())):
+                    bad.append(k)
+        except Exception as e:
+            bad.append("%s: %s" % (type(e).__name__, str(e)[:120]))
     flag = torch.tensor([float(len(bad))], device=dev)
     dist.broadcast(flag, 0)
     out["render"] = {"maps": len(shard), "mismatching_maps": bad if rank == 0 else int(flag.item()), "ok": flag.item() == 0}
@@ -491,7 +494,9 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"       # the version banner goes to stdout, which carries the ONE JSON line
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a desynchronised collective must end the run in minutes, not after NCCL's default 10-minute watchdog
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=150))
     _lib.lib()
     if rank == 0:
         ClockSampler.start_global(local)
