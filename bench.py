@@ -13,6 +13,7 @@ measured outside the headline's timed region with its own clock sample:
   strong     BASELINE configs[3]: one step over 65 536 rays in total, sharded over the N ranks (strong scaling)
   render     BASELINE configs[2]: 8 full 480x640 test renders (all maps), image rows sharded over the N ranks + one gather
   micro      BASELINE configs[4] (N = 1): composite fwd / bwd and sample_pdf vs the HBM roofline at S = 64 / 192 / 512
+  allreduce_routes (N > 1) same-box A/B of the gradient all-reduce routes (fused multimem / fused P2P / NCCL)
   dp_parity  (N > 1) correctness of the sharded paths against rank 0 computing the whole batch / image on one GPU
 """
 import argparse
@@ -331,10 +332,29 @@ def render_record(ts, dev, rank, world, local, barrier, H=480, W=640, n_poses=8)
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     clocks = sampler.stop() if sampler else None
     rays = n_poses * H * W
+    # the collective alone (ranks aligned by a barrier first): the in-loop figure above also contains the wait for the
+    # slowest rank's tile
+    pure = 0.0
+    if world > 1:
+        keys = sorted(out)
+        per = (H * W + world - 1) // world
+        res = {k: out[k][:per] for k in keys}
+        buf, _ = training.pack_maps(res, keys, per)
+        dst = torch.empty(world * per, buf.shape[1], dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(dst, buf)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(5):
+            dist.all_gather_into_tensor(dst, buf)
+        g1.record()
+        torch.cuda.synchronize()
+        pure = g0.elapsed_time(g1) / 5
     return {"config": "BASELINE configs[2]: %d synthetic poses, %dx%d, fov 60, perturb 0, all %d output maps, rows sharded over %d rank(s)"
                       % (n_poses, H, W, len(out), world),
             "metric": "render_rays_per_sec", "value": rays / ms.item() * 1e3, "unit": UNIT, "ms_per_image": ms.item() / n_poses,
-            "gather_ms_per_image": (sum(a.elapsed_time(b) for a, b in gather_ms) / n_poses) if gather_ms else 0.0,
+            "gather_ms_per_image": pure, "gather_mb_per_rank": (buf.numel() * 4 / 1e6) if world > 1 else 0.0,
+            "gather_incl_wait_for_slowest_rank_ms_per_image": (sum(a.elapsed_time(b) for a, b in gather_ms) / n_poses) if gather_ms else 0.0,
             "collectives_per_image": (len(gather_ms) / n_poses) if world > 1 else 0,
             "tflops": rays * FLOP_PER_RAY_RENDER / ms.item() / 1e9, "clocks": clocks}
 
@@ -470,7 +490,7 @@ def main():
     ap.add_argument("--precision", default=None, choices=[None, "bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the PyTorch-eager-on-GPU run of the oracle (N=1 only)")
-    ap.add_argument("--skip", default="", help="comma list of sub-records to skip: phases,strong,render,micro,dp_parity")
+    ap.add_argument("--skip", default="", help="comma list of sub-records to skip: phases,strong,render,micro,allreduce,dp_parity")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     skip = set(x for x in args.skip.split(",") if x)
@@ -642,6 +662,25 @@ def main():
         ts._bufs.clear()
         torch.cuda.empty_cache()
         extra["micro"] = micro_record(dev, local, peaks.get("hbm_gbs", 6650.0))
+    if "allreduce" not in skip and world > 1:
+        # same-box A/B of the gradient all-reduce routes of the data-parallel step, interleaved twice
+        routes = {}
+        steppers = {}
+        for route in ("multimem", "p2p", "nccl"):
+            try:
+                t2 = training.TrainStep(dev, lut, precision=args.precision, allreduce=route)
+                steppers[route] = t2
+            except Exception as e:
+                routes[route] = {"error": "%s: %s" % (type(e).__name__, str(e)[:120])}
+        for rep in range(2):
+            for route, t2 in steppers.items():
+                ms, _ = sub_timed(lambda: t2.step(o_d, d_d, tg_d), max(5, args.steps), warm=2)
+                routes.setdefault(route, {"mode": t2.allreduce_mode, "ms_per_step": []})["ms_per_step"].append(round(ms, 4))
+        routes["note"] = ("multimem / p2p: all-reduce fused into the Adam kernel over symmetric memory (a route the fabric does not "
+                          "support falls back and says so in `mode`); nccl: one NCCL all-reduce per network, overlapped with the backward")
+        extra["allreduce_routes"] = routes
+        del steppers
+        torch.cuda.empty_cache()
     if "dp_parity" not in skip and world > 1:
         try:
             extra["dp_parity"] = dp_parity(dev, rank, world, lut)

@@ -159,10 +159,14 @@ class SymmetricGradients:
         self.mode = "multimem" if self.multicast else "p2p"
 
     @staticmethod
-    def create(n_floats, device, world):
+    def create(n_floats, device, world, route="auto"):
+        """route: "auto" (multimem when the fabric has a multicast object, else P2P loads), "multimem", "p2p", or "nccl"
+        (no symmetric memory: plain NCCL all-reduce); IBLN_FUSED_ALLREDUCE = 0 / p2p overrides "auto"."""
         import os
         ok, sym = 1, None
-        if os.environ.get("IBLN_FUSED_ALLREDUCE", "1") == "0" or world > 8:
+        if route == "auto":
+            route = {"0": "nccl", "p2p": "p2p"}.get(os.environ.get("IBLN_FUSED_ALLREDUCE", "1"), "auto")
+        if route == "nccl" or world > 8:
             ok = 0
         else:
             try:
@@ -171,8 +175,10 @@ class SymmetricGradients:
                 handle = symm_mem.rendezvous(buf, dist.group.WORLD)
                 buf.zero_()
                 sym = SymmetricGradients(buf, handle, world)
-                if os.environ.get("IBLN_FUSED_ALLREDUCE") == "p2p":
+                if route == "p2p":
                     sym.multicast, sym.mode = 0, "p2p"
+                elif route == "multimem" and not sym.multicast:
+                    ok = 0
             except Exception:
                 ok = 0
         flag = torch.tensor([ok], dtype=torch.int32, device=device)
@@ -288,7 +294,7 @@ class TrainStep:
 
     def __init__(self, device, lut, near=0.5, far=8.0, lr=5e-4, seed=0, precision=None, approximate_radiance=True,
                  chunk=1 << 20, micro_batch=8192, phase=None, lrate_decay=500, betas=None, prior_irradiance_mean=0.5,
-                 fused=True, overlap_allreduce=True):
+                 fused=True, overlap_allreduce=True, allreduce="auto"):
         torch.manual_seed(seed)
         self.device = torch.device(device)
         self.coarse = IBLNeRF(**KITCHEN_ARCH).to(device)
@@ -307,7 +313,8 @@ class TrainStep:
         if self.fused_tail:
             # N > 1: gradients in symmetric memory -> the all-reduce is fused into the Adam kernel (NVSwitch multimem or P2P);
             # if symmetric memory is unavailable, NCCL all-reduces per network, overlapped with the backward
-            sym = SymmetricGradients.create(2 * FLAT_PARAMS + 4, self.device, self.world) if (self.world > 1 and self.fused) else None
+            sym = (SymmetricGradients.create(2 * FLAT_PARAMS + 4, self.device, self.world, allreduce)
+                   if (self.world > 1 and self.fused) else None)
             self.flat = FlatParameters([self.coarse, self.fine], symmetric=sym)
             self.opt = None
         else:
