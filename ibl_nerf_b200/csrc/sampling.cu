@@ -332,163 +332,6 @@ sample_pdf_small_kernel(const float* __restrict__ bins, int64_t bins_stride, con
   }
 }
 
-// ---------------------------------------------------------------- lane = ray variant (nbins <= 64)
-// ncu on the warp-per-ray kernels above: l1tex (shared-memory pipe) 88 % busy, 115 wavefronts per ray -- every sample's
-// record / guide / probe access is a RANDOM shared-memory gather across the warp (2.5 wavefronts per quarter-warp of
-// 16-byte loads, balls into banks).  Here a warp owns 32 rays and LANE l OWNS RAY l: every table is laid out
-// [entry][lane], so whatever entry a lane needs it reads from bank `lane` -- each gather is one conflict-free wavefront,
-// 16 instead of ~40 wavefronts per ray for the interpolation operands.  The row-major global rows reach that layout
-// through a [ray][33]-padded staging tile (coalesced global rows in, column reads at a fixed entry out: both
-// conflict-free), one 32-entry chunk at a time, software-pipelined with the next chunk's global loads in registers.
-// The CDF is accumulated unnormalised per lane and scaled afterwards (same 1e-7-level rounding differences from the
-// reference's pdf-then-cumsum as the warp-scan kernels); indices follow searchsorted(right=True) exactly for that CDF.
-constexpr int LR_WARPS = 7;                       // 7 x 28.3 KB of shared memory per CTA, one CTA per SM
-constexpr int LR_STAGE = 32 * 33;
-constexpr int LR_FLOATS = 2 * LR_STAGE + 64 * 32 + 64 * 32 + 32 * 32;
-constexpr int LR_CELLS = 64;
-
-__global__ void __launch_bounds__(LR_WARPS * 32)
-sample_pdf_laneray_kernel(const float* __restrict__ bins, int64_t bins_stride, const float* __restrict__ weights,
-                          int64_t w_stride, const float* __restrict__ u, int n, int nbins, int nsamp,
-                          float* __restrict__ samples) {
-  extern __shared__ __align__(16) float sm[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* base = sm + (size_t)warp * LR_FLOATS;
-  float* cdfT = base + 2 * LR_STAGE;             // [entry][lane]
-  float* binsT = cdfT + 64 * 32;                 // [entry][lane]
-  uint32_t* guide = reinterpret_cast<uint32_t*>(binsT + 64 * 32);     // [cell pair][lane]: E[2k] | E[2k+1] << 8 | E[2k+2] << 16
-  const int nw = nbins - 1;
-  const int n_wch = (nw + 31) >> 5, n_bch = (nbins + 31) >> 5, n_uch = (nsamp + 31) >> 5;
-  const int n_ch = n_wch + n_bch + n_uch;
-  const int groups = (n + 31) >> 5;
-  const int gstride = gridDim.x * LR_WARPS;
-  int g = blockIdx.x * LR_WARPS + warp;
-  if (g >= groups) return;
-
-  // chunk c of group gg -> registers (row r of the chunk = ray 32 gg + r, 32 consecutive columns: one coalesced request)
-  auto fetch = [&](int gg, int c, float (&reg)[32]) {
-    const float* src; int64_t ld; int col0, ncols;
-    if (c < n_wch) { src = weights; ld = w_stride; col0 = 32 * c; ncols = nw; }
-    else if (c < n_wch + n_bch) { src = bins; ld = bins_stride; col0 = 32 * (c - n_wch); ncols = nbins; }
-    else { src = u; ld = nsamp; col0 = 32 * (c - n_wch - n_bch); ncols = nsamp; }
-    const int col = col0 + lane;
-    const bool col_ok = col < ncols;
-#pragma unroll
-    for (int r = 0; r < 32; ++r) {
-      const int64_t ray = (int64_t)gg * 32 + r;
-      reg[r] = (col_ok && ray < n) ? __ldg(src + ray * ld + col) : 0.f;
-    }
-  };
-  auto put = [&](float* st, const float (&reg)[32]) {
-#pragma unroll
-    for (int r = 0; r < 32; ++r) st[r * 33 + lane] = reg[r];      // bank (r + lane) % 32: conflict-free
-  };
-
-  float reg[32];
-  fetch(g, 0, reg);
-  put(base, reg);
-  __syncwarp();
-  int it = 0;
-  for (; g < groups; g += gstride) {
-    float run = 0.f;                                // unnormalised prefix of (w + 1e-5)
-    for (int c = 0; c < n_ch; ++c, ++it) {
-      float* cur = base + (it & 1) * LR_STAGE;
-      float* nxt = base + ((it + 1) & 1) * LR_STAGE;
-      // next chunk of the stream (this group's, or chunk 0 of the warp's next group) in flight while this one is processed
-      const bool more = c + 1 < n_ch;
-      const int gn = more ? g : g + gstride;
-      const bool have_next = gn < groups;
-      if (have_next) fetch(gn, more ? c + 1 : 0, reg);
-      const float* mine = cur + lane * 33;          // my ray's row of the chunk: bank (lane + e) % 32 at a fixed e
-      if (c < n_wch) {
-        // ---- weights -> unnormalised CDF column
-        if (c == 0) cdfT[lane] = 0.f;
-        const int e0 = 32 * c, cnt = min(32, nw - e0);
-        for (int e = 0; e < cnt; ++e) {
-          run += mine[e] + 1e-5f;
-          cdfT[(e0 + e + 1) * 32 + lane] = run;
-        }
-      } else if (c < n_wch + n_bch) {
-        const int e0 = 32 * (c - n_wch), cnt = min(32, nbins - e0);
-        for (int e = 0; e < cnt; ++e) binsT[(e0 + e) * 32 + lane] = mine[e];
-        if (c == n_wch + n_bch - 1) {
-          // ---- normalise the CDF, histogram its entries over 64 value cells, exclusive prefix -> guide
-          const float inv_total = __fdividef(1.0f, run);
-#pragma unroll
-          for (int k = 0; k < 16; ++k) guide[k * 32 + lane] = 0u;
-          guide[lane] = 1u;                           // entry 0 (cdf = 0) sits in cell 0
-          for (int e = 1; e < nbins; ++e) {
-            const float cv = cdfT[e * 32 + lane] * inv_total;
-            cdfT[e * 32 + lane] = cv;
-            const int cell = min(LR_CELLS - 1, (int)__fmul_rn(cv, (float)LR_CELLS));
-            guide[(cell >> 2) * 32 + lane] += 1u << (8 * (cell & 3));
-          }
-          uint32_t h[16];
-#pragma unroll
-          for (int k = 0; k < 16; ++k) h[k] = guide[k * 32 + lane];
-          uint32_t t = 0;
-#pragma unroll
-          for (int k = 0; k < 16; ++k) {
-            const uint32_t incl = h[k] * 0x01010101u + t * 0x01010101u;      // inclusive byte prefix (counts <= 64: no carries)
-            guide[(2 * k) * 32 + lane] = t | ((incl & 0xffffu) << 8);         // E[4k], E[4k+1], E[4k+2]
-            guide[(2 * k + 1) * 32 + lane] = incl >> 8;                       // E[4k+2], E[4k+3], E[4k+4]
-            t = incl >> 24;
-          }
-        }
-      } else {
-        // ---- 32 sample slots of my ray, four independent lookups in flight
-        const int j0 = 32 * (c - n_wch - n_bch), cnt = min(32, nsamp - j0);
-        float* mrow = cur + lane * 33;
-        const int top = nbins - 1;
-        for (int jb = 0; jb < cnt; jb += 4) {
-          float uu[4]; int lo[4], hi[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uu[q] = mrow[min(jb + q, 31)];
-            const int m = min(LR_CELLS - 1, max(0, (int)__fmul_rn(uu[q], (float)LR_CELLS)));
-            const uint32_t wd = guide[(m >> 1) * 32 + lane] >> (8 * (m & 1));
-            lo[q] = (int)(wd & 0xffu); hi[q] = (int)((wd >> 8) & 0xffu);
-          }
-          for (;;) {
-            bool open = false;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) open |= lo[q] < hi[q];
-            if (!__any_sync(FULL, open)) break;
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              if (lo[q] < hi[q]) {
-                const int mid = (lo[q] + hi[q]) >> 1;
-                if (cdfT[mid * 32 + lane] <= uu[q]) lo[q] = mid + 1; else hi[q] = mid;
-              }
-          }
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int below = max(lo[q] - 1, 0), above = min(lo[q], top);
-            const float cb = cdfT[below * 32 + lane], ca = cdfT[above * 32 + lane];
-            const float bb = binsT[below * 32 + lane], ba = binsT[above * 32 + lane];
-            float den = __fsub_rn(ca, cb);
-            if (den < 1e-5f) den = 1.0f;
-            const float tq = __fdividef(__fsub_rn(uu[q], cb), den);
-            if (jb + q < 32) mrow[jb + q] = __fadd_rn(bb, __fmul_rn(tq, __fsub_rn(ba, bb)));
-          }
-        }
-        __syncwarp();
-        // ---- the finished chunk leaves row by row (coalesced 128-byte stores)
-        const int col = j0 + lane;
-        if (col < nsamp) {
-#pragma unroll
-          for (int r = 0; r < 32; ++r) {
-            const int64_t ray = (int64_t)g * 32 + r;
-            if (ray < n) __stcs(samples + ray * nsamp + col, cur[r * 33 + lane]);
-          }
-        }
-      }
-      if (have_next) put(nxt, reg);
-      __syncwarp();
-    }
-  }
-}
-
 // ---------------------------------------------------------------- merge / sort
 __device__ __forceinline__ void warp_bitonic_sort(float* s, int npad, int lane) {
   for (int k = 2; k <= npad; k <<= 1) {
@@ -589,15 +432,6 @@ static int launch_sample_pdf(const float* bins, int64_t bs, const float* w, int6
   size_t smem = (size_t)SP_WARPS * ray_smem_floats(nbins) * sizeof(float);
   if (smem > 200 * 1024) return IBLN_EINVAL;
   int grid = ray_grid(n, device, SP_WARPS, 16);
-  if (cdf == nullptr && nbins <= 64 && n >= 4096) {   // lane = ray kernel (weights -> samples; every shipped configuration)
-    const size_t lsm = (size_t)LR_WARPS * LR_FLOATS * sizeof(float);
-    IBLN_CUDA(cudaFuncSetAttribute(sample_pdf_laneray_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm));
-    const int groups = (n + 31) / 32;
-    int lgrid = (groups + LR_WARPS - 1) / LR_WARPS;
-    if (lgrid > num_sms(device)) lgrid = num_sms(device);
-    sample_pdf_laneray_kernel<<<lgrid, LR_WARPS * 32, lsm, (cudaStream_t)stream>>>(bins, bs, w, ws, u, n, nbins, nsamp, samples);
-    IBLN_RETURN_LAST();
-  }
   if (nbins <= 64 && nsamp <= 128) {     // register-prefetching kernel (N_samples = 64, N_importance = 128 of every shipped config)
     if (cdf != nullptr)
       sample_pdf_small_kernel<true, 0, 0><<<grid, SP_WARPS * 32, smem, (cudaStream_t)stream>>>(bins, bs, w, ws, cdf, u, n, nbins, nsamp, inds, samples);
