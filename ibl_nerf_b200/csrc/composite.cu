@@ -433,7 +433,7 @@ composite_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
 // While pass 2 walks the rows backwards, every row it has streamed out is immediately refilled with the same row of
 // the warp's NEXT ray (cp.async), so the loads of ray r+1 overlap the arithmetic of ray r.
 constexpr int RESIDENT_MAX_S = 128;
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(192, 6)
 composite_bwd_resident_kernel(const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays_d,
                               const float* __restrict__ noise, const float* __restrict__ g_weights,
                               const float* __restrict__ g_maps, const float* __restrict__ g_srgb, int n, int S,
@@ -442,11 +442,12 @@ composite_bwd_resident_kernel(const float* __restrict__ raw, const float* __rest
   extern __shared__ __align__(16) float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nrows = S / ROW;
-  float* tile = sm + (size_t)warp * ((size_t)S * C + 3 * S + 32);
+  float* tile = sm + (size_t)warp * ((size_t)S * C + 4 * S + 32);
   float* s_alpha = tile + (size_t)S * C;
   float* s_T = s_alpha + S;
   float* s_dist = s_T + S;
-  float* s_g = s_dist + S;
+  float* s_z = s_dist + S;
+  float* s_g = s_z + S;
   const int nwarps = blockDim.x >> 5;
   const int stride = gridDim.x * nwarps;
   int r = blockIdx.x * nwarps + warp;
@@ -473,10 +474,16 @@ composite_bwd_resident_kernel(const float* __restrict__ raw, const float* __rest
 #pragma unroll
     for (int c = 0; c < 15; ++c) a_col[c] = 0.f;
     // ---- pass 1: alpha / T per sample, head activations written back in place, per-ray sums
+    float z_cur = zr[lane];
     for (int k = 0; k < nrows; ++k) {
       const int i = k * ROW + lane;
-      const float zi = zr[i];
-      float dist = (i < S - 1) ? (zr[i + 1] - zi) : 1e10f;
+      const float zi = z_cur;
+      if (k + 1 < nrows) z_cur = zr[i + ROW];      // next row's depth: one global load per row, issued a row ahead
+      float z_up = __shfl_down_sync(FULL, zi, 1);  // z[i + 1]: the neighbour lane's, or the next row's first
+      const float z_first_next = __shfl_sync(FULL, z_cur, 0);
+      if (lane == 31) z_up = z_first_next;
+      s_z[i] = zi;
+      float dist = (i < S - 1) ? (z_up - zi) : 1e10f;
       dist *= dnorm;
       // a sample's 18 channels as 9 float2: with the 72-byte sample stride the 16 lanes of a half-warp hit 16 distinct
       // 8-byte bank pairs, so each access is conflict-free (scalar accesses at stride 18 are 2-way conflicted)
@@ -546,7 +553,7 @@ composite_bwd_resident_kernel(const float* __restrict__ raw, const float* __rest
     // ---- pass 2 (reverse): g_raw rows built in place, streamed out, row refilled with the next ray
     for (int k = nrows - 1; k >= 0; --k) {
       const int i = k * ROW + lane;
-      const float zi = zr[i];
+      const float zi = s_z[i];
       float2* px2 = reinterpret_cast<float2*>(tile + (size_t)i * C);
       const float alpha = s_alpha[i], T = s_T[i], w = alpha * T;
       float gw = (g_weights ? g_weights[(int64_t)r * S + i] : 0.f) + gdepth * zi + gacc;
@@ -679,14 +686,14 @@ extern "C" int ibln_composite_bwd(const float* raw, const float* z, const float*
   DeviceGuard g(device);
   if (C == 18 && nc == 3 && sigm == 1 && S % 32 == 0 && S <= RESIDENT_MAX_S && (reinterpret_cast<uintptr_t>(raw) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(g_raw) & 15) == 0) {
-    // ray-resident kernel: [S,18] tile + 3 S floats per warp (5.4 KB at S = 64, 16.1 KB at S = 192)
-    const size_t pw = ((size_t)S * 18 + 3 * (size_t)S + 32) * sizeof(float);
-    int warps = 8;
+    // ray-resident kernel: [S,18] tile + 4 S floats per warp (5.6 KB at S = 64)
+    const size_t pw = ((size_t)S * 18 + 4 * (size_t)S + 32) * sizeof(float);
+    int warps = 6;                                   // 6 CTAs of 6 warps per SM at S = 64 (36 warps, 56 registers)
     while (warps > 2 && warps * pw > 100 * 1024) warps >>= 1;
     const size_t smem = warps * pw;
-    int per_sm = (int)((220 * 1024) / (smem + 1024));
+    int per_sm = (int)((224 * 1024) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > 8) per_sm = 8;
+    if (per_sm > 6) per_sm = 6;
     IBLN_CUDA(cudaFuncSetAttribute(composite_bwd_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     composite_bwd_resident_kernel<<<comp_grid(n, device, per_sm, warps), warps * 32, smem, (cudaStream_t)stream>>>(
         raw, z, rays_d, noise, g_weights, g_maps, g_maps_srgb, n, S, g_raw);
