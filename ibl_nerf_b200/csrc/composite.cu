@@ -230,11 +230,12 @@ composite_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
   const int rowf = ROW * C;
   const int nrows = (S + ROW - 1) / ROW;
   const int Sp = nrows * ROW;
-  float* buf = sm + (size_t)warp * (2 * rowf + 3 * Sp + 32);
+  float* buf = sm + (size_t)warp * (2 * rowf + 4 * Sp + 32);
   float* s_alpha = buf + 2 * rowf;
   float* s_T = s_alpha + Sp;
   float* s_dist = s_T + Sp;
-  float* s_g = s_dist + Sp;     // 24 combined per-ray gradients
+  float* s_z = s_dist + Sp;     // the ray's depths: pass 2 re-reads them from here, not from global memory
+  float* s_g = s_z + Sp;        // 24 combined per-ray gradients
   const bool vec_ok = (((int64_t)S * C) % 4 == 0) && ((reinterpret_cast<uintptr_t>(raw) & 15) == 0) &&
                       ((reinterpret_cast<uintptr_t>(g_raw) & 15) == 0);
   const int nwarps = blockDim.x >> 5;
@@ -282,13 +283,14 @@ composite_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
       const int k = t < nrows ? t : 2 * nrows - 1 - t;
       const int i = k * ROW + lane;
       const bool valid = FULL ? true : (i < S);
-      const float zi = valid ? zr[i] : 0.f;
+      const float zi = t < nrows ? (valid ? zr[i] : 0.f) : s_z[i];
       float* pxp = cur + (size_t)(valid ? lane : 0) * C;
       float px[18];
       load_sample<FIXED>(px, pxp, C);
 
       if (t < nrows) {
         // ---- pass 1
+        s_z[i] = zi;
         float dist = (valid && i < S - 1) ? (zr[i + 1] - zi) : 1e10f;
         dist *= dnorm;
         float sig = px[0];
@@ -409,10 +411,10 @@ composite_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
 #pragma unroll
           for (int j = 0; j < 5; ++j) {
             const int e = lane + 32 * j;
-            if (j < 4 || e < 144) reinterpret_cast<float4*>(dst)[e] = reinterpret_cast<float4*>(cur)[e];
-          }
+            if (j < 4 || e < 144) __stcs(reinterpret_cast<float4*>(dst) + e, reinterpret_cast<float4*>(cur)[e]);   // streaming: keep the rows
+          }                                                                                                     // pass 2 re-reads in L2
         } else if (vec_ok) {
-          for (int e = lane; e < (n_float >> 2); e += 32) reinterpret_cast<float4*>(dst)[e] = reinterpret_cast<float4*>(cur)[e];
+          for (int e = lane; e < (n_float >> 2); e += 32) __stcs(reinterpret_cast<float4*>(dst) + e, reinterpret_cast<float4*>(cur)[e]);
         } else {
           for (int e = lane; e < n_float; e += 32) dst[e] = cur[e];
         }
@@ -701,7 +703,7 @@ extern "C" int ibln_composite_bwd(const float* raw, const float* z, const float*
   }
   int Sp = (S + 31) & ~31;
   int warps = 8;
-  size_t per_warp = (2 * (size_t)ROW * C + 3 * (size_t)Sp + 32) * sizeof(float);
+  size_t per_warp = (2 * (size_t)ROW * C + 4 * (size_t)Sp + 32) * sizeof(float);
   while (warps > 1 && warps * per_warp > 200 * 1024) warps >>= 1;
   size_t smem = warps * per_warp;
   if (smem > 220 * 1024) return IBLN_EINVAL;
