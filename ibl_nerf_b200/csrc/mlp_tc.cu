@@ -210,7 +210,10 @@ __device__ __forceinline__ void drain(const EpiCtx& c, Heads& hd, int sv_blk, in
 // Rank 0 issues the MMAs; tcgen05.commit multicasts stage-free / accumulator-ready to both CTAs; rank 1's
 // otherwise idle warp 1 relays "my half of the stage has landed" to the leader; the epilogue warps of both CTAs
 // arrive on the leader's act_ready barrier.
-template <bool SIGMA_ONLY, bool STASH>
+// NO_AF: the albedo | irradiance feature step (step 8) is skipped -- the reflected-ray march (raw2outputs_simple,
+// ibl_nerf_renderer.py:38-68) reads only sigma and the four radiance heads, so 65 536 of the 795 776 MACs per point are
+// dead there; output channels 1..3 and 5 then hold the head biases.
+template <bool SIGMA_ONLY, bool STASH, bool NO_AF = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) mlp_fwd_kernel(const __grid_constant__ FwdParams prm) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
@@ -249,6 +252,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) mlp_fw
       uint32_t phase = 0;
       for (long long r = 0; r < rounds; ++r) {
         for (int s = 0; s < n_steps; ++s) {
+          if (NO_AF && s == 8) continue;
           const Step st = step_at(s);
           const int nkb = st.aux_first + st.kb_act + st.aux_last;
           const int halves = st.n == 256 ? 2 : 1;      // my N/2 weight rows of a K-block = 128 or 64 rows of 128 B
@@ -282,6 +286,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) mlp_fw
         int tl_n = 0;
         for (long long r = 0; r < rounds; ++r) {
           for (int s = 0; s < n_steps; ++s) {
+            if (NO_AF && s == 8) continue;
             const Step st = step_at(s);
             const int nkb = st.aux_first + st.kb_act + st.aux_last;
             const uint32_t idesc = st.n == 256 ? IDESC256 : IDESC128;
@@ -440,6 +445,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) mlp_fw
 
 #pragma unroll 1
       for (int s = 0; s < n_steps; ++s) {
+        if (NO_AF && s == 8) continue;
+        const int sn = (NO_AF && s == 7) ? 9 : s + 1;      // the step that follows this one
         mbar_wait(&acc_ready[slot], acc_phase);
         acc_phase ^= 1;
         tc_fence_after();
@@ -449,11 +456,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) mlp_fw
         // prefetch the next step's constants into registers (consumed after the drain)
         float2 nb = make_float2(0.f, 0.f);
         float4 nh0 = make_float4(0.f, 0.f, 0.f, 0.f), nh1 = nh0;
-        if (s + 1 < n_steps) {
-          nb = __ldg(bias_src(s + 1));
-          if (has_heads(s + 1)) {
-            const float4* src = heads_src(s + 1);
-            const int n4 = heads_n4(s + 1);
+        if (sn < n_steps) {
+          nb = __ldg(bias_src(sn));
+          if (has_heads(sn)) {
+            const float4* src = heads_src(sn);
+            const int n4 = heads_n4(sn);
             if (gtid < n4) nh0 = __ldg(src + gtid);
             if (gtid + 128 < n4) nh1 = __ldg(src + gtid + 128);
           }
@@ -475,12 +482,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) mlp_fw
           case 12: drain<K_ADD2, STASH, 0, 4>(c, hd, SV_ADDF + 4, 11); break;
           default: drain<K_RELU_ACT, STASH, 0, 8>(c, hd, SV_H(s), s); break;
         }
-        if (s + 1 < n_steps) {
+        if (sn < n_steps) {
           if (STASH) fence_proxy_async();
           named_bar_sync(1 + slot, 128);     // everyone is done reading this step's bias row / head table; tile complete
           reinterpret_cast<float2*>(bias_s)[gtid] = nb;
-          if (has_heads(s + 1)) {
-            const int n4 = heads_n4(s + 1);
+          if (has_heads(sn)) {
+            const int n4 = heads_n4(sn);
             if (gtid < n4) reinterpret_cast<float4*>(aux)[gtid] = nh0;
             if (gtid + 128 < n4) reinterpret_cast<float4*>(aux)[gtid + 128] = nh1;
           }
@@ -694,7 +701,8 @@ extern "C" int ibln_mlp_fwd(const void* packed, int mode, const float* pts, cons
   if (!packed || !out || !rays_d || n_rays < 0 || n_samples < 1 || mode < 0 || mode > 2) return IBLN_EINVAL;
   if (mode == 0 && !pts) return IBLN_EINVAL;
   if (mode != 0 && (!rays_o || !z)) return IBLN_EINVAL;
-  if (mode == 2 && !sigma_only) return IBLN_EINVAL;
+  if (sigma_only < 0 || sigma_only > 2) return IBLN_EINVAL;
+  if (mode == 2 && sigma_only != 1) return IBLN_EINVAL;
   if (saved && sigma_only) return IBLN_EINVAL;
   if (saved && (reinterpret_cast<uintptr_t>(saved) & 15) != 0) return IBLN_EINVAL;
   if ((reinterpret_cast<uintptr_t>(packed) & 15) != 0) return IBLN_EINVAL;
@@ -717,7 +725,8 @@ extern "C" int ibln_mlp_fwd(const void* packed, int mode, const float* pts, cons
     kern<<<(unsigned)grid, N_THREADS, SMEM_REQUEST, (cudaStream_t)stream>>>(prm);
     return (int)cudaGetLastError();
   };
-  if (sigma_only) return launch(mlp_fwd_kernel<true, false>);
+  if (sigma_only == 1) return launch(mlp_fwd_kernel<true, false>);
+  if (sigma_only == 2) return launch(mlp_fwd_kernel<false, false, true>);
   if (saved) return launch(mlp_fwd_kernel<false, true>);
   return launch(mlp_fwd_kernel<false, false>);
 }

@@ -16,6 +16,7 @@ from ._lib import call, f32c, ptr
 
 # algorithmic FLOP per point evaluation (unpadded GEMMs)
 FLOP_FULL, FLOP_SIGMA = 1591552, 982528
+FLOP_REFLECTED = FLOP_FULL - 2 * 256 * 256      # reflected-ray queries skip the albedo | irradiance feature layer
 
 
 FLAT_PARAMS = sum(o * i + o for _, o, i in mlp.PARAM_ORDER)      # 798 994
@@ -215,14 +216,17 @@ class IBLNeRF(nn.Module):
         out = mlp._MLPFp32.apply(flags, x_pos, x_dir, *self.ordered_params())
         return out.reshape(n, s, -1)
 
-    def query_rays(self, rays_o, rays_d, z, sigma_only=False):
-        """Ray-march query: points o + d z generated inside the kernel (bf16 path)."""
+    def query_rays(self, rays_o, rays_d, z, sigma_only=False, radiance_only=False):
+        """Ray-march query: points o + d z generated inside the kernel (bf16 path).  radiance_only (no-grad queries of the
+        reflected ray, whose consumer raw2outputs_simple reads sigma + the radiance heads only): the albedo / irradiance
+        feature layer is skipped, channels 1..3 and 5 of the result are NOT meaningful."""
         n, s = z.shape
         if self.effective_precision() == "bf16" and not self._grad_needed():
             o, d, zz = f32c(rays_o.detach()), f32c(rays_d.detach()), f32c(z.detach())
             out = torch.empty(n * s, 1 if sigma_only else 18, dtype=torch.float32, device=zz.device)
+            sel = 1 if sigma_only else (2 if radiance_only else 0)
             call("ibln_mlp_fwd", zz.device, ptr(self.packed_weights()), 1, None, ptr(o), ptr(d), ptr(zz), n, s, 0.0,
-                 int(sigma_only), ptr(out), None, flops=n * s * (FLOP_SIGMA if sigma_only else FLOP_FULL))
+                 sel, ptr(out), None, flops=n * s * (FLOP_SIGMA if sigma_only else (FLOP_REFLECTED if radiance_only else FLOP_FULL)))
             return out.reshape(n, s, -1)
         if self._tc_grad_ok() and not sigma_only:
             out = _MLPTc.apply(self, 1, None, f32c(rays_o.detach()), f32c(rays_d.detach()), f32c(z.detach()), n, s,

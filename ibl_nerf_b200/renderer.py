@@ -257,7 +257,7 @@ def raw2outputs(rays_o, rays_d, z_vals, z_vals_constant, network_query_fn, netwo
             reflected_dirs = rays_d - 2 * torch.sum(target_normal_map * rays_d, -1, keepdim=True) * target_normal_map
         with torch.no_grad():                                                                  # :440-448
             if _fused(network_query_fn, network_fn):
-                reflected_ray_raw = network_fn.query_rays(x_surface, reflected_dirs, z_vals_constant)
+                reflected_ray_raw = network_fn.query_rays(x_surface, reflected_dirs, z_vals_constant, radiance_only=True)
             else:
                 reflected_pts = x_surface[..., None, :] + reflected_dirs[..., None, :] * z_vals_constant[..., :, None]
                 reflected_ray_raw = network_query_fn(reflected_pts, reflected_dirs, network_fn)

@@ -29,7 +29,7 @@ import torch.distributed as dist
 from . import _lib, ops
 from ._lib import call, ptr
 from .mlp import default_precision as mlp_default_precision, get_embedder
-from .model import FLAT_PARAMS, FLOP_FULL, FLOP_SIGMA, IBLNeRF, NetworkQuery
+from .model import FLAT_PARAMS, FLOP_FULL, FLOP_REFLECTED, FLOP_SIGMA, IBLNeRF, NetworkQuery
 from .renderer import render_decomp
 
 KITCHEN_ARCH = dict(D=8, W=256, input_ch=63, input_ch_views=27, skips=[4], coarse_radiance_number=3,
@@ -432,8 +432,8 @@ class TrainStep:
         call("ibln_depth_fwd", dev, ptr(b.sig4), ptr(pb.z), ptr(d), 4, n, s, ptr(b.depths4), None, None)
         call("ibln_normal_eps_finish", dev, ptr(d), ptr(b.depths4), n, eps, ptr(pb.normal), ptr(pb.refl), ptr(o), ptr(pb.maps),
              ops.MAPS_STRIDE, ptr(pb.xs))
-        call("ibln_mlp_fwd", dev, ptr(packed), 1, None, ptr(pb.xs), ptr(pb.refl), ptr(zc), n, 64, 0.0, 0, ptr(b.refl_raw), None,
-             flops=n * 64 * FLOP_FULL)
+        call("ibln_mlp_fwd", dev, ptr(packed), 1, None, ptr(pb.xs), ptr(pb.refl), ptr(zc), n, 64, 0.0, 2, ptr(b.refl_raw), None,
+             flops=n * 64 * FLOP_REFLECTED)       # sigma + radiance heads only (raw2outputs_simple)
         call("ibln_composite_simple_fwd", dev, ptr(b.refl_raw), ptr(zc), ptr(pb.refl), n, 64, 18, 3, 1, ptr(pb.pre), None)
         call("ibln_shade_fwd_maps", dev, ptr(d), ptr(pb.normal), ptr(pb.maps), ptr(b.near), ptr(b.far), ptr(pb.pre), 4,
              ptr(self.lut), self.lut.shape[1], self.lut.shape[2], 0, 1, n, ptr(pb.shade), ptr(pb.shade_srgb))

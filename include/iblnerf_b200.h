@@ -193,8 +193,10 @@ int64_t ibln_mlp_packed_bytes(void);
 int ibln_mlp_pack_weights(const float* const* params_host, void* packed, int device, void* stream);
 
 /* Fused encode + MLP forward.  mode per the table above; o,d [n_rays,3]; z [n_rays,S];
- * pts nullable (mode 0: [n_rays*S,3]).  sigma_only: out [P] (P = n_rays*S, or 4*n_rays*S in mode 2),
- * else out [P,18] fp32 straight from the fp32 accumulators.  saved (nullable): activation stash for
+ * pts nullable (mode 0: [n_rays*S,3]).  sigma_only = 1: out [P] (P = n_rays*S, or 4*n_rays*S in mode 2),
+ * else out [P,18] fp32 straight from the fp32 accumulators; sigma_only = 2: [P,18] WITHOUT the albedo / irradiance
+ * feature layer (channels 1..3 and 5 hold the head biases): the reflected-ray march of ibl_nerf_renderer.py:440-448 reads
+ * only sigma and the radiance heads (raw2outputs_simple, :38-68).  saved (nullable): activation stash for
  * the backward pass, >= ibln_mlp_saved_bytes(P) bytes. */
 int64_t ibln_mlp_saved_bytes(int64_t n_pts);
 int ibln_mlp_fwd(const void* packed, int mode, const float* pts, const float* rays_o, const float* rays_d,
