@@ -68,17 +68,23 @@ try:
 except _lib.IblnError as e:
     import traceback
     tb = traceback.format_exc()
-    assert "render_decomp" in tb and "stratified_z" in tb, tb
+    if %(mode)r == "train" and os.environ.get("IBLN_DEVICE_SAMPLER", "1") != "0":
+        # the first kernel call of train.py is then the device sample generator the launcher installed
+        assert "sample_generator_single_image" in tb and "sample_training_rays" in tb, tb
+    else:
+        assert "render_decomp" in tb and "stratified_z" in tb, tb
 print("REACHED_RENDER")
 '''
 
 
-@pytest.mark.parametrize("mode", ["train", "test"])
-def test_launcher_main_drives_the_reference_up_to_the_first_render(tmp_path, mode):
+@pytest.mark.parametrize("mode,device_sampler", [("train", "1"), ("train", "0"), ("test", "1")])
+def test_launcher_main_drives_the_reference_up_to_the_first_render(tmp_path, mode, device_sampler):
     """launcher.main == the drivers' own __main__ (device, expname from the config name, export_basedir), dataset
     load, log dir, the reference's create_IBLNeRF with this package's types substituted, sample generator: everything up
-    to the first kernel call runs here; on CPU tensors the product path then refuses (no fallback)."""
+    to the first kernel call runs here; on CPU tensors the product path then refuses (no fallback).  With the device
+    sample generator (default) train.py's first kernel call is ibln_sample_rays, with IBLN_DEVICE_SAMPLER=0 the render."""
     os.makedirs(tmp_path / "logs" / "IBL-NeRF", exist_ok=True)
     code = DRY % dict(root=ROOT, ref=REF, mode=mode, data=str(tmp_path / "kitchen"), logs=str(tmp_path / "logs"))
-    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600,
+                         env=dict(os.environ, IBLN_DEVICE_SAMPLER=device_sampler))
     assert "REACHED_RENDER" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
