@@ -243,14 +243,18 @@ composite_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
   int r = blockIdx.x * nwarps + warp;
   if (r >= n) return;
   // flat task stream per ray: t in [0, 2*nrows): row(t) = t < nrows ? t : 2*nrows-1-t
-  auto load_row = [&](float* dst, int64_t rr, int kk) {
+  // L2 policy: a row read by pass 1 is read once more by pass 2 (keep it: evict_last), after which it is dead
+  // (evict_first).  Without the hints the reverse pass of long rays misses L2 (ncu at S = 512: DRAM reads 1.64 x raw).
+  const uint64_t pol_keep = l2_evict_last_policy(), pol_drop = l2_evict_first_policy();
+  auto load_row = [&](float* dst, int64_t rr, int kk, bool second) {
     if (FIXED && FULL) {          // 32 samples x 18 channels = 144 float4 per row: 4.5 per lane, fully unrolled
       const float* src = raw + ((int64_t)rr * S + (int64_t)kk * ROW) * 18;
       if (vec_ok) {
+        const uint64_t pol = second ? pol_drop : pol_keep;
 #pragma unroll
         for (int j = 0; j < 5; ++j) {
           const int e = lane + 32 * j;
-          if (j < 4 || e < 144) cp_async16(dst + 4 * e, src + 4 * e);
+          if (j < 4 || e < 144) cp_async16_hint(dst + 4 * e, src + 4 * e, pol);
         }
         cp_async_commit();
         return;
@@ -258,7 +262,7 @@ composite_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
     }
     row_load_async(dst, raw, rr, kk, S, C, lane, vec_ok);
   };
-  load_row(buf, r, 0);
+  load_row(buf, r, 0, false);
   int it = 0;
   for (; r < n; r += stride) {
     const float dx = rays_d[3 * r], dy = rays_d[3 * r + 1], dz = rays_d[3 * r + 2];
@@ -277,7 +281,7 @@ composite_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
       const bool more = t + 1 < 2 * nrows;
       const int rn = more ? r : r + stride;
       const int tn = more ? t + 1 : 0;
-      if (rn < n) { load_row(nxt, rn, tn < nrows ? tn : 2 * nrows - 1 - tn); cp_async_wait<1>(); }
+      if (rn < n) { load_row(nxt, rn, tn < nrows ? tn : 2 * nrows - 1 - tn, tn >= nrows); cp_async_wait<1>(); }
       else cp_async_wait<0>();
       __syncwarp();
       const int k = t < nrows ? t : 2 * nrows - 1 - t;
