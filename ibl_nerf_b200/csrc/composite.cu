@@ -600,6 +600,225 @@ composite_bwd_resident_kernel(const float* __restrict__ raw, const float* __rest
   }
 }
 
+// Backward, CTA-PER-RAY variant for long rays (reference layout, S % 32 == 0, S > RESIDENT_MAX_S: the fine pass's 192
+// samples and the sweep's 256 / 512).  A warp cannot keep such a ray resident (36 KB at S = 512 would leave 4 warps per SM),
+// and the streaming kernel re-reads every row in its reverse pass -- from DRAM once the rays in flight exceed L2 (ncu at
+// S = 512: DRAM reads 1.64 x raw, 0.61 of the HBM copy peak).  Here ONE CTA of W warps owns the ray: its [S,18] tile is
+// resident in shared memory, warp w owns rows w, w + W, ... in both passes (so the tile rows stay warp-private and a
+// streamed-out row is refilled with the same row of the CTA's next ray right away), and the two scans are split into a
+// row-local shuffle scan + a carry over the row totals exchanged through shared memory:
+//   T_i      = (prod_{rows before} rowprod) * (exclusive product inside the row)        -- same order as the warp kernels
+//   sum_{k>i} gw_k w_k = (exclusive suffix inside the row) + sum_{rows after} rowsum + g_Tend T_end
+// Like the ray-resident warp kernel it evaluates every head sigmoid once and never reads raw twice.
+template <int W>
+__global__ void __launch_bounds__(W * 32, W == 8 ? 4 : (W == 6 ? 6 : 8))       // 32 / 36 / 32 warps per SM
+composite_bwd_cta_kernel(const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays_d,
+                         const float* __restrict__ noise, const float* __restrict__ g_weights,
+                         const float* __restrict__ g_maps, const float* __restrict__ g_srgb, int n, int S,
+                         float* __restrict__ g_raw) {
+  constexpr int C = 18, rowf = ROW * C;
+  extern __shared__ __align__(16) float sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nrows = S / ROW;
+  float* tile = sm;                               // [S][18]
+  float* s_alpha = tile + (size_t)S * C;          // [S] each
+  float* s_T = s_alpha + S;                       // pass 1a: exclusive product inside the row; pass 1b on: T
+  float* s_dist = s_T + S;
+  float* s_z = s_dist + S;
+  float* s_suf = s_z + S;                         // exclusive suffix of gw * w inside the row
+  float* s_gw = s_suf + S;
+  float* s_rowprod = s_gw + S;                    // [nrows]
+  float* s_rowsum = s_rowprod + nrows;            // [nrows]
+  float* s_red = s_rowsum + nrows;                // [W][20] per-warp partial sums
+  float* s_g = s_red + W * 20;                    // [32] combined per-ray gradients
+  auto load_row = [&](int64_t rr, int k) {
+    const float* src = raw + ((int64_t)rr * S + (int64_t)k * ROW) * C;
+    float* dst = tile + (size_t)k * rowf;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      const int e = lane + 32 * j;
+      if (j < 4 || e < 144) cp_async16(dst + 4 * e, src + 4 * e);
+    }
+  };
+  int r = blockIdx.x;
+  if (r >= n) return;
+  for (int k = warp; k < nrows; k += W) load_row(r, k);
+  cp_async_commit();
+  for (; r < n; r += gridDim.x) {
+    const float dx = rays_d[3 * r], dy = rays_d[3 * r + 1], dz = rays_d[3 * r + 2];
+    const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
+    const float* zr = z + (int64_t)r * S;
+    cp_async_wait<0>();
+    __syncwarp();                                  // my rows have landed (rows are warp-private)
+    // ---- pass 1a: alpha, row-local exclusive transmittance product, activations in place
+    for (int k = warp; k < nrows; k += W) {
+      const int i = k * ROW + lane;
+      const float zi = zr[i];
+      float dist = (i < S - 1) ? (zr[i + 1] - zi) : 1e10f;
+      dist *= dnorm;
+      float2* px2 = reinterpret_cast<float2*>(tile + (size_t)i * C);
+      float x[18];
+#pragma unroll
+      for (int q = 0; q < 9; ++q) { const float2 v = px2[q]; x[2 * q] = v.x; x[2 * q + 1] = v.y; }
+      float sig = x[0];
+      if (noise != nullptr) sig += noise[(int64_t)r * S + i];
+      const float alpha = 1.0f - expf(-fmaxf(sig, 0.f) * dist);
+      const float om = (1.0f - alpha) + 1e-10f;
+      float pr = om;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float v = __shfl_up_sync(FULL, pr, o);
+        if (lane >= o) pr *= v;
+      }
+      const float excl = __shfl_up_sync(FULL, pr, 1);
+      s_alpha[i] = alpha; s_T[i] = lane == 0 ? 1.0f : excl; s_dist[i] = (sig > 0.f) ? dist : 0.f; s_z[i] = zi;
+      if (lane == 31) s_rowprod[k] = pr;
+      float y[17];
+#pragma unroll
+      for (int c = 0; c < 17; ++c) y[c] = sigmoidf_fast(x[1 + c]);
+      px2[0] = make_float2(x[0], y[0]);
+#pragma unroll
+      for (int q = 1; q < 9; ++q) px2[q] = make_float2(y[2 * q - 1], y[2 * q]);
+    }
+    __syncthreads();
+    // ---- pass 1b: carries across rows -> T, weights, per-ray sums
+    float a_depth = 0.f, a_acc = 0.f, a_irr = 0.f;
+    float a_col[15];
+#pragma unroll
+    for (int c = 0; c < 15; ++c) a_col[c] = 0.f;
+    {
+      float carry = 1.0f;
+      int kk = 0;
+      for (int k = warp; k < nrows; k += W) {
+        for (; kk < k; ++kk) carry *= s_rowprod[kk];         // same multiplication order as the sequential warp kernels
+        const int i = k * ROW + lane;
+        const float T = carry * s_T[i];
+        s_T[i] = T;
+        const float w = s_alpha[i] * T;
+        a_depth += w * s_z[i]; a_acc += w;
+        if (g_srgb != nullptr) {
+          const float2* px2 = reinterpret_cast<const float2*>(tile + (size_t)i * C);
+          float yy[18];
+#pragma unroll
+          for (int q = 0; q < 9; ++q) { const float2 v = px2[q]; yy[2 * q] = v.x; yy[2 * q + 1] = v.y; }
+          a_irr += w * yy[5];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) a_col[c] += w * yy[1 + c];
+#pragma unroll
+          for (int c = 0; c < 12; ++c) a_col[3 + c] += w * yy[6 + c];
+        }
+      }
+    }
+    a_depth = warp_sum(a_depth); a_acc = warp_sum(a_acc);
+    if (g_srgb != nullptr) {
+      a_irr = warp_sum(a_irr);
+#pragma unroll
+      for (int c = 0; c < 15; ++c) a_col[c] = warp_sum(a_col[c]);
+    }
+    if (lane == 0) {
+      float* rd = s_red + warp * 20;
+      rd[0] = a_depth; rd[1] = a_acc; rd[2] = a_irr;
+#pragma unroll
+      for (int c = 0; c < 15; ++c) rd[3 + c] = a_col[c];
+    }
+    __syncthreads();
+    if (warp == 0) {
+      // totals over the warps (lane j < 18 owns sum j), then the combined gradients wrt the LINEAR maps
+      float tot = 0.f;
+      if (lane < 18)
+        for (int ww = 0; ww < W; ++ww) tot += s_red[ww * 20 + lane];
+      const float t_depth = __shfl_sync(FULL, tot, 0), t_acc = __shfl_sync(FULL, tot, 1), t_irr = __shfl_sync(FULL, tot, 2);
+      float lin = 0.f;                                        // linear map value of maps column `lane` (colour columns only)
+      if (lane == IBLN_MAP_IRR) lin = t_irr;
+#pragma unroll
+      for (int c = 0; c < 15; ++c) { const float v = __shfl_sync(FULL, tot, 3 + c); if (lane == IBLN_MAP_ALBEDO + c) lin = v; }
+      float g = 0.f;
+      if (lane < IBLN_MAPS_STRIDE) {
+        g = g_maps ? g_maps[(int64_t)r * IBLN_MAPS_STRIDE + lane] : 0.f;
+        if (g_srgb != nullptr) {
+          const float gs = g_srgb[(int64_t)r * IBLN_MAPS_STRIDE + lane];
+          const bool colour = (lane == IBLN_MAP_IRR) || (lane >= IBLN_MAP_ALBEDO && lane < IBLN_MAP_COARSE + 9);
+          g += colour ? gs * dsrgbf(lin) : gs;
+        }
+      }
+      float gdepth = __shfl_sync(FULL, g, IBLN_MAP_DEPTH), gacc = __shfl_sync(FULL, g, IBLN_MAP_ACC);
+      const float gdisp = __shfl_sync(FULL, g, IBLN_MAP_DISP);
+      if (gdisp != 0.f) {
+        const float q = t_depth / t_acc;
+        if (q > 1e-10f) {
+          const float iq2 = 1.0f / (q * q);
+          gdepth += gdisp * (-iq2 / t_acc);
+          gacc += gdisp * (iq2 * t_depth / (t_acc * t_acc));
+        }
+      }
+      if (lane < IBLN_MAPS_STRIDE) s_g[lane] = g;
+      if (lane == 0) { s_g[24] = gdepth; s_g[25] = gacc; }
+    }
+    __syncthreads();
+    const float gdepth = s_g[24], gacc = s_g[25];
+    float gm[17];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) gm[c] = s_g[IBLN_MAP_ALBEDO + c];
+    gm[3] = s_g[IBLN_MAP_ROUGH]; gm[4] = s_g[IBLN_MAP_IRR];
+#pragma unroll
+    for (int c = 0; c < 12; ++c) gm[5 + c] = s_g[IBLN_MAP_RAD + c];
+    // ---- pass 2a: gw, row-local exclusive suffix of gw * w, row totals
+    for (int k = warp; k < nrows; k += W) {
+      const int i = k * ROW + lane;
+      const float2* px2 = reinterpret_cast<const float2*>(tile + (size_t)i * C);
+      const float2 r3 = px2[3], r4 = px2[4];       // channels 6..9: radiance activations = channels 6, 7, 8
+      float gw = (g_weights ? g_weights[(int64_t)r * S + i] : 0.f) + gdepth * s_z[i] + gacc;
+      gw += gm[5] * r3.x + gm[6] * r3.y + gm[7] * r4.x;
+      const float tv = gw * (s_alpha[i] * s_T[i]);
+      float ps = tv;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float v = __shfl_down_sync(FULL, ps, o);
+        if (lane + o < 32) ps += v;
+      }
+      s_gw[i] = gw; s_suf[i] = ps - tv;
+      if (lane == 0) s_rowsum[k] = ps;
+    }
+    __syncthreads();
+    // T_end = product of all row products (sequential order)
+    float t_end = 1.0f;
+    for (int kk = 0; kk < nrows; ++kk) t_end *= s_rowprod[kk];
+    const float tend_term = s_g[IBLN_MAP_TEND] * t_end;
+    const int rn = r + gridDim.x;
+    // ---- pass 2b: g_raw rows in place, streamed out, refilled with the next ray's rows
+    for (int k = warp; k < nrows; k += W) {
+      float carry = tend_term;
+      for (int kk = nrows - 1; kk > k; --kk) carry += s_rowsum[kk];
+      const int i = k * ROW + lane;
+      float2* px2 = reinterpret_cast<float2*>(tile + (size_t)i * C);
+      const float alpha = s_alpha[i], T = s_T[i], w = alpha * T, gw = s_gw[i];
+      float yy[18], go[18];
+#pragma unroll
+      for (int q = 0; q < 9; ++q) { const float2 v = px2[q]; yy[2 * q] = v.x; yy[2 * q + 1] = v.y; }
+#pragma unroll
+      for (int c = 0; c < 17; ++c) { const float y = yy[1 + c]; go[1 + c] = w * gm[c] * y * (1.f - y); }
+      const float excl = s_suf[i] + carry;
+      const float om = (1.0f - alpha) + 1e-10f;
+      const float galpha = gw * T - excl / om;
+      go[0] = galpha * s_dist[i] * (1.0f - alpha);
+#pragma unroll
+      for (int q = 0; q < 9; ++q) px2[q] = make_float2(go[2 * q], go[2 * q + 1]);
+      __syncwarp();
+      float4* dst = reinterpret_cast<float4*>(g_raw + ((int64_t)r * S + (int64_t)k * ROW) * C);
+      const float4* srow = reinterpret_cast<const float4*>(tile + (size_t)k * rowf);
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        const int e = lane + 32 * j;
+        if (j < 4 || e < 144) __stcs(dst + e, srow[e]);
+      }
+      __syncwarp();
+      if (rn < n) load_row(rn, k);
+    }
+    cp_async_commit();
+    __syncthreads();                               // s_rowprod / s_rowsum / s_g / s_red are rewritten by the next ray
+  }
+}
+
 // sigma-only depth compositing (normal estimator / raw2outputs_depth): no tile staging needed.
 __global__ void __launch_bounds__(CP_WARPS * 32)
 depth_fwd_kernel(const float* __restrict__ sigma, const float* __restrict__ z, const float* __restrict__ rays_d,
@@ -703,6 +922,27 @@ extern "C" int ibln_composite_bwd(const float* raw, const float* z, const float*
     IBLN_CUDA(cudaFuncSetAttribute(composite_bwd_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     composite_bwd_resident_kernel<<<comp_grid(n, device, per_sm, warps), warps * 32, smem, (cudaStream_t)stream>>>(
         raw, z, rays_d, noise, g_weights, g_maps, g_maps_srgb, n, S, g_raw);
+    IBLN_RETURN_LAST();
+  }
+  if (C == 18 && nc == 3 && sigm == 1 && S % 32 == 0 && S <= 1024 && (reinterpret_cast<uintptr_t>(raw) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(g_raw) & 15) == 0) {
+    // CTA-per-ray kernel: [S,18] tile + 6 S floats + row tables per CTA (18.9 KB at S = 192, 50 KB at S = 512)
+    const int nrows = S / 32;
+    auto go = [&](auto kern, int w) -> int {
+      const size_t smem = ((size_t)S * 18 + 6 * (size_t)S + 2 * nrows + w * 20 + 32) * sizeof(float);
+      if (smem > 200 * 1024) return IBLN_EINVAL;
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+      int per_sm = (int)((226 * 1024) / (smem + 1024));
+      if (per_sm > 48 / w) per_sm = 48 / w;           // <= 48 warps per SM
+      if (per_sm < 1) per_sm = 1;
+      int64_t grid = (int64_t)num_sms(device) * per_sm;
+      if (grid > n) grid = n;
+      kern<<<(unsigned)grid, w * 32, smem, (cudaStream_t)stream>>>(raw, z, rays_d, noise, g_weights, g_maps, g_maps_srgb, n, S, g_raw);
+      return 0;
+    };
+    int rc = nrows >= 8 ? go(composite_bwd_cta_kernel<8>, 8) : (nrows >= 6 ? go(composite_bwd_cta_kernel<6>, 6) : go(composite_bwd_cta_kernel<4>, 4));
+    if (rc != 0) return rc;
     IBLN_RETURN_LAST();
   }
   int Sp = (S + 31) & ~31;
