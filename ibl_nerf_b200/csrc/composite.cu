@@ -600,8 +600,7 @@ composite_bwd_resident_kernel(const float* __restrict__ raw, const float* __rest
   }
 }
 
-// Backward, CTA-PER-RAY variant for long rays (reference layout, S % 32 == 0, S > RESIDENT_MAX_S: the fine pass's 192
-// samples and the sweep's 256 / 512).  A warp cannot keep such a ray resident (36 KB at S = 512 would leave 4 warps per SM),
+// Backward, CTA-PER-RAY variant for long rays (reference layout, S % 32 == 0, S >= 256: the sweep's 256 / 512).  A warp cannot keep such a ray resident (36 KB at S = 512 would leave 4 warps per SM),
 // and the streaming kernel re-reads every row in its reverse pass -- from DRAM once the rays in flight exceed L2 (ncu at
 // S = 512: DRAM reads 1.64 x raw, 0.61 of the HBM copy peak).  Here ONE CTA of W warps owns the ray: its [S,18] tile is
 // resident in shared memory, warp w owns rows w, w + W, ... in both passes (so the tile rows stay warp-private and a
@@ -611,7 +610,7 @@ composite_bwd_resident_kernel(const float* __restrict__ raw, const float* __rest
 //   sum_{k>i} gw_k w_k = (exclusive suffix inside the row) + sum_{rows after} rowsum + g_Tend T_end
 // Like the ray-resident warp kernel it evaluates every head sigmoid once and never reads raw twice.
 template <int W>
-__global__ void __launch_bounds__(W * 32, W == 8 ? 4 : (W == 6 ? 6 : 8))       // 32 / 36 / 32 warps per SM
+__global__ void __launch_bounds__(W * 32, 4)       // 32 warps per SM at W = 8 (64 registers)
 composite_bwd_cta_kernel(const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays_d,
                          const float* __restrict__ noise, const float* __restrict__ g_weights,
                          const float* __restrict__ g_maps, const float* __restrict__ g_srgb, int n, int S,
@@ -924,9 +923,11 @@ extern "C" int ibln_composite_bwd(const float* raw, const float* z, const float*
         raw, z, rays_d, noise, g_weights, g_maps, g_maps_srgb, n, S, g_raw);
     IBLN_RETURN_LAST();
   }
-  if (C == 18 && nc == 3 && sigm == 1 && S % 32 == 0 && S <= 1024 && (reinterpret_cast<uintptr_t>(raw) & 15) == 0 &&
+  if (C == 18 && nc == 3 && sigm == 1 && S % 32 == 0 && S >= 256 && S <= 1024 && (reinterpret_cast<uintptr_t>(raw) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(g_raw) & 15) == 0) {
-    // CTA-per-ray kernel: [S,18] tile + 6 S floats + row tables per CTA (18.9 KB at S = 192, 50 KB at S = 512)
+    // CTA-per-ray kernel: [S,18] tile + 6 S floats + row tables per CTA (50 KB at S = 512).  Measured against the streaming
+    // kernel: S = 512 0.67 vs 0.61 of the HBM copy peak; at S = 192 (one row per warp: five CTA barriers per 6 rows) 0.46 vs
+    // 0.78, so shorter rays stay on the streaming kernel.
     const int nrows = S / 32;
     auto go = [&](auto kern, int w) -> int {
       const size_t smem = ((size_t)S * 18 + 6 * (size_t)S + 2 * nrows + w * 20 + 32) * sizeof(float);
@@ -941,7 +942,7 @@ extern "C" int ibln_composite_bwd(const float* raw, const float* z, const float*
       kern<<<(unsigned)grid, w * 32, smem, (cudaStream_t)stream>>>(raw, z, rays_d, noise, g_weights, g_maps, g_maps_srgb, n, S, g_raw);
       return 0;
     };
-    int rc = nrows >= 8 ? go(composite_bwd_cta_kernel<8>, 8) : (nrows >= 6 ? go(composite_bwd_cta_kernel<6>, 6) : go(composite_bwd_cta_kernel<4>, 4));
+    int rc = go(composite_bwd_cta_kernel<8>, 8);
     if (rc != 0) return rc;
     IBLN_RETURN_LAST();
   }
