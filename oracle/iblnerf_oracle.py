@@ -294,7 +294,8 @@ def object_masks(mask_img, count):
 
 
 def raw2outputs(rays_o, rays_d, z, z_const, query, near, far, lut=None, approximate_radiance=False,
-                eps=0.01, gamma_correct=True, lut_coefficient="F", correct_depth=True, n_coarse=3, gt_values=None, **edit):
+                eps=0.01, gamma_correct=True, lut_coefficient="F", correct_depth=True, n_coarse=3, gt_values=None,
+                normal_kind="normal_map_from_depth_gradient_epsilon", **edit):
     """nerf_models/ibl_nerf_renderer.py:153-527 for the kitchen configuration (normal from depth gradient epsilon,
     sigmoid radiance, reflected ray under no_grad) including the two editing modes of test.py (`edit`: insert_object /
     edit_intrinsic and their lists, :218-256, 378-410).  The reference performs the edits IN PLACE on tensors that
@@ -316,8 +317,11 @@ def raw2outputs(rays_o, rays_d, z, z_const, query, near, far, lut=None, approxim
     res["target_depth_map"] = res["depth_map"]
     x_surface = (rays_o + rays_d * res["depth_map"][:, None]).detach()
     if approximate_radiance:
-        with torch.no_grad():
-            normal = normal_eps(rays_o, rays_d, z, query, eps)
+        if normal_kind == "ground_truth":                    # :371-372
+            normal = torch.nn.functional.normalize(2 * gt_values["normal"] - 1, dim=-1)
+        else:
+            with torch.no_grad():
+                normal = normal_eps(rays_o, rays_d, z, query, eps)
         albedo, rough, irr = res["albedo_map"], res["roughness_map"], res["irradiance_map"]
         vec = lambda v: torch.tensor(v, dtype=torch.float32)
         if edit.get("edit_intrinsic", False):

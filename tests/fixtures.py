@@ -127,3 +127,11 @@ def edit_insert_inputs(n=48, seed=61):
     edit = dict(edit_intrinsic=True, num_edit_objects=2, edit_depth=True, edit_normal=True, edit_albedo=True, edit_roughness=True,
                 editing_target_roughness_list=[0.05, 0.9], editing_target_albedo_list=[0.2, 0.7, 0.3, 0.6, 0.6, 0.1])
     return gt, insert, edit
+
+
+def make_gt_normals(n, seed=71):
+    """gt_values["normal"] as the datasets store it (unit normal mapped to [0,1]): facing the camera-ish hemisphere."""
+    g = torch.Generator().manual_seed(seed)
+    v = torch.randn(n, 3, generator=g)
+    v = v / v.norm(dim=-1, keepdim=True)
+    return 0.5 * (v + 1.0)

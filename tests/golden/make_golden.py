@@ -239,6 +239,40 @@ def g_render_rays():
     npz("render_rays_test.npz", rays=rays, **{k: v for k, v in res.items()})
 
 
+def g_render_rays_gtnormal():
+    """render_rays with the normals taken from gt_values (target_normal_map_for_radiance_calculation="ground_truth",
+    ibl_nerf_renderer.py:371-372) instead of the ill-conditioned finite-difference estimate: a well-conditioned end-to-end
+    case whose shading-head gradients can be compared tightly."""
+    coarse, fine = build_nets()
+    e10, _ = get_embedder(10, 0)
+    e4, _ = get_embedder(4, 0)
+    fx.structure_(coarse, e10, seed=11)
+    fx.structure_(fine, e10, seed=12)
+    lut = fx.load_lut()
+    n = 40
+    ro, rd = fx.make_rays(n, seed=1)
+    tg = fx.make_targets(n)
+    gt_normal = fx.make_gt_normals(n)
+    q = lambda p, v, f: run_network(p, v, f, e10, e4, 65536)
+    rays = torch.cat([ro, rd, torch.full((n, 1), fx.NEAR), torch.full((n, 1), fx.FAR), rd / rd.norm(dim=-1, keepdim=True)], -1)
+    kw = dict(network_fn=coarse, network_fine=fine, network_query_fn=q, N_samples=64, N_importance=128,
+              perturb=1.0, raw_noise_std=0., pytest=True, brdf_lut=lut, epsilon=0.01, gamma_correct=True,
+              lut_coefficient="F", target_normal_map_for_radiance_calculation="ground_truth",
+              correct_depth_for_prefiltered_radiance_infer=True, use_viewdirs=True, white_bkgd=False, lindisp=False,
+              gt_values={"normal": gt_normal})
+    res = render_rays(rays, approximate_radiance=True, **kw)
+    loss = fx.phase_b_loss(res, tg)
+    loss.backward()
+    gsel = {}
+    for nm, net in (("c", coarse), ("f", fine)):
+        for k, v in net.named_parameters():
+            if v.grad is not None:
+                gsel["ng_%s_%s" % (nm, k.replace(".", "__"))] = torch.tensor([v.grad.double().norm().item(), v.grad.double().sum().item()])
+    keep = ("color_map", "color_map0", "specular_map", "diffuse_map", "n_dot_v_map", "target_normal_map", "prefiltered_reflected_map",
+            "albedo_map", "roughness_map", "irradiance_map", "depth_map", "depth_map0")
+    npz("render_rays_gtnormal.npz", rays=rays, loss=loss.detach(), **{k: res[k] for k in keep}, **gsel)
+
+
 def g_rays_few():
     """get_rays_few (nerf_renderer_helper.py:14-23) exactly as sample_generator_single_image calls it
     (utils/generator_utils.py:108-142): numpy pixel draws -> torch.Tensor uv -> rays of one posed pinhole view."""
@@ -272,7 +306,7 @@ def g_depth_to_normal():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["lut", "posenc", "sample_pdf", "composite", "shading", "mlp", "render_rays", "depth_to_normal", "edit_insert", "rays_few"]
+    which = sys.argv[1:] or ["lut", "posenc", "sample_pdf", "composite", "shading", "mlp", "render_rays", "depth_to_normal", "edit_insert", "rays_few", "render_rays_gtnormal"]
     for w in which:
         {"lut": dump_lut, "posenc": g_posenc, "sample_pdf": g_sample_pdf, "composite": g_composite,
-         "shading": g_shading, "edit_insert": g_edit_insert, "rays_few": g_rays_few, "mlp": g_mlp, "render_rays": g_render_rays, "depth_to_normal": g_depth_to_normal}[w]()
+         "shading": g_shading, "edit_insert": g_edit_insert, "rays_few": g_rays_few, "render_rays_gtnormal": g_render_rays_gtnormal, "mlp": g_mlp, "render_rays": g_render_rays, "depth_to_normal": g_depth_to_normal}[w]()

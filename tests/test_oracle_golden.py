@@ -197,6 +197,28 @@ def test_render_rays_test_time():
         close(res[k], g[k], rtol=2e-3, atol=2e-4, name=k)
 
 
+def test_render_rays_ground_truth_normals():
+    """The well-conditioned end-to-end case: normals from gt_values instead of finite differences
+    (target_normal_map_for_radiance_calculation = "ground_truth"); values, loss and every gradient norm."""
+    g = G("render_rays_gtnormal.npz")
+    pc, pf = structured_nets()
+    n = g["rays"].shape[0]
+    res = orc.render_rays(g["rays"], pc, pf, fx.load_lut(), perturb=1.0, pytest=True, approximate_radiance=True,
+                          normal_kind="ground_truth", gt_values={"normal": fx.make_gt_normals(n)})
+    for k in ("color_map", "color_map0", "specular_map", "diffuse_map", "n_dot_v_map", "target_normal_map", "albedo_map",
+              "roughness_map", "depth_map", "depth_map0"):
+        close(res[k], g[k], rtol=2e-3, atol=3e-4, name=k)
+    loss = fx.phase_b_loss(res, fx.make_targets(n))
+    close(loss, g["loss"], rtol=1e-4, name="loss")
+    loss.backward()
+    for tag, p in (("c", pc), ("f", pf)):
+        for k, v in p.items():
+            key = "ng_%s_%s" % (tag, k.replace(".", "__"))
+            if key in g and v.grad is not None:
+                ref = g[key][0].item()
+                assert abs(v.grad.double().norm().item() - ref) <= 2e-2 * ref + 1e-9, (k, v.grad.norm().item(), ref)
+
+
 def test_depth_to_normal():
     """utils/depth_to_normal_utils.py:26-46 (export path): oracle vs the reference's output on a seeded depth image."""
     g = G("depth_to_normal.npz")
