@@ -5,6 +5,7 @@ import torch
 
 import fixtures as fx
 import ibl_nerf_b200 as ib
+from oracle import iblnerf_oracle as orc
 from util import G, build_nets, close, close_frac, close_mostly
 
 pytestmark = pytest.mark.gpu
@@ -129,6 +130,18 @@ def test_render_rays_bf16_psnr_criterion():
     for key in ("radiance_map", "color_map"):
         d = abs(psnr(out["bf16"][key]) - psnr(out["fp32"][key]))
         assert d < 0.05, (key, d)
+    # ... and directly against the fp32 REFERENCE algorithm (the CPU oracle, pinned on the reference's goldens) on the
+    # first 256 of these rays: the exact-fp32 kernels above are themselves only transitively pinned
+    m = 256
+    coarse, fine = build_nets(DEV, structured=True, precision="bf16")
+    with torch.no_grad():
+        want = orc.render_rays(rays[:m].cpu(), {k: v.detach().cpu() for k, v in coarse.state_dict().items()},
+                               {k: v.detach().cpu() for k, v in fine.state_dict().items()}, fx.load_lut(), perturb=0.,
+                               approximate_radiance=True)
+    psnr_m = lambda a: (-10. * torch.log10(torch.mean((a.cpu() - tg[:m].cpu()) ** 2))).item()
+    for key in ("radiance_map", "color_map"):
+        d = abs(psnr_m(out["bf16"][key][:m]) - psnr_m(want[key]))
+        assert d < 0.05, (key, "vs oracle", d)
 
 
 def test_training_step_micro_batches_match_full_batch():
