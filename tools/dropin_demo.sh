@@ -23,6 +23,10 @@ exp = os.path.join(T, "logs", "IBL-NeRF")
 acc = EventAccumulator(exp, size_guidance={"scalars": 0}); acc.Reload()
 print("reference src/train.py + src/test.py (unmodified, baseline/_ref) through ibl_nerf_b200.launcher; synthetic Mitsuba-format scene 96x128, 6 views")
 print("train.py: 120 iterations, N_rand 4096, phases: radiance-only < 40 <= full IBL < 80 <= priors + freeze; wall %.1f s incl. dataset load, test-set export at 100" % (E - S))
+el = [(e.step, e.value) for e in acc.Scalars("elapsed_time")]
+if len(el) >= 3:      # train.py accumulates the wall time of its iterations (train.py:501-502); skip the first interval (warm-up)
+    print("train.py iteration time through the drop-in (autograd route, the driver's own torch losses / optimizer): "
+          + ", ".join("%d-%d: %.1f ms" % (a[0], b[0], 1e3 * (b[1] - a[1]) / (b[0] - a[0])) for a, b in zip(el[1:-1], el[2:])))
 for tag in ("Loss/Total_Loss", "Loss/Loss_radiance_render", "Loss/Loss_render", "Loss/Loss_prior_albedo", "Loss/Loss_irradiance_reg"):
     print("%-28s" % tag, " ".join("%d:%.4f" % (e.step, e.value) for e in acc.Scalars(tag)))
 print("checkpoints:", sorted(os.path.basename(p) for p in glob.glob(os.path.join(exp, "*.tar"))))
