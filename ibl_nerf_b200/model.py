@@ -122,11 +122,23 @@ class IBLNeRF(nn.Module):
                 list(self.skips) == [4] and self.coarse_radiance_number == 3 and not self.is_color_independent_to_direction)
 
     def ordered_params(self):
-        sd = dict(self.named_parameters())
+        """The 46 parameters in state-dict order.  The list is cached (module traversal per query showed up in the step's
+        host time); nn.Module keeps the Parameter objects across .to() / load_state_dict, and the cache is rebuilt if one
+        of them is replaced."""
+        cached = self.__dict__.get("_ordered")
+        if (cached is not None and cached[0] is self.positions_linears[0].weight and cached[20] is self.sigma_linear.weight and
+                cached[-1] is self.additional_radiance_linear[-1].bias):
+            return cached
         out = []
         for name, _, _ in mlp.PARAM_ORDER:
-            out += [sd[name + ".weight"], sd[name + ".bias"]]
+            mod = self.get_submodule(name)
+            out += [mod.weight, mod.bias]
+        self.__dict__["_ordered"] = out
         return out
+
+    def _apply(self, fn, *args, **kwargs):          # .to() / .cuda() / .float(): drop the cache (Parameters may be replaced)
+        self.__dict__.pop("_ordered", None)
+        return super()._apply(fn, *args, **kwargs)
 
     def effective_precision(self):
         return self.precision or mlp.default_precision()
