@@ -244,6 +244,95 @@ sample_pdf_kernel(const float* __restrict__ bins, int64_t bins_stride, const flo
   }
 }
 
+// Larger rays (64 < nbins <= 32 K, the sweep's 191 / 384 and 511 / 1024 shapes) through the weights -> samples path:
+// ncu on sample_pdf_kernel put `long_scoreboard` (exposed global-load latency: weights twice, bins in the guide build, one
+// round trip per 128-sample batch of uniforms) at 7 of 13 stalled warps per issue.  Same arithmetic (bit-identical CDF and
+// samples), but every global load is issued ahead of its use: the NEXT ray's weights / bins travel in K register slots
+// per lane while the current ray is sampled, the next batch of uniforms while the current batch is inverted.
+template <int K>
+__global__ void __launch_bounds__(SP_WARPS * 32)
+sample_pdf_prefetch_kernel(const float* __restrict__ bins, int64_t bins_stride, const float* __restrict__ weights,
+                           int64_t w_stride, const float* __restrict__ u, int n, int nbins, int nsamp,
+                           float* __restrict__ samples) {
+  extern __shared__ __align__(16) float sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const RaySmem rs = carve(sm + (size_t)warp * ray_smem_floats(nbins), nbins);
+  const int stride = gridDim.x * SP_WARPS;
+  const int nw = nbins - 1;
+  const int nbatch = (nsamp + 127) >> 7;
+  auto fetch_wb = [&](int r, float (&w)[K], float (&b)[K]) {
+    const float* wrow = weights + (int64_t)r * w_stride;
+    const float* brow = bins + (int64_t)r * bins_stride;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int i = lane + 32 * k;
+      w[k] = (r < n && i < nw) ? wrow[i] : 0.f;
+      b[k] = (r < n && i < nbins) ? brow[i] : 0.f;
+    }
+  };
+  auto fetch_u = [&](int r, int batch, float (&uu)[4]) {
+    const float* urow = u + (int64_t)r * nsamp;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int j = batch * 128 + 32 * q + lane;
+      uu[q] = j < nsamp ? urow[j] : 0.f;
+    }
+  };
+  int r = blockIdx.x * SP_WARPS + warp;
+  float wc[K], bc[K], wn[K], bn[K];
+  fetch_wb(r, wc, bc);
+  for (; r < n; r += stride) {
+    float uc[4], un[4];
+    fetch_u(r, 0, uc);
+    // ---- CDF from the register-held weights: the summation order of warp_build_cdf
+    float part = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+      if (lane + 32 * k < nw) part += wc[k] + 1e-5f;
+    const float inv_total = __fdividef(1.0f, warp_sum(part));
+    float carry = 0.f;
+    if (lane == 0) rs.cdf[0] = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      if (32 * k < nw) {
+        const int i = lane + 32 * k;
+        float p = (i < nw) ? (wc[k] + 1e-5f) * inv_total : 0.f;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const float v = __shfl_up_sync(FULL, p, o);
+          if (lane >= o) p += v;
+        }
+        if (i < nw) rs.cdf[i + 1] = carry + p;
+        carry += __shfl_sync(FULL, p, 31);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+      if (lane + 32 * k < nbins) rs.bins[lane + 32 * k] = bc[k];
+    __syncwarp();
+    fetch_wb(r + stride, wn, bn);                   // in flight during the guide build and the sampling of this ray
+    warp_build_guide(rs, rs.bins, nbins, lane);
+    float* orow = samples + (int64_t)r * nsamp;
+    for (int b = 0; b < nbatch; ++b) {
+      if (b + 1 < nbatch) fetch_u(r, b + 1, un);
+      float sv[4];
+      int ind[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) sv[q] = invert_one<false>(rs, uc[q], &ind[q]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int j = b * 128 + 32 * q + lane;
+        if (j < nsamp) orow[j] = sv[q];
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) uc[q] = un[q];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < K; ++k) { wc[k] = wn[k]; bc[k] = bn[k]; }
+  }
+}
+
 // The shipped shape (nbins <= 64, nsamp <= 128: 63 bins / 128 samples): every input of a ray fits in 8 registers
 // per lane, so the NEXT ray's weights / bins / uniforms are fetched while the current ray is processed -- the
 // generic kernel exposes three dependent global-load round trips per ray (ncu: 53 % long-scoreboard stalls).
@@ -439,6 +528,16 @@ static int launch_sample_pdf(const float* bins, int64_t bs, const float* w, int6
       sample_pdf_small_kernel<false, 63, 128><<<grid, SP_WARPS * 32, smem, (cudaStream_t)stream>>>(bins, bs, w, ws, cdf, u, n, nbins, nsamp, inds, samples);
     else
       sample_pdf_small_kernel<false, 0, 0><<<grid, SP_WARPS * 32, smem, (cudaStream_t)stream>>>(bins, bs, w, ws, cdf, u, n, nbins, nsamp, inds, samples);
+    IBLN_RETURN_LAST();
+  }
+  if (cdf == nullptr && nbins <= 512) {   // weights -> samples for longer rays: register-prefetching kernel
+    auto go = [&](auto kern) -> int {
+      if (smem > 48 * 1024) { cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return (int)e; }
+      kern<<<grid, SP_WARPS * 32, smem, (cudaStream_t)stream>>>(bins, bs, w, ws, u, n, nbins, nsamp, samples);
+      return 0;
+    };
+    int rc = nbins <= 192 ? go(sample_pdf_prefetch_kernel<6>) : go(sample_pdf_prefetch_kernel<16>);
+    if (rc != 0) return rc;
     IBLN_RETURN_LAST();
   }
   if (cdf != nullptr) {   // explicit-CDF entry: bit-exact arithmetic

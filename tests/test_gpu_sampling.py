@@ -58,6 +58,19 @@ def test_hierarchical_sample_and_merge(n, s0, s1):
     assert torch.equal(ib.ops.merge_sort_z(z.to(DEV), zs), zm)
 
 
+@pytest.mark.parametrize("n,nbins,nsamp", [(301, 191, 384), (77, 511, 1024), (130, 100, 77), (9, 65, 129), (40, 700, 300)])
+def test_sample_pdf_longer_rays_vs_oracle(n, nbins, nsamp):
+    """The weights -> samples path beyond the shipped 63 / 128 shape (BASELINE config 5 sweep: 191 / 384, 511 / 1024; ragged
+    sizes; > 512 bins falls back to the generic kernel) against the oracle's sample_pdf."""
+    g = torch.Generator().manual_seed(nbins)
+    bins = torch.sort(torch.rand(n, nbins, generator=g) * 7.5 + 0.5, -1)[0]
+    w = torch.rand(n, nbins - 1, generator=g) ** 3
+    w[0] = 0.0
+    u = torch.rand(n, nsamp, generator=g)
+    got = ib.ops.sample_pdf_u(bins.to(DEV), w.to(DEV), u.to(DEV))
+    close_mostly(got, orc.sample_pdf(bins, w, u), rtol=1e-5, atol=2e-6, name="samples")
+
+
 def test_sample_pdf_large_properties():
     """BASELINE config 5 scale: monotone in u, inside the bin range, deterministic."""
     n = 1 << 17
