@@ -111,3 +111,29 @@ def test_raw2outputs_edit_and_insert_modes_golden(tag):
         tight = k in ("depth_map", "target_depth_map", "disp_map", "roughness_map", "albedo_map", "irradiance_map",
                       "target_normal_map", "n_dot_v_map")
         close(a[m], b[m], rtol=2e-4 if tight else 5e-3, atol=2e-5 if tight else 3e-3, name=k + " (masked)")
+
+
+def test_aux_mlp_through_the_generic_query_path():
+    """infer_normal with an auxiliary position MLP (ibl_nerf_renderer.py:267-275; PositionMLP in the reference, any
+    nn.Module here): run_network's generic route -- CUDA positional encoding + the module called as an opaque function --
+    composited with the detached weights, and differentiable through torch autograd."""
+    n, s = 24, 64
+    torch.manual_seed(3)
+    aux = torch.nn.Sequential(torch.nn.Linear(63, 32), torch.nn.ReLU(), torch.nn.Linear(32, 3)).to(DEV)
+    q = ib.NetworkQuery(ib.get_embedder(10)[0], ib.get_embedder(4)[0], 65536)
+
+    def query(pts, vd, net):
+        return q(pts, vd, net) if isinstance(net, torch.nn.Module) else fx.analytic_query(pts, vd, net)
+    ro, rd = fx.make_rays(n, seed=5)
+    ro = ro * 0.3
+    z = fx.make_sorted_z(n, s, seed=6)
+    res = ib.raw2outputs(ro.to(DEV), rd.to(DEV), z.to(DEV), z.to(DEV), query, fx.STUB_NET, infer_normal=True, normal_mlp=aux,
+                         gamma_correct=False, approximate_radiance=False)
+    pts = ro[:, None] + rd[:, None] * z[..., None]
+    w = orc.composite(fx.analytic_query(pts, rd, None), z, rd)["weights"]
+    cpu = torch.nn.Sequential(torch.nn.Linear(63, 32), torch.nn.ReLU(), torch.nn.Linear(32, 3))
+    cpu.load_state_dict({k: v.cpu() for k, v in aux.state_dict().items()})
+    want = (w[..., None] * (2 * torch.sigmoid(cpu(orc.embed(pts.reshape(-1, 3), 10)).reshape(n, s, 3)) - 1)).sum(-2)
+    close(res["inferred_normal_map"], want, rtol=2e-4, atol=2e-5, name="inferred_normal_map")
+    res["inferred_normal_map"].square().sum().backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() and p.grad.abs().sum() > 0 for p in aux.parameters())
