@@ -1,10 +1,9 @@
 #!/bin/bash
-# A/B timing of prebuilt library variants (variants/var_*.so) on ONE box, interleaved, 3 repetitions
-cp ibl_nerf_b200/libiblnerf_b200.so /tmp/orig.so
+# A/B timing of prebuilt DIAGNOSTICS-build library variants (variants/var_*.so) on ONE box, interleaved, 3 repetitions.
+# usage: tools/var_probe.sh [probe script, default tools/bwd_probe.py]
+probe=${1:-tools/bwd_probe.py}
 for rep in 1 2 3; do
 for v in variants/var_*.so; do
-  cp $v ibl_nerf_b200/libiblnerf_b200.so
-  echo "== $v $(python tools/stash_probe.py | tr '\n' ' ')"
+  echo "== $v $(IBLN_LIB=$PWD/$v python $probe | tr '\n' ' ')"
 done
 done
-cp /tmp/orig.so ibl_nerf_b200/libiblnerf_b200.so
