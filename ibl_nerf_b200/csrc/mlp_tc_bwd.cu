@@ -530,6 +530,7 @@ __global__ void __launch_bounds__(128, 2) mlp_dgrad_freeze_kernel(FreezeParams p
 // TMEM accumulator (red.global.add.f32) only once per (job, range) segment: ~200 flushes per network
 // instead of one per CTA per job, and no launch gaps between the jobs.
 struct WOut { int off; int m_lo, m_hi, n_lo, n_hi, stride_m, stride_n; };
+struct WHead { int off, ch_lo, ch_hi; };      // rows [ch_lo, ch_hi) of the G-head accumulator -> flat[off + (ch - ch_lo) * 256 + feature]
 struct WJob {
   int a_sv, a_blk;       // A operand: record (1 = forward stash, 0 = dY record) and first block of m-half 0
   int b_sv, b_blk;
@@ -538,29 +539,40 @@ struct WJob {
   int n_total;           // N of the main MMA (multiple of 16, <= 256)
   int with_ones;
   int a_noswz;           // A blocks are in the slice-interleaved no-swizzle layout (SV_AF, SV_ADDF 0..3)
+  int xb, x_sv, x_blk;   // one extra 64-column B block sharing A (accumulator columns 320..383): the encoding part of a
+                         // layer whose input is [activation | encoding]
+  int gh;                // G head: a second GEMM sharing B, D2[g channel][B column] = G^T B (M = 64; class c takes B
+                         // columns 128c..128c+127, accumulator columns 320..447): the small heads that read this job's B
   int cost;              // relative streaming cost of one tile for a CTA pair
-  int n_out;
+  int n_out, n_head;
   WOut out[4];
+  WHead head[2];
 };
-constexpr int WG_MAX_JOBS = 21;
+constexpr int WG_MAX_JOBS = 17;
 struct WgradParams {
   const uint8_t* sv; const uint8_t* dy; float* flat;
   long long n_tiles;
   int n_jobs;
   WJob job[WG_MAX_JOBS];
 };
+static_assert(sizeof(WgradParams) <= 4096, "kernel parameter space");
 
-// Operand ring: a stage holds WG_STAGE_PTS points of every block (the rows of a 16 KB block are contiguous, so a
-// row range is one bulk copy per block).  Small stages keep more bytes in flight per SM (Little's law: the
+// Operand ring: a stage holds WG_STAGE_PTS points of every block of the job (the rows of a 16 KB block are contiguous,
+// so a row range is one bulk copy per block).  Small stages keep more bytes in flight per SM (Little's law: the
 // kernel is a pure HBM/L2 stream, ~0.09 FLOP/B short of the tensor roofline) than whole-tile double buffering.
+// The ring is re-cut per job: a job with k blocks per stage gets min(16, 52 / k) stages of k * 4 KB (3 blocks: 16
+// stages, 6: 8, 7: 7), after the stages of the previous geometry have drained.
 constexpr int WG_STAGE_PTS = 32;
 constexpr int WG_SUB = TILE_M / WG_STAGE_PTS;              // stages per tile
 constexpr int WG_BLK_BYTES = WG_STAGE_PTS * 128;           // bytes of one block's row range
-constexpr int WG_STAGE_BYTES = 6 * WG_BLK_BYTES;           // A (2 blocks) + B (<= 4 blocks)
-constexpr int WG_NSTAGES = 8;
-constexpr int WG_SMEM_ONES = WG_NSTAGES * WG_STAGE_BYTES;  // [WG_STAGE_PTS rows][64] ones tile
+constexpr int WG_RING_BLOCKS = 52;
+constexpr int WG_MAX_STAGES = 16;
+constexpr int WG_SMEM_ONES = WG_RING_BLOCKS * WG_BLK_BYTES;  // [WG_STAGE_PTS rows][64] ones tile
 constexpr int WG_SMEM_BAR = WG_SMEM_ONES + WG_BLK_BYTES;
-constexpr int WG_SMEM_REQUEST = WG_SMEM_BAR + 256 + 1024;
+constexpr int WG_SMEM_REQUEST = WG_SMEM_BAR + 512 + 1024;
+constexpr int WG_COL_ONES = 256, WG_COL_EXTRA = 320;       // accumulator columns of the bias sums / the extra GEMM
+__host__ __device__ inline int wg_stage_blocks(const WJob& jb) { return 2 + jb.nb + jb.xb + jb.gh; }
+__device__ __forceinline__ int wg_stages(int nblk) { const int n = WG_RING_BLOCKS / nblk; return n > WG_MAX_STAGES ? WG_MAX_STAGES : n; }
 // warps 0..3 producers (stage i of the running stage counter belongs to producer i % 4: one thread issuing the
 // 3-6 bulk copies of every 32-point slice was the pacing item -- ncu: the lone producer busy 85 % of the time, the
 // MMA thread waiting for data 55 %), warp 4 MMA, warps 5-8 epilogue
@@ -588,22 +600,59 @@ __device__ __forceinline__ WSeg wgrad_segment(const WgradParams& prm, int j, lon
   return s;
 }
 
+// MMA issue loop of one (job, tile range) segment: n stages of 32 points = 2 K-steps each.
+// EXTRA: 0 none, 1 extra B block (N = 64, shares A), 2 G head (A = G block with M = 64, B = this CTA's half of B)
+struct WgMma {
+  uint32_t smem, st_bytes, e_off, h_off, ones_addr, tmem, idesc;
+  int nst;
+  uint64_t* full; uint64_t* empty;
+};
+template <bool ONES, bool NOSWZ, int EXTRA>
+__device__ __forceinline__ void wg_mma_segment(const WgMma& mm, long long n, int& slot, uint32_t& par) {
+  constexpr uint32_t idesc1 = make_idesc_bf16(128, 64, 1, 1);   // whole 64-wide swizzle atom (ones tile: only column 0 is non-zero)
+  constexpr uint32_t idesc_head = make_idesc_bf16(64, 128, 1, 1);
+  for (long long it = 0; it < n; ++it) {
+    const int stage = slot;
+    const uint32_t ph = (par >> stage) & 1u;
+    par ^= 1u << stage;
+    if (++slot == mm.nst) slot = 0;
+    mbar_wait(&mm.full[stage], ph);
+    tc_fence_after();
+    const uint32_t a_addr = mm.smem + stage * mm.st_bytes;
+    const uint32_t b_addr = a_addr + 2 * WG_BLK_BYTES;
+#pragma unroll
+    for (int ks = 0; ks < WG_STAGE_PTS / 16; ++ks) {       // 16 points per MMA
+      const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
+      const uint64_t da = NOSWZ ? make_desc_mnmajor_noswz(a_addr + ks * 256, 128, 512)
+                                : make_desc_mnmajor_sw128(a_addr + ks * 2048, WG_BLK_BYTES);
+      umma_bf16(mm.tmem, da, make_desc_mnmajor_sw128(b_addr + ks * 2048, WG_BLK_BYTES), mm.idesc, acc);
+      if (ONES) umma_bf16(mm.tmem + WG_COL_ONES, da, make_desc_mnmajor_sw128(mm.ones_addr + ks * 2048, WG_BLK_BYTES), idesc1, acc);
+      if (EXTRA == 1)
+        umma_bf16(mm.tmem + WG_COL_EXTRA, da, make_desc_mnmajor_sw128(a_addr + mm.e_off + ks * 2048, WG_BLK_BYTES), idesc1, acc);
+      if (EXTRA == 2)
+        umma_bf16(mm.tmem + WG_COL_EXTRA, make_desc_mnmajor_sw128(a_addr + mm.e_off + ks * 2048, WG_BLK_BYTES),
+                  make_desc_mnmajor_sw128(a_addr + mm.h_off + ks * 2048, WG_BLK_BYTES), idesc_head, acc);
+    }
+    umma_commit(&mm.empty[stage]);
+  }
+}
+
 __global__ void __launch_bounds__(WG_THREADS, 1) mlp_wgrad_kernel(const __grid_constant__ WgradParams prm) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WG_SMEM_BAR);
-  uint64_t* full = bars;                       // [WG_NSTAGES]
-  uint64_t* empty = bars + WG_NSTAGES;         // [WG_NSTAGES]
-  uint64_t* done = bars + 2 * WG_NSTAGES;      // MMA -> epilogue: the segment's accumulator is complete
-  uint64_t* acc_free = bars + 2 * WG_NSTAGES + 1;   // epilogue -> MMA: the accumulator has been drained
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * WG_NSTAGES + 2);
+  uint64_t* full = bars;                       // [WG_MAX_STAGES]
+  uint64_t* empty = bars + WG_MAX_STAGES;      // [WG_MAX_STAGES]
+  uint64_t* done = bars + 2 * WG_MAX_STAGES;   // MMA -> epilogue: the segment's accumulator is complete
+  uint64_t* acc_free = bars + 2 * WG_MAX_STAGES + 1;   // epilogue -> MMA: the accumulator has been drained
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * WG_MAX_STAGES + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pair = blockIdx.x >> 1, r = blockIdx.x & 1, pairs = gridDim.x >> 1;
   long long w_total = 0;
   for (int j = 0; j < prm.n_jobs; ++j) w_total += prm.n_tiles * prm.job[j].cost;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < WG_NSTAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < WG_MAX_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(done, 1);
     mbar_init(acc_free, 4);
     fence_barrier_init();
@@ -620,66 +669,82 @@ __global__ void __launch_bounds__(WG_THREADS, 1) mlp_wgrad_kernel(const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
+  // Every role walks the same (job, tile, slice) sequence; `par` holds the phase parity of each ring slot's next use.
   if (warp < WG_PRODUCERS) {
     if (elect_one()) {
-      long long i = 0, job_start = 0;           // i: running stage counter of this CTA (ring position)
+      long long i = 0, job_start = 0;           // i: running stage counter of this CTA (producer round robin)
+      uint32_t par = 0;
+      int nblk = 0, nst = 0, slot = 0;
       for (int j = 0; j < prm.n_jobs; ++j) {
         const WJob& jb = prm.job[j];
         const WSeg sg = wgrad_segment(prm, j, job_start, w_total, pair, pairs, r);
         job_start += prm.n_tiles * jb.cost;
+        if (sg.t1 <= sg.t0) continue;
+        if (wg_stage_blocks(jb) != nblk) {       // new ring geometry: every stage of the old one has been consumed
+          for (int s2 = 0; s2 < nst; ++s2) mbar_wait(&empty[s2], ((par >> s2) & 1u) ^ 1u);
+          nblk = wg_stage_blocks(jb); nst = wg_stages(nblk); slot = 0;
+        }
         const uint8_t* a_base = (jb.a_sv ? prm.sv : prm.dy) + (size_t)(jb.a_blk + 2 * sg.cls) * KB_BYTES;
         const uint8_t* b_base = (jb.b_sv ? prm.sv : prm.dy) + (size_t)jb.b_blk * KB_BYTES;
+        const uint8_t* x_base = (jb.x_sv ? prm.sv : prm.dy) + (size_t)jb.x_blk * KB_BYTES;
+        const uint8_t* g_base = prm.dy + (size_t)DY_G * KB_BYTES;
         const long long a_stride = jb.a_sv ? SV_BYTES : DY_BYTES, b_stride = jb.b_sv ? SV_BYTES : DY_BYTES;
-        const uint32_t st_bytes = (uint32_t)(2 + jb.nb) * WG_BLK_BYTES;
+        const long long x_stride = jb.x_sv ? SV_BYTES : DY_BYTES;
+        const uint32_t st_bytes = (uint32_t)nblk * WG_BLK_BYTES;
+        const int nb = jb.nb;                      // job fields in registers: the asm memory clobbers would re-read them
+        const bool xb = jb.xb, gh = jb.gh;
         for (long long t = sg.t0; t < sg.t1; ++t) {
           const uint8_t* a_src = a_base + (size_t)t * a_stride;
           const uint8_t* b_src = b_base + (size_t)t * b_stride;
           for (int q = 0; q < WG_SUB; ++q, ++i) {
+            const int stage = slot;
+            const uint32_t ph = (par >> stage) & 1u;
+            par ^= 1u << stage;
+            if (++slot == nst) slot = 0;
             if ((int)(i % WG_PRODUCERS) != warp) continue;
-            const int stage = (int)(i % WG_NSTAGES);
-            const uint32_t ph = (uint32_t)((i / WG_NSTAGES) & 1);
             mbar_wait(&empty[stage], ph ^ 1);
             mbar_arrive_expect_tx(&full[stage], st_bytes);
-            uint8_t* dst = smem + stage * WG_STAGE_BYTES;
+            uint8_t* dst = smem + (size_t)stage * st_bytes;
             for (int b = 0; b < 2; ++b)
               bulk_g2s(dst + b * WG_BLK_BYTES, a_src + (size_t)b * KB_BYTES + q * WG_BLK_BYTES, WG_BLK_BYTES, &full[stage]);
-            for (int b = 0; b < jb.nb; ++b)
+            for (int b = 0; b < nb; ++b)
               bulk_g2s(dst + (2 + b) * WG_BLK_BYTES, b_src + (size_t)b * KB_BYTES + q * WG_BLK_BYTES, WG_BLK_BYTES, &full[stage]);
+            if (xb)
+              bulk_g2s(dst + (2 + nb) * WG_BLK_BYTES, x_base + (size_t)t * x_stride + q * WG_BLK_BYTES, WG_BLK_BYTES, &full[stage]);
+            if (gh)
+              bulk_g2s(dst + (2 + nb) * WG_BLK_BYTES, g_base + (size_t)t * DY_BYTES + q * WG_BLK_BYTES, WG_BLK_BYTES, &full[stage]);
           }
         }
       }
     }
   } else if (warp == WG_PRODUCERS) {
     if (elect_one()) {
-      const uint32_t idesc1 = make_idesc_bf16(128, 64, 1, 1);   // whole 64-wide swizzle atom; only column 0 is non-zero
       const uint32_t ones_addr = smem_u32(smem + WG_SMEM_ONES);
-      long long i = 0, job_start = 0;
-      uint32_t nseg = 0;
+      long long job_start = 0;
+      uint32_t nseg = 0, par = 0;
+      int nblk = 0, nst = 0, slot = 0;
       for (int j = 0; j < prm.n_jobs; ++j) {
         const WJob& jb = prm.job[j];
         const WSeg sg = wgrad_segment(prm, j, job_start, w_total, pair, pairs, r);
         job_start += prm.n_tiles * jb.cost;
         if (sg.t1 <= sg.t0) continue;
+        if (wg_stage_blocks(jb) != nblk) { nblk = wg_stage_blocks(jb); nst = wg_stages(nblk); slot = 0; }
         if (nseg > 0) { mbar_wait(acc_free, (nseg - 1) & 1); tc_fence_after(); }
         ++nseg;
-        const uint32_t idesc = make_idesc_bf16(128, (uint32_t)jb.n_total, 1, 1);
-        for (long long t = sg.t0; t < sg.t1; ++t) {
-          for (int q = 0; q < WG_SUB; ++q, ++i) {
-            const int stage = (int)(i % WG_NSTAGES);
-            const uint32_t ph = (uint32_t)((i / WG_NSTAGES) & 1);
-            mbar_wait(&full[stage], ph);
-            tc_fence_after();
-            const uint32_t a_addr = smem_u32(smem + stage * WG_STAGE_BYTES);
-            const uint32_t b_addr = a_addr + 2 * WG_BLK_BYTES;
-            for (int ks = 0; ks < WG_STAGE_PTS / 16; ++ks) {       // 16 points per MMA
-              const uint32_t acc = (t > sg.t0 || q > 0 || ks > 0) ? 1u : 0u;
-              const uint64_t da = jb.a_noswz ? make_desc_mnmajor_noswz(a_addr + ks * 256, 128, 512)
-                                             : make_desc_mnmajor_sw128(a_addr + ks * 2048, WG_BLK_BYTES);
-              umma_bf16(tmem_base, da, make_desc_mnmajor_sw128(b_addr + ks * 2048, WG_BLK_BYTES), idesc, acc);
-              if (jb.with_ones) umma_bf16(tmem_base + 256, da, make_desc_mnmajor_sw128(ones_addr + ks * 2048, WG_BLK_BYTES), idesc1, acc);
-            }
-            umma_commit(&empty[stage]);
-          }
+        WgMma mm;
+        mm.smem = smem_u32(smem); mm.st_bytes = (uint32_t)nblk * WG_BLK_BYTES; mm.e_off = (uint32_t)(2 + jb.nb) * WG_BLK_BYTES;
+        mm.h_off = (uint32_t)(2 + 2 * sg.cls) * WG_BLK_BYTES; mm.ones_addr = ones_addr; mm.tmem = tmem_base;
+        mm.idesc = make_idesc_bf16(128, (uint32_t)jb.n_total, 1, 1); mm.nst = nst; mm.full = full; mm.empty = empty;
+        const long long n = (sg.t1 - sg.t0) * WG_SUB;
+        // the issuing thread paces the 12 KB-stage jobs (~560 clk per stage): one loop per job shape, nothing predicated
+        const int shape = (jb.a_noswz ? 1 : 0) | (jb.with_ones ? 2 : 0) | (jb.xb ? 4 : 0) | (jb.gh ? 8 : 0);
+        switch (shape) {
+          case 0: wg_mma_segment<false, false, 0>(mm, n, slot, par); break;
+          case 1: wg_mma_segment<false, true, 0>(mm, n, slot, par); break;
+          case 2: wg_mma_segment<true, false, 0>(mm, n, slot, par); break;
+          case 6: wg_mma_segment<true, false, 1>(mm, n, slot, par); break;
+          case 10: wg_mma_segment<true, false, 2>(mm, n, slot, par); break;
+          default: __trap();
         }
         umma_commit(done);
       }
@@ -699,9 +764,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) mlp_wgrad_kernel(const __grid_c
       tc_fence_after();
       const int m = sg.cls * 128 + quarter * 32 + lane;
       const int nmain = (jb.n_total + 31) & ~31;
-      const int ncols = jb.with_ones ? 288 : nmain;
+      const int ncols = jb.xb ? WG_COL_EXTRA + 64 : jb.with_ones ? WG_COL_ONES + 32 : nmain;
       for (int c0 = 0; c0 < ncols; c0 += 32) {
-        if (c0 >= nmain && c0 < 256) continue;
+        if (c0 >= nmain && c0 < WG_COL_ONES) continue;
+        if (c0 >= WG_COL_ONES + 32 && c0 < WG_COL_EXTRA) continue;
+        if (c0 == WG_COL_ONES && !jb.with_ones) continue;
         uint32_t raw[32];
         tmem_ld32(t_lane + c0, raw);
         tmem_wait_ld();
@@ -716,6 +783,20 @@ __global__ void __launch_bounds__(WG_THREADS, 1) mlp_wgrad_kernel(const __grid_c
           }
         }
       }
+      if (jb.gh && quarter == 0) {     // G head: accumulator row = g channel (rows 0..15 live in lanes 0..15), column = B column
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t raw[32];
+          tmem_ld32(t_lane + WG_COL_EXTRA + c0, raw);
+          tmem_wait_ld();
+          for (int o = 0; o < jb.n_head; ++o) {
+            const WHead hd = jb.head[o];
+            if (lane < hd.ch_lo || lane >= hd.ch_hi) continue;
+            float* dst = prm.flat + hd.off + (lane - hd.ch_lo) * 256 + sg.cls * 128 + c0;
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) atomicAdd(dst + jj, __uint_as_float(raw[jj]));
+          }
+        }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_free);
@@ -726,7 +807,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) mlp_wgrad_kernel(const __grid_c
   if (warp == WG_PRODUCERS) { __syncwarp(); tmem_dealloc(tmem_base, 512); }
 }
 
-// the 21 GEMMs of one network's weight gradient (freeze = 0), or the 2-3 that remain in the freeze modes
+// the 17 jobs of one network's weight gradient (freeze = 0; 21 GEMMs, four of them riding on a job that streams
+// their operand anyway), or the 2 that remain in the freeze modes
 // (1: freeze_radiance, 2: freeze_radiance + freeze_roughness)
 static WgradParams make_wgrad_jobs(int freeze) {
   WgradParams P;
@@ -738,6 +820,14 @@ static WgradParams make_wgrad_jobs(int freeze) {
     j.with_ones = with_ones; j.n_out = 0; j.a_noswz = 0;
     j.cost = (2 + nb) * (m_halves == 2 ? 2 : 1);
     return j;
+  };
+  // the encoding block that completes this job's layer input rides along as a fifth B block
+  auto add_extra = [&](WJob& j, int x_sv, int x_blk) { j.xb = 1; j.x_sv = x_sv; j.x_blk = x_blk; j.cost = wg_stage_blocks(j) * 2; };
+  // a small head that reads this job's B operand: rows [ch_lo, ch_hi) of G^T B
+  auto add_head = [&](WJob& j, int off, int ch_lo, int ch_hi) {
+    j.gh = 1; j.cost = wg_stage_blocks(j) * 2;
+    WHead& h = j.head[j.n_head++];
+    h.off = off; h.ch_lo = ch_lo; h.ch_hi = ch_hi;
   };
   auto add_out = [&](WJob& j, int off, int m_lo, int m_hi, int n_lo, int n_hi, int stride_m, int stride_n) {
     WOut& o = j.out[j.n_out++];
@@ -751,6 +841,7 @@ static WgradParams make_wgrad_jobs(int freeze) {
       add_out(p, fo.w[14], 128, 256, 0, 256, 256, 1);
       add_out(p, fo.b[11], 0, 128, 256, 257, 1, 0);
       add_out(p, fo.b[14], 128, 256, 256, 257, 1, 0);
+      if (freeze == 1) add_head(p, fo.w[13], 4, 5);   // roughness head from h7
     }
     {   // albedo / irradiance heads from AF
       WJob& p = job(SVR, SV_AF, 2, DYR, DY_G, 1, 64, 0);
@@ -758,30 +849,31 @@ static WgradParams make_wgrad_jobs(int freeze) {
       add_out(p, fo.w[12], 0, 128, 1, 4, 1, 128);
       add_out(p, fo.w[15], 128, 256, 5, 6, 1, 0);
     }
-    if (freeze == 1) {   // roughness head from h7
-      WJob& p = job(SVR, SV_H(7), 2, DYR, DY_G, 1, 64, 0);
-      add_out(p, fo.w[13], 0, 256, 4, 5, 1, 0);
-    }
     return P;
   }
   // trunk layers: dW_l = dY_l^T X_l (+ bias through the ones column)
   for (int l = 0; l < 8; ++l) {
     const int ld = l == 0 ? 63 : (l == 5 ? 319 : 256);
-    if (l == 0 || l == 5) {   // positional-encoding part (63 valid of 64 columns)
-      WJob& p = job(DYR, DY_H(l), 2, SVR, SV_PE, 1, 64, l == 0);
+    if (l == 0) {   // positional encoding (63 valid of 64 columns)
+      WJob& p = job(DYR, DY_H(l), 2, SVR, SV_PE, 1, 64, 1);
       add_out(p, fo.w[l], 0, 256, 0, 63, ld, 1);
-      if (l == 0) add_out(p, fo.b[l], 0, 256, 256, 257, 1, 0);
-    }
-    if (l > 0) {
+      add_out(p, fo.b[l], 0, 256, 256, 257, 1, 0);
+    } else {
       WJob& p = job(DYR, DY_H(l), 2, SVR, SV_H(l - 1), 4, 256, 1);
       add_out(p, fo.w[l] + (l == 5 ? 63 : 0), 0, 256, 0, 256, ld, 1);
       add_out(p, fo.b[l], 0, 256, 256, 257, 1, 0);
+      if (l == 5) {   // skip layer: input = [encoding | h4]
+        add_extra(p, SVR, SV_PE);
+        add_out(p, fo.w[l], 0, 256, WG_COL_EXTRA, WG_COL_EXTRA + 63, ld, 1);
+      }
     }
   }
   {   // feature_linear: dY_feat x h7
     WJob& p = job(DYR, DY_FEAT, 2, SVR, SV_H(7), 4, 256, 1);
     add_out(p, fo.w[9], 0, 256, 0, 256, 256, 1);
     add_out(p, fo.b[9], 0, 256, 256, 257, 1, 0);
+    add_head(p, fo.w[10], 0, 1);      // sigma / roughness heads from h7
+    add_head(p, fo.w[13], 4, 5);
   }
   {   // albedo / irradiance feature linears: dY_af x h7 (rows 0..127 albedo_f, 128..255 irradiance_f)
     WJob& p = job(DYR, DY_AF, 2, SVR, SV_H(7), 4, 256, 1);
@@ -794,8 +886,8 @@ static WgradParams make_wgrad_jobs(int freeze) {
     WJob& p = job(DYR, DY_VIEW, 2, SVR, SV_FEAT, 4, 256, 1);
     add_out(p, fo.w[8], 0, 256, 0, 256, 283, 1);
     add_out(p, fo.b[8], 0, 256, 256, 257, 1, 0);
-    WJob& q = job(DYR, DY_VIEW, 2, SVR, SV_DE, 1, 64, 0);   // columns 27.. of the tile are unused
-    add_out(q, fo.w[8] + 256, 0, 256, 0, 27, 283, 1);
+    add_extra(p, SVR, SV_DE);                                  // columns 27.. of the encoding tile are unused
+    add_out(p, fo.w[8] + 256, 0, 256, WG_COL_EXTRA, WG_COL_EXTRA + 27, 283, 1);
   }
   {   // coarse-radiance feature linears: dY_addf x hv
     WJob& p = job(DYR, DY_ADDF01, 2, SVR, SV_HV, 4, 256, 1);
@@ -803,25 +895,17 @@ static WgradParams make_wgrad_jobs(int freeze) {
     add_out(p, fo.w[18], 128, 256, 0, 256, 256, 1);
     add_out(p, fo.b[17], 0, 128, 256, 257, 1, 0);
     add_out(p, fo.b[18], 128, 256, 256, 257, 1, 0);
+    add_head(p, fo.w[16], 6, 9);      // radiance head from hv
     WJob& q = job(DYR, DY_ADDF2, 1, SVR, SV_HV, 4, 256, 1);
     add_out(q, fo.w[19], 0, 128, 0, 256, 256, 1);
     add_out(q, fo.b[19], 0, 128, 256, 257, 1, 0);
   }
   // small heads: D[feature col][g channel] = X^T G
-  {   // sigma / roughness from h7
-    WJob& p = job(SVR, SV_H(7), 2, DYR, DY_G, 1, 64, 0);
-    add_out(p, fo.w[10], 0, 256, 0, 1, 1, 0);
-    add_out(p, fo.w[13], 0, 256, 4, 5, 1, 0);
-  }
   {   // albedo (cols 0..127 x channels 1..3) / irradiance (cols 128..255 x channel 5) from AF
     WJob& p = job(SVR, SV_AF, 2, DYR, DY_G, 1, 64, 0);
     p.a_noswz = 1;
     add_out(p, fo.w[12], 0, 128, 1, 4, 1, 128);
     add_out(p, fo.w[15], 128, 256, 5, 6, 1, 0);
-  }
-  {   // radiance from hv
-    WJob& p = job(SVR, SV_HV, 2, DYR, DY_G, 1, 64, 0);
-    add_out(p, fo.w[16], 0, 256, 6, 9, 1, 256);
   }
   for (int k = 0; k < 3; ++k) {   // coarse radiance heads from ADDF block pair k
     WJob& p = job(SVR, SV_ADDF + 2 * k, 1, DYR, DY_G, 1, 64, 0);
