@@ -14,7 +14,7 @@ for n, steps in ((4096, 300), (4097, 20), (1000, 20), (333, 20), (1, 5), (9001, 
     o = (torch.rand(n, 3, generator=g) * 2 - 1).to(dev)
     d = torch.randn(n, 3, generator=g); d = (d / d.norm(dim=-1, keepdim=True) * 1.1).to(dev)
     tg = {k: torch.rand(n, 3, generator=g).to(dev) for k in ("rgb", "rgb_1", "rgb_2", "rgb_3")}
-    losses = [ts.step(o, d, tg) for _ in range(steps)]
+    losses = [ts.step(o, d, tg).clone() for _ in range(steps)]      # the fused route returns a view of its loss slot
     torch.cuda.synchronize()
     l = torch.stack(losses).cpu()
     assert torch.isfinite(l).all(), (n, l)
