@@ -145,7 +145,8 @@ class IBLNeRF(nn.Module):
 
     def packed_weights(self):
         """bf16 chunk stream for the tensor-core kernel; re-packed whenever a parameter changed
-        (optimizer.step() bumps the tensors' version counters)."""
+        (optimizer.step() bumps the tensors' version counters; torch's `fused=True` optimizers do not, see
+        _bump_versions_after_fused_step below)."""
         ps = self.ordered_params()
         key = tuple((p.data_ptr(), p._version) for p in ps)
         if self._packed is None or self._packed_key != key or self._packed.device != ps[0].device:
@@ -298,3 +299,20 @@ class NetworkQuery:
 
     def __call__(self, inputs, viewdirs, network_fn):
         return run_network(inputs, viewdirs, network_fn, self.embed_fn, self.embeddirs_fn, self.netchunk)
+
+
+def _bump_versions_after_fused_step(optimizer, args, kwargs):
+    """torch's fused optimizer kernels (`torch.optim.Adam(..., fused=True)` and friends) update the parameters without
+    bumping their version counters (measured: `_version` stays 0 across `step()`), and the version counters are what
+    IBLNeRF.packed_weights() watches -- a network trained that way would keep querying its first packed image.  A
+    process-wide optimizer post-step hook bumps them for every fused parameter group; it costs no kernel launch."""
+    for group in optimizer.param_groups:
+        if group.get("fused"):
+            touched = [p for p in group["params"] if p.grad is not None]
+            if touched:
+                torch.autograd.graph.increment_version(touched)
+
+
+from torch.optim.optimizer import register_optimizer_step_post_hook as _register_post_hook  # noqa: E402
+
+_register_post_hook(_bump_versions_after_fused_step)

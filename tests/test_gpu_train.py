@@ -260,3 +260,39 @@ def test_device_sample_generator_yields_the_reference_tuple():
     gen = sampling.sample_generator_single_image(ds, batch_size=256, precrop_iters=0)
     out = next(gen)
     assert len(out) == 6 and out[1].shape == (256, 3) and out[3] == {} and out[4] is None and out[0]["rgb"].shape == (256, 3)
+
+
+@pytest.mark.gpu
+def test_use_fused_adam_keeps_the_update_and_drops_the_syncs():
+    """factory.use_fused_adam: same torch.optim.Adam object, same update as the default implementation, `step`
+    counters on the device (the drivers' CUDA default tensor type makes the default implementation read them back
+    with .item() per parameter), counters restored from a checkpoint moved along."""
+    from ibl_nerf_b200 import factory
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    a = [torch.randn(7, 5, device=dev, requires_grad=True), torch.randn(11, device=dev, requires_grad=True)]
+    b = [p.detach().clone().requires_grad_(True) for p in a]
+    ref = torch.optim.Adam(params=a, lr=5e-4, betas=(0.9, 0.999))
+    opt = torch.optim.Adam(params=[{"params": b, "name": "nerf"}], lr=5e-4, betas=(0.9, 0.999))
+    assert factory.use_fused_adam(opt) is opt and opt.param_groups[0]["fused"] is True
+    for it in range(5):
+        for pa, pb in zip(a, b):
+            g = torch.randn_like(pa)
+            pa.grad, pb.grad = g.clone(), g.clone()
+        for grp in opt.param_groups:               # train.py:483-498 writes the decayed rate into the groups
+            grp["lr"] = 5e-4 * 0.9 ** it
+        for grp in ref.param_groups:
+            grp["lr"] = 5e-4 * 0.9 ** it
+        ref.step(); opt.step()
+    for pa, pb in zip(a, b):
+        assert torch.allclose(pa, pb, rtol=1e-5, atol=1e-7)
+    assert all(st["step"].is_cuda for st in opt.state.values())
+    # a checkpoint written by the default implementation (CPU counters) loads and keeps stepping
+    sd = ref.state_dict()
+    opt2 = torch.optim.Adam(params=[p.detach().clone().requires_grad_(True) for p in a], lr=5e-4)
+    opt2.load_state_dict(sd)
+    factory.use_fused_adam(opt2)
+    for p in opt2.param_groups[0]["params"]:
+        p.grad = torch.ones_like(p)
+    opt2.step()
+    assert all(float(st["step"]) == 6.0 for st in opt2.state.values())

@@ -110,3 +110,20 @@ def test_sample_generator_crop_window():
     assert sampling.crop_window(480, 640, 0, 500, 0.5) == (160, 480, 120, 360)
     assert sampling.crop_window(480, 640, 500, 500, 0.5) == (0, 640, 0, 480)
     assert sampling.crop_window(480, 640, 10, 0, 0.5, "patch") == (1, 639, 1, 479)
+
+
+def test_fused_optimizers_bump_parameter_versions():
+    """IBLNeRF.packed_weights() re-packs when a parameter's version counter moved; torch's fused optimizer kernels do
+    not move it, so importing the package installs a post-step hook that does (model._bump_versions_after_fused_step)."""
+    import torch
+    import ibl_nerf_b200.model  # noqa: installs the hook
+    p = [torch.randn(5, requires_grad=True), torch.randn(3, requires_grad=True)]
+    try:
+        opt = torch.optim.Adam(p, lr=1e-3, fused=True)
+    except RuntimeError:
+        import pytest
+        pytest.skip("fused Adam unavailable on CPU in this torch build")
+    p[0].grad = torch.ones(5)          # p[1] has no gradient: untouched by the step, version unchanged
+    v0, v1 = p[0]._version, p[1]._version
+    opt.step()
+    assert p[0]._version > v0 and p[1]._version == v1
